@@ -1,0 +1,155 @@
+/* orb_b200.h -- C ABI of the B200-native ORB extractor (the only layer that touches CUDA).
+ *
+ * This is the drop-in boundary for the reference's hand-written ORB path
+ * (WeeFav/Visual-Odometry-GPU).  Every entry point below names the reference interface it
+ * replaces (file:line relative to the reference tree).  The reference crosses from C++ into
+ * .cu files with cv::Mat / std::vector (include/Fast.cuh:5-6, include/Brief.cuh:5,
+ * include/HarrisScore.cuh:5, include/NMS.cuh:5); here that seam is plain pointers and sizes,
+ * so the C++ facade (include/orb.hpp in this repo), ctypes, cgo or JNI can all bind it.
+ *
+ * Conventions
+ *  - all functions return ORB_OK (0) or a negative orb_status; no exit(), no exceptions
+ *    (the reference's cudaCheckErrors macro prints and exit(1)s, src/cuda/Fast.cu:8-18);
+ *  - images are 8-bit single channel, row-major, `pitch` bytes between rows (cv::Mat::step);
+ *  - a context owns every device allocation (arena sized at create from max_* fields),
+ *    its stream and its resize tables; nothing is allocated on the hot path
+ *    (the reference cudaMallocs per call and never frees);
+ *  - a context is not thread-safe; distinct contexts are independent (one per device/thread);
+ *  - there is NO CPU fallback: without a CUDA device orb_create fails with ORB_E_CUDA.
+ */
+#ifndef ORB_B200_H
+#define ORB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORB_B200_ABI_VERSION 1
+
+/* == Keypoint, reference include/orb.hpp:4 (x = column, y = row, level-0 coordinates) */
+typedef struct { int32_t x, y; } orb_keypoint;
+/* == ORBDescriptor, reference include/orb.hpp:6-8; bit i lives at data[i>>3] bit (i&7) */
+typedef struct { uint8_t data[32]; } orb_descriptor;
+
+typedef enum {
+  ORB_OK = 0,
+  ORB_E_INVALID = -1,      /* bad argument / unsupported parameter value          */
+  ORB_E_CUDA = -2,         /* CUDA runtime error (see orb_last_error)             */
+  ORB_E_CAPACITY = -3,     /* image / batch larger than the context was built for */
+  ORB_E_OVERFLOW = -4,     /* more corner candidates than the arena holds         */
+  ORB_E_NOMEM = -5
+} orb_status;
+
+/* selection policy for the per-level keypoint cap */
+#define ORB_SELECT_RASTER_FIRST_N 0 /* first N NMS survivors in raster order: reference src/orb_cpu.cpp:110 */
+#define ORB_SELECT_HARRIS_TOP_N   1 /* top quota_l by Harris response:       reference src/orb.cpp:62-86    */
+
+typedef struct {
+  /* ORB ctor, reference include/orb.hpp:36 */
+  int32_t nfeatures;        /* total keypoint budget (per frame)                           */
+  float   scale_factor;     /* pyramid scale, 1.2f                                         */
+  int32_t nlevels;          /* pyramid levels, 8                                           */
+  /* OrientedFAST ctor, reference include/orb.hpp:12 / include/orb_cpu.hpp:6 */
+  int32_t fast_threshold;   /* 20 (orb.hpp) or 50 (orb_cpu.hpp)                            */
+  int32_t fast_n;           /* contiguous arc length, 9                                    */
+  int32_t nms_window;       /* 3 (radius 1); 1 disables NMS                                */
+  int32_t orient_patch;     /* 31 (orb.hpp) or 9 (orb_cpu.hpp)                             */
+  int32_t select_policy;    /* ORB_SELECT_*                                                */
+  int32_t blur_levels;      /* 1: resize+GaussianBlur5x5 (src/orb_cpu.cpp:288-289); 0: resize only (src/orb.cpp:119) */
+  float   harris_k;         /* 0.04f (intended value at src/orb.cpp:65)                    */
+  /* device / capacity (no reference counterpart: the reference allocates per call) */
+  int32_t device;           /* CUDA device ordinal                                         */
+  int32_t max_width, max_height;
+  int32_t max_batch;        /* frames per orb_detect_and_compute_batch call                */
+  int32_t chunk_frames;     /* frames processed per kernel wave (scratch kept L2-resident); 0 = auto */
+  int32_t max_keypoints;    /* output slots per frame (>= what selection can return); 0 = nfeatures   */
+  int32_t reserved[4];
+} orb_params;
+
+typedef struct orb_ctx orb_ctx;
+
+/* fills *p with the reference defaults of include/orb.hpp (500 / 1.2f / 8, thr 20, n 9, nms 3,
+ * patch 31), HARRIS_TOP_N, blurred pyramid, k = 0.04f, 1241x376, batch 1. */
+void orb_default_params(orb_params* p);
+
+/* replaces: ORB::ORB + OrientedFAST::OrientedFAST + RotatedBRIEF::RotatedBRIEF
+ * (reference src/orb.cpp:9-20,35-38,46-56) and every per-call cudaMalloc below them. */
+int  orb_create(const orb_params* p, orb_ctx** out);
+void orb_destroy(orb_ctx* ctx);
+const char* orb_last_error(const orb_ctx* ctx);   /* ctx may be NULL: error of the failed orb_create */
+int  orb_abi_version(void);
+
+/* run the context's work on a caller-provided cudaStream_t (passed as void*); NULL = the
+ * context's own stream.  Lets a host framework time the kernels with events on its stream. */
+int  orb_set_stream(orb_ctx* ctx, void* cuda_stream);
+
+/* replaces: ORB::detectAndCompute (reference include/orb.hpp:37, src/orb.cpp:58-109; CPU twin
+ * ORBCPU::detectAndCompute include/orb_cpu.hpp:31, src/orb_cpu.cpp:271-276).
+ * img is a HOST pointer.  Writes at most `cap` records, levels concatenated 0..L-1, each level
+ * in raster order.  n_per_level may be NULL (else nlevels ints).  Synchronous. */
+int  orb_detect_and_compute(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch,
+                            int cap, orb_keypoint* kps, float* angles, orb_descriptor* desc,
+                            int* n_out, int* n_per_level);
+
+/* batch form of the same call: n_frames images of identical shape.
+ *  frames_on_device = 0: host frames are copied in; 1: `frames` is a device pointer.
+ *  outputs_on_device = 0: kps/angles/desc/n_out are host buffers ([n_frames][cap] records,
+ *  n_out[n_frames]); 1: they are device buffers and the call returns without synchronising.
+ * Frames are independent (reference src/orb.cpp:58-109 keeps no state between calls). */
+int  orb_detect_and_compute_batch(orb_ctx* ctx, const uint8_t* frames, int frames_on_device,
+                                  int n_frames, int w, int h, size_t pitch, size_t frame_stride,
+                                  int cap, orb_keypoint* kps, float* angles, orb_descriptor* desc,
+                                  int* n_out, int outputs_on_device);
+
+/* ---- stage entry points (one image, host pointers, synchronous) ---------------------------
+ * They exist so that the facade's per-stage methods and the parity tests can exercise each
+ * kernel against the matching oracle stage. */
+
+/* replaces: ORBCPU::buildPyramid / ORB::buildPyramid (reference src/orb_cpu.cpp:278-290,
+ * src/orb.cpp:111-120).  Pyramid pixels of `level` of frame `frame` of the LAST batch call. */
+int  orb_get_level(orb_ctx* ctx, int frame, int level, uint8_t* dst, size_t dst_pitch, int* w, int* h);
+/* level geometry and per-level quota (reference src/orb_cpu.cpp:284-285, src/orb.cpp:62) */
+int  orb_level_size(const orb_ctx* ctx, int w, int h, int level, int* lw, int* lh);
+int  orb_level_quota(const orb_ctx* ctx, int level);
+
+/* replaces: Fast() + d_NMS (reference include/Fast.cuh:5, src/cuda/Fast.cu:211-270,
+ * src/cuda/NMS.cu:21-128) == OrientedFASTCPU::detect (src/orb_cpu.cpp:23-137).
+ * FAST-n segment test, SAD score, 3x3 NMS; first `nfeatures` survivors in raster order. */
+int  orb_fast_detect(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch,
+                     int nfeatures, orb_keypoint* kps, int* n_out);
+/* replaces: HarrisScore() (reference include/HarrisScore.cuh:5, src/cuda/HarrisScore.cu:42-89) */
+int  orb_harris(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch,
+                const orb_keypoint* kps, int n, float* response);
+/* replaces: Orientations() (reference include/Fast.cuh:6, src/cuda/Orientations.cu:65-100)
+ * == OrientedFASTCPU::compute_orientations (src/orb_cpu.cpp:139-183) */
+int  orb_orientations(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch,
+                      const orb_keypoint* kps, int n, float* angles);
+/* replaces: Brief() (reference include/Brief.cuh:5, src/cuda/Brief.cu:97-137)
+ * == RotatedBRIEFCPU::compute (src/orb_cpu.cpp:203-258) */
+int  orb_brief(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch,
+               const orb_keypoint* kps, const float* angles, int n, orb_descriptor* desc);
+
+/* ---- side arrays of the LAST orb_detect_and_compute[_batch] call (testing / diagnostics) ----
+ * level-space coordinates, level id and Harris response of output record i of `frame`
+ * (the reference drops them, src/orb.cpp:94-102).  Any pointer may be NULL. */
+int  orb_get_side_arrays(orb_ctx* ctx, int frame, int n, orb_keypoint* level_xy,
+                         int32_t* level_id, float* response);
+/* all NMS survivors of (frame, level) of the last call, unordered: coordinates + response */
+int  orb_get_candidates(orb_ctx* ctx, int frame, int level, int cap, orb_keypoint* xy,
+                        float* response, int* n_out);
+/* the 49 Harris window weights the context uses (createGaussianKernel(7), reference
+ * src/GaussianBlur.cpp:7-37) */
+int  orb_get_harris_weights(const orb_ctx* ctx, float* w49);
+/* number of kernel launches issued by the last detect call (for bench accounting) */
+int  orb_last_launch_count(const orb_ctx* ctx);
+
+/* == extern int bit_pattern_31_[256*4], reference include/orb_pattern.hpp:2 */
+extern int bit_pattern_31_[256 * 4];
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORB_B200_H */
