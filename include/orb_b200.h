@@ -66,7 +66,8 @@ typedef struct {
   int32_t max_batch;        /* frames per orb_detect_and_compute_batch call                */
   int32_t chunk_frames;     /* frames processed per kernel wave (scratch kept L2-resident); 0 = auto */
   int32_t max_keypoints;    /* output slots per frame (>= what selection can return); 0 = nfeatures   */
-  int32_t reserved[4];
+  int32_t keep_side_arrays; /* 1: also record level-space xy / level id / response per output (diagnostics) */
+  int32_t reserved[3];
 } orb_params;
 
 typedef struct orb_ctx orb_ctx;
@@ -143,6 +144,12 @@ int  orb_get_candidates(orb_ctx* ctx, int frame, int level, int cap, orb_keypoin
 /* the 49 Harris window weights the context uses (createGaussianKernel(7), reference
  * src/GaussianBlur.cpp:7-37) */
 int  orb_get_harris_weights(const orb_ctx* ctx, float* w49);
+/* wait for the context's stream and report deferred errors (candidate overflow) of calls made with
+ * outputs_on_device = 1 */
+int  orb_synchronize(orb_ctx* ctx);
+/* libm twins used on the device, evaluated on host arrays (test hook): op 0 atan2f(a,b), 1 cosf(a),
+ * 2 sinf(a), 3 lround(a) -- the glibc calls of reference src/orb_cpu.cpp:178,217-218,228-232 */
+int  orb_debug_eval_math(orb_ctx* ctx, int op, const float* a, const float* b, int n, float* out);
 /* number of kernel launches issued by the last detect call (for bench accounting) */
 int  orb_last_launch_count(const orb_ctx* ctx);
 

@@ -1,0 +1,654 @@
+// orb_api.cu -- host side of the C ABI declared in include/orb_b200.h.
+// Owns the device arena, the per-shape plan (level geometry, quotas, resize tap tables) and the
+// launch sequence.  No CPU compute path exists here: every result comes from the kernels in
+// orb_kernels.cuh.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/orb_b200.h"
+#include "../../include/orb_brief_pattern.h"
+#include "orb_kernels.cuh"
+#include "orb_plan.h"
+
+using orbk::Bufs;
+using orbk::DescribeJob;
+
+#ifndef ORB_TILE_W
+#define ORB_TILE_W 128
+#endif
+#ifndef ORB_TILE_H
+#define ORB_TILE_H 64
+#endif
+typedef orbk::Tile<ORB_TILE_W, ORB_TILE_H> TileT;
+
+// == extern int bit_pattern_31_[256*4] of the reference (include/orb_pattern.hpp:2)
+extern "C" { int bit_pattern_31_[256 * 4]; }
+namespace {
+struct PatternInit {
+  PatternInit() { for (int i = 0; i < 1024; i++) bit_pattern_31_[i] = ORB_BRIEF_PATTERN_31[i]; }
+} g_pattern_init;
+char g_create_error[512] = "";
+}  // namespace
+
+struct orb_ctx {
+  orb_params p;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  char err[512];
+  int chunk = 1, max_kp = 0;
+  // plan of the last shape + arena limits (plan of the max shape)
+  OrbPlan plan, max_plan;
+  bool plan_valid = false;
+  int xtab_cap = 0, ytab_cap = 0;
+  // arena
+  uint8_t* d_frames = nullptr; size_t frames_slot_bytes = 0; int frames_pitch = 0;
+  uint8_t* d_pyr = nullptr; uint16_t* d_box = nullptr; unsigned long long* d_cand = nullptr;
+  int* d_cand_count = nullptr; uint32_t* d_kept_xy = nullptr; float* d_kept_r = nullptr; int* d_kept_count = nullptr;
+  OrbTap *d_xtab = nullptr, *d_ytab = nullptr;
+  float* d_harris_w = nullptr; char4* d_pattern = nullptr; int* d_flags = nullptr; int* h_flags = nullptr;
+  orb_keypoint* d_kps = nullptr; float* d_angles = nullptr; orb_descriptor* d_desc = nullptr; int* d_nout = nullptr;
+  orb_keypoint* d_side_xy = nullptr; int* d_side_level = nullptr; float* d_side_resp = nullptr;
+  orb_keypoint* d_list_kps = nullptr; float* d_list_angles = nullptr; float* d_list_out = nullptr; int list_cap = 0;
+  float harris_w[49];
+  // last detect call (for the read-back entry points)
+  int last_n = 0, last_chunk_start = 0, last_chunk_n = 0, last_cap = 0;
+  const uint8_t* last_frames = nullptr; size_t last_stride = 0; int last_pitch = 0;
+  bool last_outputs_ctx = false;
+  int launches = 0;
+};
+
+namespace {
+
+int fail(orb_ctx* c, int code, const char* fmt, ...) {
+  char* dst = c ? c->err : g_create_error;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return fail(ctx, ORB_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                                       __FILE__, __LINE__);                                              \
+  } while (0)
+
+inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// float scale = pow(scaleFactor, i);   ref src/orb_cpu.cpp:284 / src/orb.cpp:95
+float level_scale(float f, int l) { return (float)std::pow((double)f, (double)l); }
+void level_size(int W, int H, float f, int l, int* w, int* h) {
+  if (l == 0) { *w = W; *h = H; return; }
+  float s = level_scale(f, l);
+  *w = (int)std::round(W / s);   // cv::Size(round(W / scale), round(H / scale)), ref src/orb_cpu.cpp:285
+  *h = (int)std::round(H / s);
+}
+// int nfeatures_l = nfeatures * ((1 - 1/f) / (1 - pow(1/f, L))) * pow(1/f, l);   ref src/orb.cpp:62
+int level_quota(int nfeatures, float f, int L, int l) {
+  float inv = 1 / f;
+  double a = (1 - inv) / (1 - std::pow((double)inv, (double)L));
+  return (int)(nfeatures * a * std::pow((double)inv, (double)l));
+}
+
+// cv::resize(INTER_LINEAR) tap table for one axis (OpenCV's float recipe, 11-bit coefficients)
+void make_taps(int src, int dst, OrbTap* t) {
+  double scale = 1.0 / ((double)dst / src);
+  for (int d = 0; d < dst; d++) {
+    float fx = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)std::floor(fx);
+    fx -= s;
+    if (s < 0) { s = 0; fx = 0.f; }
+    if (s >= src - 1) { s = src - 1; fx = 0.f; }
+    t[d].s0 = (uint16_t)s;
+    t[d].s1 = (uint16_t)std::min(s + 1, src - 1);
+    t[d].a0 = (int16_t)std::lrintf((1.f - fx) * 2048.f);
+    t[d].a1 = (int16_t)std::lrintf(fx * 2048.f);
+  }
+}
+
+// createGaussianKernel(7), ref src/GaussianBlur.cpp:7-37 (float arithmetic, sigma heuristic)
+void harris_weights(float* k) {
+  const int ks = 7, half = 3;
+  float sigma = 0.3f * ((ks - 1) * 0.5f) + 0.8f, sum = 0.0f;
+  for (int y = -half; y <= half; ++y)
+    for (int x = -half; x <= half; ++x) {
+      float v = std::exp(-(x * x + y * y) / (2 * sigma * sigma));
+      k[(y + half) * ks + (x + half)] = v;
+      sum += v;
+    }
+  for (int i = 0; i < ks * ks; ++i) k[i] /= sum;
+}
+
+// geometry of one frame shape; nlevels/policy/quota may be overridden for the single-image stages
+void build_plan(const orb_params& p, int W, int H, int nlevels, int policy, int quota_override, OrbPlan* P) {
+  memset(P, 0, sizeof(*P));
+  P->nlevels = nlevels; P->W = W; P->H = H;
+  P->fast_threshold = p.fast_threshold; P->fast_n = p.fast_n;
+  P->nms_radius = p.nms_window / 2; P->patch_radius = p.orient_patch / 2;
+  P->select_policy = policy; P->blur_levels = p.blur_levels; P->harris_k = p.harris_k;
+  int tile = 0, kept = 0, xo = 0, yo = 0;
+  unsigned long long lv = 0, bx = 0, cd = 0;
+  for (int l = 0; l < nlevels; l++) {
+    OrbLevel& G = P->lv[l];
+    level_size(W, H, p.scale_factor, l, &G.w, &G.h);
+    G.w = std::max(G.w, 1); G.h = std::max(G.h, 1);
+    G.pitch = align_up(G.w, 16);
+    G.bpitch = align_up(G.w + 1, 8);
+    G.tiles_x = (G.w + TileT::TW - 1) / TileT::TW;
+    G.tiles_y = (G.h + TileT::TH - 1) / TileT::TH;
+    G.tile_ofs = tile; tile += G.tiles_x * G.tiles_y;
+    int q = quota_override >= 0 ? quota_override
+            : (policy == ORB_SELECT_HARRIS_TOP_N ? level_quota(p.nfeatures, p.scale_factor, p.nlevels, l) : p.nfeatures);
+    G.quota = std::max(0, std::min(q, ORB_SORT_CAP));
+    G.cand_cap = std::max(2048, G.w * G.h / 8);
+    G.kept_ofs = kept; kept += align_up(std::max(G.quota, 1), 4);
+    G.xtab_ofs = xo; G.ytab_ofs = yo; xo += G.w; yo += G.h;
+    G.scale = level_scale(p.scale_factor, l);
+    G.lvl_ofs = lv; if (l > 0) lv += (unsigned long long)align_up(G.h * G.pitch, 256);
+    G.box_ofs = bx; bx += (unsigned long long)align_up((G.h + 1) * G.bpitch, 128);
+    G.cand_ofs = cd; cd += (unsigned long long)align_up(G.cand_cap, 32);
+  }
+  P->tiles_per_frame = tile; P->kept_per_frame = kept;
+  P->pyr_frame_bytes = std::max<unsigned long long>(lv, 256); P->box_frame_elems = bx; P->cand_frame_elems = cd;
+}
+
+int upload_tables(orb_ctx* ctx, const OrbPlan& P) {
+  std::vector<OrbTap> xt, yt;
+  for (int l = 0; l < P.nlevels; l++) {
+    const OrbLevel& G = P.lv[l];
+    xt.resize(G.xtab_ofs + G.w); yt.resize(G.ytab_ofs + G.h);
+    make_taps(P.W, G.w, xt.data() + G.xtab_ofs);
+    make_taps(P.H, G.h, yt.data() + G.ytab_ofs);
+  }
+  if ((int)xt.size() > ctx->xtab_cap || (int)yt.size() > ctx->ytab_cap) return fail(ctx, ORB_E_CAPACITY, "tap tables exceed arena");
+  CK(cudaMemcpyAsync(ctx->d_xtab, xt.data(), xt.size() * sizeof(OrbTap), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_ytab, yt.data(), yt.size() * sizeof(OrbTap), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));   // host vectors die here
+  return ORB_OK;
+}
+
+int get_plan(orb_ctx* ctx, int w, int h) {
+  if (w < 1 || h < 1) return fail(ctx, ORB_E_INVALID, "bad image size %dx%d", w, h);
+  if (w > ctx->p.max_width || h > ctx->p.max_height)
+    return fail(ctx, ORB_E_CAPACITY, "image %dx%d exceeds context capacity %dx%d", w, h, ctx->p.max_width, ctx->p.max_height);
+  if (ctx->plan_valid && ctx->plan.W == w && ctx->plan.H == h) return ORB_OK;
+  build_plan(ctx->p, w, h, ctx->p.nlevels, ctx->p.select_policy, -1, &ctx->plan);
+  ctx->plan_valid = false;
+  int rc = upload_tables(ctx, ctx->plan);
+  if (rc) return rc;
+  ctx->plan_valid = true;
+  return ORB_OK;
+}
+
+void fill_bufs(orb_ctx* ctx, Bufs* B) {
+  memset(B, 0, sizeof(*B));
+  B->pyr = ctx->d_pyr; B->box = ctx->d_box; B->cand = ctx->d_cand; B->cand_count = ctx->d_cand_count;
+  B->kept_xy = ctx->d_kept_xy; B->kept_r = ctx->d_kept_r; B->kept_count = ctx->d_kept_count;
+  B->xtab = ctx->d_xtab; B->ytab = ctx->d_ytab; B->harris_w = ctx->d_harris_w; B->pattern = ctx->d_pattern;
+  B->flags = ctx->d_flags;
+}
+
+int launch_pyramid_fast(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, int nframes) {
+  CK(cudaMemsetAsync(ctx->d_cand_count, 0, sizeof(int) * ORB_MAX_LEVELS * nframes, ctx->stream));
+  dim3 grid(P.tiles_per_frame, nframes);
+  orbk::k_pyramid_fast<TileT><<<grid, orbk::K1_THREADS, TileT::SMEM, ctx->stream>>>(P, B);
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  return ORB_OK;
+}
+int launch_select(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, int nframes) {
+  int mq = 1;
+  for (int l = 0; l < P.nlevels; l++) mq = std::max(mq, P.lv[l].quota);
+  int npow2 = 1;
+  while (npow2 < mq) npow2 <<= 1;
+  dim3 grid(P.nlevels, nframes);
+  orbk::k_select<<<grid, orbk::K2_THREADS, (size_t)npow2 * 8, ctx->stream>>>(P, B);
+  CK(cudaGetLastError());
+  ctx->launches += 1;
+  return ORB_OK;
+}
+int launch_describe(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, const DescribeJob& J, int nwarps, int nframes) {
+  if (nwarps <= 0) return ORB_OK;
+  dim3 grid((nwarps + orbk::K3_WARPS - 1) / orbk::K3_WARPS, nframes);
+  orbk::k_describe<<<grid, orbk::K3_WARPS * 32, 0, ctx->stream>>>(P, B, J);
+  CK(cudaGetLastError());
+  ctx->launches += 1;
+  return ORB_OK;
+}
+
+int check_flags(orb_ctx* ctx) {
+  CK(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (*ctx->h_flags & 1) {
+    CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
+    return fail(ctx, ORB_E_OVERFLOW, "corner candidates exceeded the per-level arena (w*h/8 slots)");
+  }
+  return ORB_OK;
+}
+
+// copy one host image into frame slot 0 of the staging area (single-image stage entry points)
+int stage_image(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch) {
+  if (!img || w < 1 || h < 1 || pitch < (size_t)w) return fail(ctx, ORB_E_INVALID, "bad image argument");
+  if (w > ctx->p.max_width || h > ctx->p.max_height)
+    return fail(ctx, ORB_E_CAPACITY, "image %dx%d exceeds context capacity %dx%d", w, h, ctx->p.max_width, ctx->p.max_height);
+  CK(cudaMemcpy2DAsync(ctx->d_frames, ctx->frames_pitch, img, pitch, w, h, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->last_n = 0;   // stage calls reuse slot 0 of the arena
+  return ORB_OK;
+}
+
+void stage_plan(orb_ctx* ctx, int w, int h, int policy, int quota, OrbPlan* P, Bufs* B) {
+  build_plan(ctx->p, w, h, 1, policy, quota, P);
+  P->lv[0].cand_cap = ctx->max_plan.lv[0].cand_cap;
+  fill_bufs(ctx, B);
+  B->frames = ctx->d_frames; B->frame_stride = ctx->frames_slot_bytes; B->pitch0 = ctx->frames_pitch;
+  B->out_kps = ctx->d_kps; B->out_angles = ctx->d_angles; B->out_desc = ctx->d_desc; B->out_n = ctx->d_nout;
+  B->out_cap = ctx->list_cap;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orb_abi_version(void) { return ORB_B200_ABI_VERSION; }
+
+void orb_default_params(orb_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->nfeatures = 500; p->scale_factor = 1.2f; p->nlevels = 8;            // ref include/orb.hpp:36
+  p->fast_threshold = 20; p->fast_n = 9; p->nms_window = 3; p->orient_patch = 31;   // ref include/orb.hpp:12
+  p->select_policy = ORB_SELECT_HARRIS_TOP_N; p->blur_levels = 1; p->harris_k = 0.04f;
+  p->device = 0; p->max_width = 1241; p->max_height = 376; p->max_batch = 1; p->chunk_frames = 0;
+  p->max_keypoints = 0; p->keep_side_arrays = 0;
+}
+
+const char* orb_last_error(const orb_ctx* ctx) { return ctx ? ctx->err : g_create_error; }
+
+void orb_destroy(orb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->p.device);
+  void* ptrs[] = {ctx->d_frames, ctx->d_pyr, ctx->d_box, ctx->d_cand, ctx->d_cand_count, ctx->d_kept_xy, ctx->d_kept_r,
+                  ctx->d_kept_count, ctx->d_xtab, ctx->d_ytab, ctx->d_harris_w, ctx->d_pattern, ctx->d_flags, ctx->d_kps,
+                  ctx->d_angles, ctx->d_desc, ctx->d_nout, ctx->d_side_xy, ctx->d_side_level, ctx->d_side_resp,
+                  ctx->d_list_kps, ctx->d_list_angles, ctx->d_list_out};
+  for (void* q : ptrs) if (q) cudaFree(q);
+  if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+int orb_create(const orb_params* p, orb_ctx** out) {
+  orb_ctx* ctx = nullptr;   // errors before allocation go to the global create-error string
+  if (!p || !out) return fail(ctx, ORB_E_INVALID, "null argument");
+  *out = nullptr;
+  if (p->nlevels < 1 || p->nlevels > ORB_MAX_LEVELS) return fail(ctx, ORB_E_INVALID, "nlevels must be 1..%d", ORB_MAX_LEVELS);
+  if (!(p->scale_factor > 1.0f) && p->nlevels > 1) return fail(ctx, ORB_E_INVALID, "scale_factor must be > 1");
+  if (p->fast_n < 1 || p->fast_n > 16) return fail(ctx, ORB_E_INVALID, "fast_n must be 1..16");
+  if (p->fast_threshold < 0 || p->fast_threshold > 255) return fail(ctx, ORB_E_INVALID, "fast_threshold must be 0..255");
+  if (p->nms_window != 1 && p->nms_window != 3 && p->nms_window != 0 && p->nms_window != 2)
+    return fail(ctx, ORB_E_INVALID, "nms_window must be 1 or 3 (radius 0 or 1)");
+  if (p->orient_patch < 1 || p->orient_patch > 63) return fail(ctx, ORB_E_INVALID, "orient_patch must be 1..63");
+  if (p->select_policy != ORB_SELECT_RASTER_FIRST_N && p->select_policy != ORB_SELECT_HARRIS_TOP_N)
+    return fail(ctx, ORB_E_INVALID, "unknown select_policy");
+  if (p->nfeatures < 1) return fail(ctx, ORB_E_INVALID, "nfeatures must be >= 1");
+  if (p->max_width < 1 || p->max_height < 1 || p->max_width > 65535 || p->max_height > 65535 || p->max_batch < 1)
+    return fail(ctx, ORB_E_INVALID, "bad capacity fields");
+  if ((p->select_policy == ORB_SELECT_RASTER_FIRST_N ? p->nfeatures : level_quota(p->nfeatures, p->scale_factor, p->nlevels, 0)) > ORB_SORT_CAP)
+    return fail(ctx, ORB_E_INVALID, "per-level keypoint budget exceeds %d", ORB_SORT_CAP);
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(ctx, ORB_E_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (p->device < 0 || p->device >= ndev) return fail(ctx, ORB_E_INVALID, "device %d out of range (%d devices)", p->device, ndev);
+
+  ctx = new orb_ctx();
+  ctx->p = *p;
+  ctx->err[0] = 0;
+  int rc = ORB_OK;
+  auto body = [&]() -> int {
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    build_plan(ctx->p, p->max_width, p->max_height, p->nlevels, p->select_policy, -1, &ctx->max_plan);
+    const OrbPlan& M = ctx->max_plan;
+    // single-image stages reuse slot 0 with a 1-level plan whose kept list may hold ORB_SORT_CAP entries
+    OrbPlan S;
+    build_plan(ctx->p, p->max_width, p->max_height, 1, ORB_SELECT_RASTER_FIRST_N, ORB_SORT_CAP, &S);
+    int kept_per_frame = std::max(M.kept_per_frame, S.kept_per_frame);
+    // outputs per frame
+    int total_quota = 0;
+    for (int l = 0; l < M.nlevels; l++) total_quota += M.lv[l].quota;
+    ctx->max_kp = p->max_keypoints > 0 ? p->max_keypoints : total_quota;
+    // chunking: keep one chunk's scratch (levels + box sums) well inside the 126 MB L2
+    size_t per_frame = (size_t)M.pyr_frame_bytes + (size_t)M.box_frame_elems * 2 + (size_t)p->max_width * p->max_height;
+    int chunk = p->chunk_frames > 0 ? p->chunk_frames : (int)std::max<size_t>(1, ((size_t)64 << 20) / per_frame);
+    ctx->chunk = std::max(1, std::min(chunk, p->max_batch));
+    const int C = ctx->chunk, Bn = p->max_batch;
+    ctx->frames_pitch = align_up(p->max_width, 16);
+    ctx->frames_slot_bytes = (size_t)ctx->frames_pitch * p->max_height;
+    CK(cudaMalloc(&ctx->d_frames, ctx->frames_slot_bytes * Bn));
+    CK(cudaMalloc(&ctx->d_pyr, (size_t)M.pyr_frame_bytes * C));
+    CK(cudaMalloc(&ctx->d_box, (size_t)M.box_frame_elems * 2 * C));
+    CK(cudaMalloc(&ctx->d_cand, (size_t)M.cand_frame_elems * 8 * C));
+    CK(cudaMalloc(&ctx->d_cand_count, sizeof(int) * ORB_MAX_LEVELS * C));
+    CK(cudaMalloc(&ctx->d_kept_count, sizeof(int) * ORB_MAX_LEVELS * C));
+    CK(cudaMalloc(&ctx->d_kept_xy, sizeof(uint32_t) * (size_t)kept_per_frame * C));
+    CK(cudaMalloc(&ctx->d_kept_r, sizeof(float) * (size_t)kept_per_frame * C));
+    ctx->xtab_cap = 0; ctx->ytab_cap = 0;
+    for (int l = 0; l < M.nlevels; l++) { ctx->xtab_cap += M.lv[l].w; ctx->ytab_cap += M.lv[l].h; }
+    CK(cudaMalloc(&ctx->d_xtab, sizeof(OrbTap) * ctx->xtab_cap));
+    CK(cudaMalloc(&ctx->d_ytab, sizeof(OrbTap) * ctx->ytab_cap));
+    CK(cudaMalloc(&ctx->d_harris_w, sizeof(float) * 49));
+    CK(cudaMalloc(&ctx->d_pattern, sizeof(char4) * 256));
+    CK(cudaMalloc(&ctx->d_flags, sizeof(int)));
+    CK(cudaMallocHost(&ctx->h_flags, sizeof(int)));
+    ctx->list_cap = std::max(ORB_SORT_CAP, Bn * ctx->max_kp);
+    size_t nrec = (size_t)ctx->list_cap;
+    CK(cudaMalloc(&ctx->d_kps, sizeof(orb_keypoint) * nrec));
+    CK(cudaMalloc(&ctx->d_angles, sizeof(float) * nrec));
+    CK(cudaMalloc(&ctx->d_desc, sizeof(orb_descriptor) * nrec));
+    CK(cudaMalloc(&ctx->d_nout, sizeof(int) * Bn));
+    if (p->keep_side_arrays) {
+      CK(cudaMalloc(&ctx->d_side_xy, sizeof(orb_keypoint) * nrec));
+      CK(cudaMalloc(&ctx->d_side_level, sizeof(int) * nrec));
+      CK(cudaMalloc(&ctx->d_side_resp, sizeof(float) * nrec));
+    }
+    CK(cudaMalloc(&ctx->d_list_kps, sizeof(orb_keypoint) * nrec));
+    CK(cudaMalloc(&ctx->d_list_angles, sizeof(float) * nrec));
+    CK(cudaMalloc(&ctx->d_list_out, sizeof(float) * nrec));
+    harris_weights(ctx->harris_w);
+    CK(cudaMemcpy(ctx->d_harris_w, ctx->harris_w, sizeof(float) * 49, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_pattern, ORB_BRIEF_PATTERN_31, 1024, cudaMemcpyHostToDevice));
+    CK(cudaMemset(ctx->d_flags, 0, sizeof(int)));
+    CK(cudaFuncSetAttribute(orbk::k_pyramid_fast<TileT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileT::SMEM));
+    CK(cudaFuncSetAttribute(orbk::k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, ORB_SORT_CAP * 8));
+    return ORB_OK;
+  };
+  rc = body();
+  if (rc != ORB_OK) {
+    snprintf(g_create_error, sizeof(g_create_error), "%s", ctx->err);
+    orb_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return ORB_OK;
+}
+
+int orb_set_stream(orb_ctx* ctx, void* s) {
+  if (!ctx) return ORB_E_INVALID;
+  ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+  return ORB_OK;
+}
+
+int orb_synchronize(orb_ctx* ctx) {
+  if (!ctx) return ORB_E_INVALID;
+  CK(cudaSetDevice(ctx->p.device));
+  return check_flags(ctx);
+}
+
+int orb_level_size(const orb_ctx* ctx, int w, int h, int level, int* lw, int* lh) {
+  if (!ctx || level < 0 || level >= ctx->p.nlevels || !lw || !lh) return ORB_E_INVALID;
+  level_size(w, h, ctx->p.scale_factor, level, lw, lh);
+  return ORB_OK;
+}
+int orb_level_quota(const orb_ctx* ctx, int level) {
+  if (!ctx || level < 0 || level >= ctx->p.nlevels) return ORB_E_INVALID;
+  return ctx->p.select_policy == ORB_SELECT_HARRIS_TOP_N ? level_quota(ctx->p.nfeatures, ctx->p.scale_factor, ctx->p.nlevels, level)
+                                                         : ctx->p.nfeatures;
+}
+int orb_get_harris_weights(const orb_ctx* ctx, float* w49) {
+  if (!ctx || !w49) return ORB_E_INVALID;
+  memcpy(w49, ctx->harris_w, sizeof(float) * 49);
+  return ORB_OK;
+}
+int orb_last_launch_count(const orb_ctx* ctx) { return ctx ? ctx->launches : ORB_E_INVALID; }
+
+int orb_detect_and_compute_batch(orb_ctx* ctx, const uint8_t* frames, int frames_on_device, int n_frames, int w, int h,
+                                 size_t pitch, size_t frame_stride, int cap, orb_keypoint* kps, float* angles,
+                                 orb_descriptor* desc, int* n_out, int outputs_on_device) {
+  if (!ctx) return ORB_E_INVALID;
+  if (!frames || !kps || !angles || !desc || !n_out) return fail(ctx, ORB_E_INVALID, "null buffer");
+  if (n_frames < 1 || cap < 1 || pitch < (size_t)w || frame_stride < pitch * (size_t)(h - 1) + w)
+    return fail(ctx, ORB_E_INVALID, "bad batch geometry");
+  if (n_frames > ctx->p.max_batch) return fail(ctx, ORB_E_CAPACITY, "batch %d exceeds max_batch %d", n_frames, ctx->p.max_batch);
+  if (!outputs_on_device && cap > ctx->max_kp)
+    return fail(ctx, ORB_E_CAPACITY, "cap %d exceeds max_keypoints %d of the context", cap, ctx->max_kp);
+  if (ctx->p.keep_side_arrays && cap > ctx->max_kp) return fail(ctx, ORB_E_CAPACITY, "cap exceeds side-array capacity");
+  CK(cudaSetDevice(ctx->p.device));
+  int rc = get_plan(ctx, w, h);
+  if (rc) return rc;
+  const OrbPlan& P = ctx->plan;
+  ctx->launches = 0;
+
+  const uint8_t* src = frames;
+  size_t stride = frame_stride;
+  int sp = (int)pitch;
+  if (!frames_on_device) {
+    // host frames -> staging area (pitch re-aligned to 16 B)
+    if (frame_stride == pitch * (size_t)h && ctx->frames_slot_bytes == (size_t)ctx->frames_pitch * h) {
+      CK(cudaMemcpy2DAsync(ctx->d_frames, ctx->frames_pitch, frames, pitch, w, (size_t)h * n_frames,
+                           cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+      for (int f = 0; f < n_frames; f++)
+        CK(cudaMemcpy2DAsync(ctx->d_frames + (size_t)f * ctx->frames_slot_bytes, ctx->frames_pitch,
+                             frames + (size_t)f * frame_stride, pitch, w, h, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    src = ctx->d_frames; stride = ctx->frames_slot_bytes; sp = ctx->frames_pitch;
+  }
+  orb_keypoint* o_kps = outputs_on_device ? kps : ctx->d_kps;
+  float* o_ang = outputs_on_device ? angles : ctx->d_angles;
+  orb_descriptor* o_desc = outputs_on_device ? desc : ctx->d_desc;
+  int* o_n = outputs_on_device ? n_out : ctx->d_nout;
+
+  int total_quota = 0;
+  for (int l = 0; l < P.nlevels; l++) total_quota += P.lv[l].quota;
+  const int nwarps = std::min(total_quota, cap);
+
+  for (int c0 = 0; c0 < n_frames; c0 += ctx->chunk) {
+    const int nc = std::min(ctx->chunk, n_frames - c0);
+    Bufs B;
+    fill_bufs(ctx, &B);
+    B.frames = src + (size_t)c0 * stride; B.frame_stride = stride; B.pitch0 = sp;
+    B.out_kps = o_kps + (size_t)c0 * cap; B.out_angles = o_ang + (size_t)c0 * cap; B.out_desc = o_desc + (size_t)c0 * cap;
+    B.out_n = o_n + c0; B.out_cap = cap;
+    if (ctx->p.keep_side_arrays) {
+      B.side_xy = ctx->d_side_xy + (size_t)c0 * cap; B.side_level = ctx->d_side_level + (size_t)c0 * cap;
+      B.side_resp = ctx->d_side_resp + (size_t)c0 * cap;
+    }
+    if ((rc = launch_pyramid_fast(ctx, P, B, nc))) return rc;
+    if ((rc = launch_select(ctx, P, B, nc))) return rc;
+    DescribeJob J{0, nullptr, nullptr, 0};
+    if ((rc = launch_describe(ctx, P, B, J, nwarps, nc))) return rc;
+    if (nwarps == 0) CK(cudaMemsetAsync(B.out_n, 0, sizeof(int) * nc, ctx->stream));
+    ctx->last_chunk_start = c0; ctx->last_chunk_n = nc;
+  }
+  ctx->last_n = n_frames; ctx->last_cap = cap;
+  ctx->last_frames = src; ctx->last_stride = stride; ctx->last_pitch = sp;
+  ctx->last_outputs_ctx = !outputs_on_device;
+
+  if (!outputs_on_device) {
+    size_t nrec = (size_t)n_frames * cap;
+    CK(cudaMemcpyAsync(kps, ctx->d_kps, sizeof(orb_keypoint) * nrec, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(angles, ctx->d_angles, sizeof(float) * nrec, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(desc, ctx->d_desc, sizeof(orb_descriptor) * nrec, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(n_out, ctx->d_nout, sizeof(int) * n_frames, cudaMemcpyDeviceToHost, ctx->stream));
+    return check_flags(ctx);
+  }
+  return ORB_OK;
+}
+
+int orb_detect_and_compute(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch, int cap, orb_keypoint* kps,
+                           float* angles, orb_descriptor* desc, int* n_out, int* n_per_level) {
+  if (!ctx) return ORB_E_INVALID;
+  int rc = orb_detect_and_compute_batch(ctx, img, 0, 1, w, h, pitch, pitch * (size_t)h, cap, kps, angles, desc, n_out, 0);
+  if (rc) return rc;
+  if (n_per_level) {
+    int kc[ORB_MAX_LEVELS];
+    CK(cudaMemcpy(kc, ctx->d_kept_count, sizeof(kc), cudaMemcpyDeviceToHost));
+    int left = *n_out;
+    for (int l = 0; l < ctx->p.nlevels; l++) { n_per_level[l] = std::min(kc[l], left); left -= n_per_level[l]; }
+  }
+  return ORB_OK;
+}
+
+int orb_get_level(orb_ctx* ctx, int frame, int level, uint8_t* dst, size_t dst_pitch, int* w, int* h) {
+  if (!ctx || !dst) return ORB_E_INVALID;
+  if (level < 0 || level >= ctx->p.nlevels) return fail(ctx, ORB_E_INVALID, "level out of range");
+  if (frame < ctx->last_chunk_start || frame >= ctx->last_chunk_start + ctx->last_chunk_n || ctx->last_n == 0)
+    return fail(ctx, ORB_E_INVALID, "frame %d is not resident (last chunk holds frames %d..%d)", frame, ctx->last_chunk_start,
+                ctx->last_chunk_start + ctx->last_chunk_n - 1);
+  CK(cudaSetDevice(ctx->p.device));
+  const OrbLevel& G = ctx->plan.lv[level];
+  if (dst_pitch < (size_t)G.w) return fail(ctx, ORB_E_INVALID, "dst_pitch too small");
+  const uint8_t* s; size_t sp;
+  if (level == 0) { s = ctx->last_frames + (size_t)frame * ctx->last_stride; sp = ctx->last_pitch; }
+  else { s = ctx->d_pyr + (size_t)(frame - ctx->last_chunk_start) * ctx->plan.pyr_frame_bytes + G.lvl_ofs; sp = G.pitch; }
+  CK(cudaMemcpy2DAsync(dst, dst_pitch, s, sp, G.w, G.h, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (w) *w = G.w;
+  if (h) *h = G.h;
+  return ORB_OK;
+}
+
+int orb_get_side_arrays(orb_ctx* ctx, int frame, int n, orb_keypoint* level_xy, int32_t* level_id, float* response) {
+  if (!ctx) return ORB_E_INVALID;
+  if (!ctx->p.keep_side_arrays) return fail(ctx, ORB_E_INVALID, "context was created without keep_side_arrays");
+  if (frame < 0 || frame >= ctx->last_n || n < 0 || n > ctx->last_cap) return fail(ctx, ORB_E_INVALID, "frame / n out of range");
+  CK(cudaSetDevice(ctx->p.device));
+  size_t o = (size_t)frame * ctx->last_cap;
+  if (level_xy) CK(cudaMemcpyAsync(level_xy, ctx->d_side_xy + o, sizeof(orb_keypoint) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (level_id) CK(cudaMemcpyAsync(level_id, ctx->d_side_level + o, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (response) CK(cudaMemcpyAsync(response, ctx->d_side_resp + o, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return ORB_OK;
+}
+
+int orb_get_candidates(orb_ctx* ctx, int frame, int level, int cap, orb_keypoint* xy, float* response, int* n_out) {
+  if (!ctx || !n_out) return ORB_E_INVALID;
+  if (level < 0 || level >= ctx->p.nlevels) return fail(ctx, ORB_E_INVALID, "level out of range");
+  if (frame < ctx->last_chunk_start || frame >= ctx->last_chunk_start + ctx->last_chunk_n || ctx->last_n == 0)
+    return fail(ctx, ORB_E_INVALID, "frame %d is not resident", frame);
+  CK(cudaSetDevice(ctx->p.device));
+  const int slot = frame - ctx->last_chunk_start;
+  const OrbLevel& G = ctx->plan.lv[level];
+  int n = 0;
+  CK(cudaMemcpy(&n, ctx->d_cand_count + slot * ORB_MAX_LEVELS + level, sizeof(int), cudaMemcpyDeviceToHost));
+  *n_out = n;
+  int m = std::min(std::min(n, cap), G.cand_cap);
+  if (m > 0 && (xy || response)) {
+    std::vector<unsigned long long> keys(m);
+    CK(cudaMemcpy(keys.data(), ctx->d_cand + (size_t)slot * ctx->plan.cand_frame_elems + G.cand_ofs, 8 * (size_t)m,
+                  cudaMemcpyDeviceToHost));
+    for (int i = 0; i < m; i++) {
+      uint32_t lo = (uint32_t)keys[i], hi = ~(uint32_t)(keys[i] >> 32);
+      if (xy) xy[i] = orb_keypoint{(int)(lo & 0xffff), (int)(lo >> 16)};
+      if (response) {
+        uint32_t u = (hi & 0x80000000u) ? (hi & 0x7fffffffu) : ~hi;
+        float r;
+        memcpy(&r, &u, 4);
+        response[i] = ctx->p.select_policy == ORB_SELECT_HARRIS_TOP_N ? r : 0.0f;
+      }
+    }
+  }
+  return ORB_OK;
+}
+
+// ---- single-image stage entry points ----------------------------------------------------------
+int orb_fast_detect(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch, int nfeatures, orb_keypoint* kps, int* n_out) {
+  if (!ctx || !kps || !n_out) return ORB_E_INVALID;
+  if (nfeatures < 0 || nfeatures > ORB_SORT_CAP) return fail(ctx, ORB_E_CAPACITY, "nfeatures must be 0..%d", ORB_SORT_CAP);
+  CK(cudaSetDevice(ctx->p.device));
+  int rc = stage_image(ctx, img, w, h, pitch);
+  if (rc) return rc;
+  OrbPlan P; Bufs B;
+  stage_plan(ctx, w, h, ORB_SELECT_RASTER_FIRST_N, nfeatures, &P, &B);
+  if ((rc = launch_pyramid_fast(ctx, P, B, 1))) return rc;
+  if ((rc = launch_select(ctx, P, B, 1))) return rc;
+  int m = 0;
+  CK(cudaMemcpyAsync(&m, ctx->d_kept_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if ((rc = check_flags(ctx))) return rc;
+  std::vector<uint32_t> xy(std::max(m, 1));
+  CK(cudaMemcpy(xy.data(), ctx->d_kept_xy, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < m; i++) kps[i] = orb_keypoint{(int)(xy[i] & 0xffff), (int)(xy[i] >> 16)};
+  *n_out = m;
+  return ORB_OK;
+}
+
+int orb_harris(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch, const orb_keypoint* kps, int n, float* response) {
+  if (!ctx || (n > 0 && (!kps || !response))) return ORB_E_INVALID;
+  CK(cudaSetDevice(ctx->p.device));
+  int rc = stage_image(ctx, img, w, h, pitch);
+  if (rc) return rc;
+  for (int i = 0; i < n; i++)
+    if (kps[i].x < 0 || kps[i].x >= w || kps[i].y < 0 || kps[i].y >= h) return fail(ctx, ORB_E_INVALID, "keypoint %d outside the image", i);
+  for (int o = 0; o < n; o += ctx->list_cap) {
+    int m = std::min(ctx->list_cap, n - o);
+    CK(cudaMemcpyAsync(ctx->d_list_kps, kps + o, sizeof(orb_keypoint) * m, cudaMemcpyHostToDevice, ctx->stream));
+    orbk::k_harris_list<<<(m + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_frames, ctx->frames_pitch, w, h, ctx->d_list_kps, m,
+                                                                 ctx->d_harris_w, ctx->p.harris_k, ctx->d_list_out);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(response + o, ctx->d_list_out, sizeof(float) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return ORB_OK;
+}
+
+static int describe_list(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch, const orb_keypoint* kps,
+                         const float* angles_in, int n, float* angles_out, orb_descriptor* desc_out) {
+  CK(cudaSetDevice(ctx->p.device));
+  int rc = stage_image(ctx, img, w, h, pitch);
+  if (rc) return rc;
+  for (int i = 0; i < n; i++)
+    if (kps[i].x < 0 || kps[i].x >= w || kps[i].y < 0 || kps[i].y >= h) return fail(ctx, ORB_E_INVALID, "keypoint %d outside the image", i);
+  OrbPlan P; Bufs B;
+  stage_plan(ctx, w, h, ORB_SELECT_RASTER_FIRST_N, 0, &P, &B);
+  if (desc_out && (rc = launch_pyramid_fast(ctx, P, B, 1))) return rc;   // builds the box-sum image of the frame
+  for (int o = 0; o < n; o += ctx->list_cap) {
+    int m = std::min(ctx->list_cap, n - o);
+    CK(cudaMemcpyAsync(ctx->d_list_kps, kps + o, sizeof(orb_keypoint) * m, cudaMemcpyHostToDevice, ctx->stream));
+    if (angles_in) CK(cudaMemcpyAsync(ctx->d_list_angles, angles_in + o, sizeof(float) * m, cudaMemcpyHostToDevice, ctx->stream));
+    DescribeJob J{desc_out ? 2 : 1, ctx->d_list_kps, ctx->d_list_angles, m};
+    if ((rc = launch_describe(ctx, P, B, J, m, 1))) return rc;
+    if (angles_out) CK(cudaMemcpyAsync(angles_out + o, ctx->d_angles, sizeof(float) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    if (desc_out) CK(cudaMemcpyAsync(desc_out + o, ctx->d_desc, sizeof(orb_descriptor) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return ORB_OK;
+}
+
+int orb_orientations(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch, const orb_keypoint* kps, int n, float* angles) {
+  if (!ctx || (n > 0 && (!kps || !angles))) return ORB_E_INVALID;
+  return describe_list(ctx, img, w, h, pitch, kps, nullptr, n, angles, nullptr);
+}
+
+int orb_brief(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch, const orb_keypoint* kps, const float* angles, int n,
+              orb_descriptor* desc) {
+  if (!ctx || (n > 0 && (!kps || !angles || !desc))) return ORB_E_INVALID;
+  return describe_list(ctx, img, w, h, pitch, kps, angles, n, nullptr, desc);
+}
+
+int orb_debug_eval_math(orb_ctx* ctx, int op, const float* a, const float* b, int n, float* out) {
+  if (!ctx || !a || !out || n < 0 || op < 0 || op > 3 || (op == 0 && !b)) return ORB_E_INVALID;
+  CK(cudaSetDevice(ctx->p.device));
+  float *da = nullptr, *db = nullptr, *dout = nullptr;
+  CK(cudaMalloc(&da, sizeof(float) * std::max(n, 1)));
+  CK(cudaMalloc(&db, sizeof(float) * std::max(n, 1)));
+  CK(cudaMalloc(&dout, sizeof(float) * std::max(n, 1)));
+  CK(cudaMemcpy(da, a, sizeof(float) * n, cudaMemcpyHostToDevice));
+  if (b) CK(cudaMemcpy(db, b, sizeof(float) * n, cudaMemcpyHostToDevice));
+  if (n > 0) orbk::k_eval_math<<<(n + 255) / 256, 256, 0, ctx->stream>>>(op, da, db, n, dout);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(out, dout, sizeof(float) * n, cudaMemcpyDeviceToHost));
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  return ORB_OK;
+}
+
+}  // extern "C"

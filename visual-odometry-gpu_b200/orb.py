@@ -1,0 +1,334 @@
+"""Host-side mirror of the reference's ORB interface over the C ABI (include/orb_b200.h).
+
+Class and method names follow the reference's C++ facade (include/orb.hpp:10-49 and the CPU twins
+include/orb_cpu.hpp:4-43): ``ORB(nfeatures, scaleFactor, nlevels).detectAndCompute(image)``,
+``OrientedFAST(threshold, n, nms_window, patch_size).detect(image, nfeatures)`` /
+``.compute_orientations(image, keypoints)``, ``RotatedBRIEF().compute(image, keypoints, orientations)``.
+Images are numpy uint8 2-D arrays (the cv::Mat CV_8UC1 of the reference); keypoints come back as a
+structured array with fields x, y (== Keypoint, include/orb.hpp:4), descriptors as (N, 32) uint8
+(== ORBDescriptor, include/orb.hpp:6-8).
+
+There is no CPU fallback: everything below calls liborb_b200.so, and creating a context without a
+CUDA device raises OrbError.  The C++ facade with the reference's exact signatures is
+include/orb.hpp of this repository; both sit on the same C ABI.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+KP = np.dtype([("x", "<i4"), ("y", "<i4")])
+
+SELECT_RASTER_FIRST_N = 0
+SELECT_HARRIS_TOP_N = 1
+
+
+class OrbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("orb_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("fast_threshold", C.c_int32), ("fast_n", C.c_int32), ("nms_window", C.c_int32),
+                ("orient_patch", C.c_int32), ("select_policy", C.c_int32), ("blur_levels", C.c_int32),
+                ("harris_k", C.c_float), ("device", C.c_int32), ("max_width", C.c_int32),
+                ("max_height", C.c_int32), ("max_batch", C.c_int32), ("chunk_frames", C.c_int32),
+                ("max_keypoints", C.c_int32), ("keep_side_arrays", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+EXPORTS = [
+    "orb_abi_version", "orb_default_params", "orb_create", "orb_destroy", "orb_last_error", "orb_set_stream",
+    "orb_synchronize", "orb_detect_and_compute", "orb_detect_and_compute_batch", "orb_get_level", "orb_level_size",
+    "orb_level_quota", "orb_fast_detect", "orb_harris", "orb_orientations", "orb_brief", "orb_get_side_arrays",
+    "orb_get_candidates", "orb_get_harris_weights", "orb_last_launch_count", "orb_debug_eval_math", "bit_pattern_31_",
+]
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load_library():
+    """dlopen liborb_b200.so (building it in-tree with nvcc if it is missing or stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build()
+    L = C.CDLL(path)
+    vp, i, sz = C.c_void_p, C.c_int, C.c_size_t
+    L.orb_abi_version.restype = i
+    L.orb_default_params.argtypes = [C.POINTER(Params)]
+    L.orb_default_params.restype = None
+    L.orb_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    L.orb_destroy.argtypes = [vp]
+    L.orb_destroy.restype = None
+    L.orb_last_error.argtypes = [vp]
+    L.orb_last_error.restype = C.c_char_p
+    L.orb_set_stream.argtypes = [vp, vp]
+    L.orb_synchronize.argtypes = [vp]
+    L.orb_detect_and_compute.argtypes = [vp, vp, i, i, sz, i, vp, vp, vp, vp, vp]
+    L.orb_detect_and_compute_batch.argtypes = [vp, vp, i, i, i, i, sz, sz, i, vp, vp, vp, vp, i]
+    L.orb_get_level.argtypes = [vp, i, i, vp, sz, C.POINTER(i), C.POINTER(i)]
+    L.orb_level_size.argtypes = [vp, i, i, i, C.POINTER(i), C.POINTER(i)]
+    L.orb_level_quota.argtypes = [vp, i]
+    L.orb_fast_detect.argtypes = [vp, vp, i, i, sz, i, vp, C.POINTER(i)]
+    L.orb_harris.argtypes = [vp, vp, i, i, sz, vp, i, vp]
+    L.orb_orientations.argtypes = [vp, vp, i, i, sz, vp, i, vp]
+    L.orb_brief.argtypes = [vp, vp, i, i, sz, vp, vp, i, vp]
+    L.orb_get_side_arrays.argtypes = [vp, i, i, vp, vp, vp]
+    L.orb_get_candidates.argtypes = [vp, i, i, i, vp, vp, C.POINTER(i)]
+    L.orb_get_harris_weights.argtypes = [vp, vp]
+    L.orb_last_launch_count.argtypes = [vp]
+    L.orb_debug_eval_math.argtypes = [vp, i, vp, vp, i, vp]
+    _lib = L
+    return L
+
+
+def default_params():
+    p = Params()
+    load_library().orb_default_params(C.byref(p))
+    return p
+
+
+def _img(a):
+    a = np.asarray(a)
+    if a.dtype != np.uint8 or a.ndim != 2:
+        raise ValueError("image must be a 2-D uint8 array (CV_8UC1)")   # CV_Assert at ref src/orb_cpu.cpp:26
+    if a.strides[1] != 1:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One orb_ctx: device arena + stream + plan.  Not thread-safe; one per (device, host thread)."""
+
+    def __init__(self, params):
+        self.lib = load_library()
+        self.params = params
+        h = C.c_void_p()
+        rc = self.lib.orb_create(C.byref(params), C.byref(h))
+        if rc != 0:
+            raise OrbError(rc, self.lib.orb_last_error(None).decode())
+        self.h = h
+        tq = sum(self.level_quota(l) for l in range(params.nlevels))
+        self.max_kp = params.max_keypoints if params.max_keypoints > 0 else min(tq, 8192 * params.nlevels)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.orb_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise OrbError(rc, self.lib.orb_last_error(self.h).decode())
+
+    def set_stream(self, cuda_stream):
+        self._ck(self.lib.orb_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._ck(self.lib.orb_synchronize(self.h))
+
+    def level_size(self, w, h, level):
+        lw, lh = C.c_int(), C.c_int()
+        self._ck(self.lib.orb_level_size(self.h, w, h, level, C.byref(lw), C.byref(lh)))
+        return lw.value, lh.value
+
+    def level_quota(self, level):
+        return self.lib.orb_level_quota(self.h, level)
+
+    def launch_count(self):
+        return self.lib.orb_last_launch_count(self.h)
+
+    # ---- whole path -----------------------------------------------------------------------
+    def detect_and_compute(self, image, cap=None):
+        img = _img(image)
+        cap = cap or self.max_kp
+        kps = np.zeros(cap, KP)
+        ang = np.zeros(cap, np.float32)
+        des = np.zeros((cap, 32), np.uint8)
+        n = C.c_int()
+        npl = np.zeros(self.params.nlevels, np.int32)
+        self._ck(self.lib.orb_detect_and_compute(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], cap,
+                                                 _p(kps), _p(ang), _p(des), C.byref(n), _p(npl)))
+        return kps[:n.value], ang[:n.value], des[:n.value], npl
+
+    def detect_and_compute_batch(self, frames, cap=None, out=None):
+        """frames: (F, H, W) uint8 host array.  Returns (kps[F,cap], angles[F,cap], desc[F,cap,32], n[F])."""
+        frames = np.asarray(frames)
+        if frames.dtype != np.uint8 or frames.ndim != 3 or frames.strides[2] != 1:
+            raise ValueError("frames must be a (F, H, W) uint8 array")
+        F, H, W = frames.shape
+        cap = cap or self.max_kp
+        if out is None:
+            out = (np.zeros((F, cap), KP), np.zeros((F, cap), np.float32), np.zeros((F, cap, 32), np.uint8),
+                   np.zeros(F, np.int32))
+        kps, ang, des, n = out
+        self._ck(self.lib.orb_detect_and_compute_batch(self.h, _p(frames), 0, F, W, H, frames.strides[1],
+                                                       frames.strides[0], cap, _p(kps), _p(ang), _p(des), _p(n), 0))
+        return kps, ang, des, n
+
+    def detect_and_compute_batch_ptr(self, frames_ptr, frames_on_device, n_frames, w, h, pitch, frame_stride, cap,
+                                     kps_ptr, ang_ptr, des_ptr, n_ptr, outputs_on_device):
+        """Raw-pointer form (device or pinned-host buffers owned by the caller, e.g. torch tensors)."""
+        self._ck(self.lib.orb_detect_and_compute_batch(self.h, C.c_void_p(frames_ptr), int(frames_on_device), n_frames,
+                                                       w, h, pitch, frame_stride, cap, C.c_void_p(kps_ptr),
+                                                       C.c_void_p(ang_ptr), C.c_void_p(des_ptr), C.c_void_p(n_ptr),
+                                                       int(outputs_on_device)))
+
+    # ---- read-backs of the last call --------------------------------------------------------
+    def get_level(self, frame, level, w, h):
+        lw, lh = self.level_size(w, h, level)
+        out = np.zeros((lh, lw), np.uint8)
+        ow, oh = C.c_int(), C.c_int()
+        self._ck(self.lib.orb_get_level(self.h, frame, level, _p(out), lw, C.byref(ow), C.byref(oh)))
+        assert (ow.value, oh.value) == (lw, lh)
+        return out
+
+    def get_side_arrays(self, frame, n):
+        xy = np.zeros(n, KP)
+        lid = np.zeros(n, np.int32)
+        rsp = np.zeros(n, np.float32)
+        self._ck(self.lib.orb_get_side_arrays(self.h, frame, n, _p(xy), _p(lid), _p(rsp)))
+        return xy, lid, rsp
+
+    def get_candidates(self, frame, level, cap=1 << 20):
+        xy = np.zeros(cap, KP)
+        rsp = np.zeros(cap, np.float32)
+        n = C.c_int()
+        self._ck(self.lib.orb_get_candidates(self.h, frame, level, cap, _p(xy), _p(rsp), C.byref(n)))
+        m = min(n.value, cap)
+        return xy[:m], rsp[:m], n.value
+
+    def harris_weights(self):
+        w = np.zeros(49, np.float32)
+        self._ck(self.lib.orb_get_harris_weights(self.h, _p(w)))
+        return w
+
+    # ---- stages -------------------------------------------------------------------------------
+    def fast_detect(self, image, nfeatures):
+        img = _img(image)
+        kps = np.zeros(max(nfeatures, 1), KP)
+        n = C.c_int()
+        self._ck(self.lib.orb_fast_detect(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], nfeatures,
+                                          _p(kps), C.byref(n)))
+        return kps[:n.value].copy()
+
+    def harris(self, image, kps):
+        img = _img(image)
+        kps = np.ascontiguousarray(kps, KP)
+        out = np.zeros(len(kps), np.float32)
+        self._ck(self.lib.orb_harris(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), len(kps), _p(out)))
+        return out
+
+    def orientations(self, image, kps):
+        img = _img(image)
+        kps = np.ascontiguousarray(kps, KP)
+        out = np.zeros(len(kps), np.float32)
+        self._ck(self.lib.orb_orientations(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps),
+                                           len(kps), _p(out)))
+        return out
+
+    def brief(self, image, kps, angles):
+        img = _img(image)
+        kps = np.ascontiguousarray(kps, KP)
+        angles = np.ascontiguousarray(angles, np.float32)
+        if len(angles) != len(kps):
+            raise ValueError("keypoints / orientations length mismatch")
+        out = np.zeros((len(kps), 32), np.uint8)
+        self._ck(self.lib.orb_brief(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), _p(angles),
+                                    len(kps), _p(out)))
+        return out
+
+    def eval_math(self, op, a, b=None):
+        a = np.ascontiguousarray(a, np.float32)
+        b = None if b is None else np.ascontiguousarray(b, np.float32)
+        out = np.zeros(len(a), np.float32)
+        self._ck(self.lib.orb_debug_eval_math(self.h, op, _p(a), _p(b), len(a), _p(out)))
+        return out
+
+
+def make_params(nfeatures=500, scaleFactor=1.2, nlevels=8, threshold=20, n=9, nms_window=3, patch_size=31,
+                select_policy=SELECT_HARRIS_TOP_N, blur_levels=1, harris_k=0.04, device=0, max_width=1241,
+                max_height=376, max_batch=1, chunk_frames=0, max_keypoints=0, keep_side_arrays=0):
+    p = default_params()
+    p.nfeatures, p.scale_factor, p.nlevels = nfeatures, scaleFactor, nlevels
+    p.fast_threshold, p.fast_n, p.nms_window, p.orient_patch = threshold, n, nms_window, patch_size
+    p.select_policy, p.blur_levels, p.harris_k = select_policy, blur_levels, harris_k
+    p.device, p.max_width, p.max_height, p.max_batch = device, max_width, max_height, max_batch
+    p.chunk_frames, p.max_keypoints, p.keep_side_arrays = chunk_frames, max_keypoints, keep_side_arrays
+    return p
+
+
+# ---- the reference's class surface ------------------------------------------------------------
+class OrientedFAST:
+    """ref include/orb.hpp:10-22: OrientedFAST(threshold=20, n=9, nms_window=3, patch_size=31)."""
+
+    def __init__(self, threshold=20, n=9, nms_window=3, patch_size=31, device=0, max_width=4096, max_height=2304):
+        self._ctx = Context(make_params(nfeatures=3000, nlevels=1, threshold=threshold, n=n, nms_window=nms_window,
+                                        patch_size=patch_size, select_policy=SELECT_RASTER_FIRST_N, device=device,
+                                        max_width=max_width, max_height=max_height))
+
+    def detect(self, image, nfeatures):
+        """std::vector<Keypoint> detect(const cv::Mat&, int nfeatures) -- ref src/orb.cpp:22-27."""
+        return self._ctx.fast_detect(image, nfeatures)
+
+    def compute_orientations(self, image, keypoints):
+        """ref src/orb.cpp:29-33 / src/orb_cpu.cpp:139-183."""
+        return self._ctx.orientations(image, keypoints)
+
+
+class RotatedBRIEF:
+    """ref include/orb.hpp:24-32: n_bits = 256, patch_size = 31."""
+
+    def __init__(self, device=0, max_width=4096, max_height=2304):
+        self._ctx = Context(make_params(nfeatures=3000, nlevels=1, select_policy=SELECT_RASTER_FIRST_N, device=device,
+                                        max_width=max_width, max_height=max_height))
+
+    def compute(self, image, keypoints, orientations):
+        """ref src/orb.cpp:40-44 / src/orb_cpu.cpp:203-258."""
+        return self._ctx.brief(image, keypoints, orientations)
+
+
+class ORB:
+    """ref include/orb.hpp:34-49: ORB(nfeatures=500, scaleFactor=1.2f, nlevels=8).
+
+    Extra keyword knobs (FAST threshold, patch, selection policy, blur, device, capacities) default to the
+    reference's include/orb.hpp values, so ORB() behaves like the reference constructor.
+    """
+
+    def __init__(self, nfeatures=500, scaleFactor=1.2, nlevels=8, **kw):
+        kw.setdefault("keep_side_arrays", 0)
+        self.params = make_params(nfeatures=nfeatures, scaleFactor=scaleFactor, nlevels=nlevels, **kw)
+        self.ctx = Context(self.params)
+
+    def detectAndCompute(self, image):
+        """void detectAndCompute(image, keypoints, orientations, descriptors) -- ref src/orb.cpp:58-109.
+        Returns (keypoints, orientations, descriptors)."""
+        k, a, d, _ = self.ctx.detect_and_compute(image)
+        return k, a, d
+
+    def detectAndComputeBatch(self, frames, cap=None):
+        return self.ctx.detect_and_compute_batch(frames, cap)
+
+
+class ORBCPU(ORB):
+    """Name-compatible stand-in for the reference's CPU twin (include/orb_cpu.hpp:28-43): the SAME GPU
+    path configured the way ORBCPU::detectAndCompute actually runs as shipped (single level, FAST thr 50,
+    raster-first 3000, patch 9).  It is not a CPU implementation."""
+
+    def __init__(self, nfeatures=500, scaleFactor=1.2, nlevels=8, **kw):
+        kw.setdefault("max_keypoints", 3000)
+        super().__init__(nfeatures=3000, scaleFactor=scaleFactor, nlevels=1, threshold=50, patch_size=9,
+                         select_policy=SELECT_RASTER_FIRST_N, **kw)
