@@ -1,0 +1,321 @@
+#!/usr/bin/env python3
+"""bench.py -- ORB frames/s on synthetic KITTI-shaped frames (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the whole hot path (pyramid -> FAST+NMS+Harris -> top-N -> orientation -> BRIEF) over one
+batch of `--frames` synthetic 1241x376 frames per GPU (8 levels, f = 1.2, N = 2000, thr 20, patch 31).
+  value : whole-job frames/s, frames and outputs resident in HBM, CUDA events on the launching stream, max over
+          ranks.  The input batch (frames x 0.47 MB) is larger than L2, which is the cache-hygiene rule used here.
+  e2e   : same metric through the host-buffer C-ABI call (pinned host frames in, host records out), H2D and D2H
+          inside the timed region.
+  roofline : the kernel with the largest share of the step; algorithmic bytes per frame = sum of pyramid pixels for
+          k_pyramid (level 0 read + levels written) and k_fast (levels read), 44 B/record for k_describe; HBM peak from
+          MEASURED_PEAKS.json.  config.pass_* report the whole-pass figure with B_min = sum(P) + 44 K.
+  cpu_baseline : the CPU oracle (port of the reference's orb_cpu path, multi-level composition) on this box's host
+          cores, bounded sample, rank 0 only.
+Frames are independent, so ranks shard by frame and there is no data-path collective (weak scaling: fixed frames
+per GPU).  --impl reference times the CPU oracle alone with all host threads.
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, LEVELS, NFEAT, THR, PATCH, SCALE = 1241, 376, 8, 2000, 20, 31, 1.2
+PITCH = 1248                                  # 16-byte aligned rows in HBM
+SUM_P = 1444097                               # sum of pyramid pixels, SURVEY.md 8 (1241x376, 8 levels)
+P0 = W * H
+
+
+def level_sizes():
+    out = [(W, H)]
+    for l in range(1, LEVELS):
+        s = np.float32(np.float64(np.float32(SCALE)) ** l)
+        out.append((int(np.floor(np.float32(W) / s + np.float32(0.5))), int(np.floor(np.float32(H) / s + np.float32(0.5)))))
+    return out
+
+
+def workload_name(frames):
+    return "kitti_synth_%dx%d_L%d_N%d_thr%d_patch%d_batch%d_per_gpu" % (W, H, LEVELS, NFEAT, THR, PATCH, frames)
+
+
+def peaks():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(pk["hbm_gbs"]), "MEASURED_PEAKS.json (measured)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons during the timed regions (pynvml, 20 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop_evt, self.active = threading.Event(), False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+        while not self._stop_evt.is_set():
+            if self.active:
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                except Exception:
+                    pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def oracle_params(O):
+    return O.params(nfeatures=NFEAT, scale_factor=SCALE, nlevels=LEVELS, fast_threshold=THR, orient_patch=PATCH,
+                    select_policy=1, blur_levels=1, harris_k=0.04)
+
+
+def cpu_leg(frames_np, threads, steps, warmup):
+    """CPU oracle, frame-parallel over `threads` std::threads; returns (frames/s, seconds per step)."""
+    from oracle import pyoracle as O
+    p = oracle_params(O)
+    for _ in range(warmup):
+        O.detect_and_compute_batch(frames_np, p, NFEAT, threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.detect_and_compute_batch(frames_np, p, NFEAT, threads)
+    dt = (time.perf_counter() - t0) / steps
+    return frames_np.shape[0] / dt, dt
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU algorithm for this path on the host cores (oracle port; the
+    reference's own orb_cpu.cpp is single-level and needs OpenCV)."""
+    if rank != 0:
+        return
+    V = importlib.import_module("visual-odometry-gpu_b200")
+    cores = os.cpu_count() or 1
+    sample = max(cores, min(8 * cores, 256))
+    frames = np.ascontiguousarray(V.synth_frames(sample, W, H))
+    fps, dt = cpu_leg(frames, cores, args.steps, max(args.warmup, 1))
+    line = {"impl": "reference", "metric": "orb_frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload_name(args.frames), "step_sample_frames": sample},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": "%d synthetic frames per step, frame-parallel over %d threads" % (sample, cores)},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=1000, help="frames per GPU per step")
+    ap.add_argument("--chunk", type=int, default=0, help="frames per kernel wave (0 = library default)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the ORB path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    V = importlib.import_module("visual-odometry-gpu_b200")
+
+    F, cap = args.frames, NFEAT
+    lo, hi = V.shard_range(F * world, world, rank)          # global frame ids of this rank (weak scaling)
+    # synthetic frames: a pool of distinct frames, tiled to the batch (generator is not in the timed region)
+    pool = min(F, 64)
+    host_pool = V.synth_frames(pool, W, H, start=lo % 1000, pitch=PITCH)
+    idx = np.arange(F) % pool
+    h_frames = torch.from_numpy(host_pool)[torch.from_numpy(idx)].contiguous().pin_memory()      # (F, H, PITCH) pinned
+    d_frames = h_frames.to(dev, non_blocking=True)
+    d_k = torch.zeros(F, cap, 2, dtype=torch.int32, device=dev)
+    d_a = torch.zeros(F, cap, dtype=torch.float32, device=dev)
+    d_d = torch.zeros(F, cap, 32, dtype=torch.uint8, device=dev)
+    d_n = torch.zeros(F, dtype=torch.int32, device=dev)
+    h_k = torch.zeros(F, cap, 2, dtype=torch.int32).pin_memory()
+    h_a = torch.zeros(F, cap, dtype=torch.float32).pin_memory()
+    h_d = torch.zeros(F, cap, 32, dtype=torch.uint8).pin_memory()
+    h_n = torch.zeros(F, dtype=torch.int32).pin_memory()
+
+    ctx = V.Context(V.make_params(nfeatures=NFEAT, scaleFactor=SCALE, nlevels=LEVELS, threshold=THR, patch_size=PATCH,
+                                  device=local_rank, max_width=W, max_height=H, max_batch=F, chunk_frames=args.chunk,
+                                  max_keypoints=cap))
+    stream = torch.cuda.Stream(device=dev)       # all ORB work and the timing events go to this stream
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+
+    def step_device():
+        ctx.detect_and_compute_batch_ptr(d_frames.data_ptr(), 1, F, W, H, PITCH, H * PITCH, cap, d_k.data_ptr(),
+                                         d_a.data_ptr(), d_d.data_ptr(), d_n.data_ptr(), 1)
+
+    def step_e2e():
+        ctx.detect_and_compute_batch_ptr(h_frames.data_ptr(), 0, F, W, H, PITCH, H * PITCH, cap, h_k.data_ptr(),
+                                         h_a.data_ptr(), h_d.data_ptr(), h_n.data_ptr(), 0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.active = True
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        sampler.active = False
+        ms = e0.elapsed_time(e1)
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    ms_dev = timed(step_device, args.steps, args.warmup)
+    ctx.synchronize()
+    launches_per_step = ctx.launch_count()
+    n_kp = int(d_n.sum().item())
+
+    # per-kernel times of the same step (separate pass: the event brackets are not in the headline number)
+    ctx.set_profiling(True)
+    for _ in range(2):
+        step_device()
+    ctx.stage_ms()
+    prof_steps = max(1, min(args.steps, 5))
+    for _ in range(prof_steps):
+        step_device()
+    st_ms, st_n = ctx.stage_ms()
+    ctx.set_profiling(False)
+
+    ms_e2e = timed(step_e2e, max(1, args.steps // 2), 2)
+    e2e_steps = max(1, args.steps // 2)
+    sampler.stop()
+    assert int(h_n.sum().item()) == n_kp, "host and device paths disagree"
+
+    total_frames = F * world
+    value = total_frames * args.steps / (ms_dev * 1e-3)
+    e2e_value = total_frames * e2e_steps / (ms_e2e * 1e-3)
+    peak, peak_src = peaks()
+    # dominant kernel = largest share of the step; its algorithmic bytes per frame ("Kernels"):
+    #   k_pyramid : level 0 read once + levels >= 1 written once          = sum(P)
+    #   k_fast    : every level read once (box sums / candidates are ours) = sum(P)
+    #   k_select  : 8 B per candidate read (count unknown here; use K)     ~ 8 K
+    #   k_describe: 44 B per output record written                         = 44 K
+    names = ["k_pyramid", "k_fast", "k_select", "k_describe"]
+    kpf = n_kp / F
+    alg_bytes = [SUM_P, SUM_P, 8.0 * kpf, 44.0 * kpf]
+    dom = int(np.argmax(st_ms))
+    k1_ms = st_ms[dom] / max(1, st_n[dom])                    # average duration of one launch of that kernel
+    frames_per_launch = F * prof_steps / max(1, st_n[dom])
+    achieved = alg_bytes[dom] * frames_per_launch / (k1_ms * 1e-3) / 1e9
+    kp_per_frame = n_kp / F
+    b_min = SUM_P + 44.0 * kp_per_frame
+    pass_gbs = b_min * F * args.steps / (ms_dev * 1e-3) / 1e9       # per GPU
+    stage_share = [m / max(1e-9, sum(st_ms)) for m in st_ms]
+
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "latest_ncu.json")))
+        traffic = prof.get(names[int(np.argmax(st_ms))], {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    line = {
+        "metric": "orb_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(F), "frames_per_gpu_per_step": F, "levels": LEVELS, "nfeatures": NFEAT,
+                   "keypoints_per_frame": kp_per_frame, "chunk_frames": args.chunk,
+                   "cache_hygiene": "input batch %.0f MB > 126 MB L2; scratch arena reused per chunk" % (F * H * PITCH / 1e6),
+                   "stage_names": ["k_pyramid", "k_fast", "k_select", "k_describe"],
+                   "stage_ms_per_step": [m / prof_steps for m in st_ms], "stage_share": stage_share,
+                   "pass_b_min_bytes_per_frame": b_min, "pass_hbm_gbs_per_gpu": pass_gbs, "pass_hbm_frac": pass_gbs / peak,
+                   "peak_source": peak_src},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(F * H * PITCH),
+                "d2h_bytes_per_step": int(F * cap * 44 + F * 4)},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic,
+                     "algorithmic_bytes_per_launch": alg_bytes[dom] * frames_per_launch, "avg_launch_ms": k1_ms},
+        "clocks": sampler.summary(),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        sample = max(cores, min(8 * cores, 256))
+        fps, dt = cpu_leg(np.ascontiguousarray(V.synth_frames(sample, W, H)), cores, 1, 1)
+        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": "%d synthetic frames, frame-parallel over %d threads, %.1f s" % (sample, cores, dt)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -83,9 +83,11 @@ void orb_destroy(orb_ctx* ctx);
 const char* orb_last_error(const orb_ctx* ctx);   /* ctx may be NULL: error of the failed orb_create */
 int  orb_abi_version(void);
 
-/* run the context's work on a caller-provided cudaStream_t (passed as void*); NULL = the
- * context's own stream.  Lets a host framework time the kernels with events on its stream. */
+/* run the context's work on a caller-provided cudaStream_t (passed as void*; NULL is the CUDA legacy
+ * default stream, exactly as in the runtime API).  Lets a host framework order and time the kernels with
+ * events on its own stream.  orb_use_own_stream goes back to the context's private non-blocking stream. */
 int  orb_set_stream(orb_ctx* ctx, void* cuda_stream);
+int  orb_use_own_stream(orb_ctx* ctx);
 
 /* replaces: ORB::detectAndCompute (reference include/orb.hpp:37, src/orb.cpp:58-109; CPU twin
  * ORBCPU::detectAndCompute include/orb_cpu.hpp:31, src/orb_cpu.cpp:271-276).
@@ -150,6 +152,13 @@ int  orb_synchronize(orb_ctx* ctx);
 /* libm twins used on the device, evaluated on host arrays (test hook): op 0 atan2f(a,b), 1 cosf(a),
  * 2 sinf(a), 3 lround(a) -- the glibc calls of reference src/orb_cpu.cpp:178,217-218,228-232 */
 int  orb_debug_eval_math(orb_ctx* ctx, int op, const float* a, const float* b, int n, float* out);
+/* per-kernel timing (bench / roofline accounting): when enabled, every kernel launch of the detect calls is
+ * bracketed by CUDA events on the context's stream.  orb_get_stage_ms waits for the stream and returns, for the
+ * launches since the last call, the summed device time [ms] and launch count of
+ * stage 0 = pyramid kernel (resize+blur), 1 = FAST+NMS+Harris+box-sum kernel, 2 = selection kernel,
+ * 3 = orientation+BRIEF kernel. */
+int  orb_set_profiling(orb_ctx* ctx, int enable);
+int  orb_get_stage_ms(orb_ctx* ctx, float ms[4], int launches[4]);
 /* number of kernel launches issued by the last detect call (for bench accounting) */
 int  orb_last_launch_count(const orb_ctx* ctx);
 

@@ -1,0 +1,56 @@
+// Reads a raw 8-bit image, runs the reference-style C++ facade (include/orb.hpp, include/orb_cpu.hpp) and dumps the
+// results as raw arrays so the pytest harness can compare them with the oracle.  Written the way the reference's
+// only driver uses the classes (src/compare.cpp:39-65).
+//   facade_test <raw> <w> <h> <outprefix>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "orb.hpp"
+#include "orb_cpu.hpp"
+#include "orb_pattern.hpp"
+
+template <class T> static void dump(const std::string& path, const std::vector<T>& v) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) { perror(path.c_str()); exit(2); }
+    if (!v.empty()) fwrite(v.data(), sizeof(T), v.size(), f);
+    fclose(f);
+}
+
+int main(int argc, char** argv) {
+    if (argc < 5) return 1;
+    int w = atoi(argv[2]), h = atoi(argv[3]);
+    std::string out = argv[4];
+    std::vector<unsigned char> pix((size_t)w * h);
+    FILE* f = fopen(argv[1], "rb");
+    if (!f || fread(pix.data(), 1, pix.size(), f) != pix.size()) { fprintf(stderr, "cannot read %s\n", argv[1]); return 2; }
+    fclose(f);
+    cv::Mat image(h, w, CV_8UC1, pix.data(), (size_t)w);
+    try {
+        ORB orb_gpu;                                   // src/compare.cpp:40
+        std::vector<Keypoint> keypoints_gpu; std::vector<float> orientations_gpu; std::vector<ORBDescriptor> descriptors_gpu;
+        orb_gpu.detectAndCompute(image, keypoints_gpu, orientations_gpu, descriptors_gpu);   // :65
+        size_t first = keypoints_gpu.size();
+        orb_gpu.detectAndCompute(image, keypoints_gpu, orientations_gpu, descriptors_gpu);   // appends (src/orb.cpp:100-102)
+        if (keypoints_gpu.size() != 2 * first) { fprintf(stderr, "append semantics broken\n"); return 3; }
+        keypoints_gpu.resize(first); orientations_gpu.resize(first); descriptors_gpu.resize(first);
+        dump(out + ".orb.kps", keypoints_gpu); dump(out + ".orb.ang", orientations_gpu); dump(out + ".orb.desc", descriptors_gpu);
+
+        ORBCPU orb_cpu;                                // src/compare.cpp:39 (commented there)
+        std::vector<Keypoint> kc(7); std::vector<float> ac(7); std::vector<ORBDescriptor> dc(7);
+        orb_cpu.detectAndCompute(image, kc, ac, dc);   // assigns (src/orb_cpu.cpp:272-275)
+        dump(out + ".cpu.kps", kc); dump(out + ".cpu.ang", ac); dump(out + ".cpu.desc", dc);
+
+        OrientedFAST fast;                             // include/orb.hpp:12 defaults
+        RotatedBRIEF brief;
+        std::vector<Keypoint> ks = fast.detect(image, 700);
+        std::vector<float> as = fast.compute_orientations(image, ks);
+        std::vector<ORBDescriptor> ds = brief.compute(image, ks, as);
+        dump(out + ".stage.kps", ks); dump(out + ".stage.ang", as); dump(out + ".stage.desc", ds);
+        long s = 0; for (int i = 0; i < 1024; i++) s += bit_pattern_31_[i];
+        printf("FACADE_OK %zu %zu %zu pattern_sum %ld\n", first, kc.size(), ks.size(), s);
+    } catch (const std::exception& e) {
+        fprintf(stderr, "exception: %s\n", e.what());
+        return 4;
+    }
+    return 0;
+}

@@ -1,0 +1,60 @@
+"""The C++ facade (include/orb.hpp, include/orb_cpu.hpp: the reference's class names and signatures) compiled with
+g++ against liborb_b200.so and driven the way the reference's src/compare.cpp drives its classes."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build(tmp_path, V):
+    exe = str(tmp_path / "facade_test")
+    libdir = os.path.dirname(V.lib_path())
+    cmd = ["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "facade_test.cpp"),
+           "-o", exe, "-L" + libdir, "-lorb_b200", "-Wl,-rpath," + libdir]
+    env = {k: v for k, v in os.environ.items() if k not in ("CXX", "CC")}
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    assert r.returncode == 0, r.stdout
+    return exe
+
+
+def test_facade_compiles_without_gpu(tmp_path, V):
+    """Header-only facade + C ABI link on the CPU box (no compute call)."""
+    V.load_library()
+    _build(tmp_path, V)
+
+
+@pytest.mark.gpu
+def test_facade_matches_oracle(tmp_path, V, O, kitti0):
+    V.load_library()
+    exe = _build(tmp_path, V)
+    raw = tmp_path / "k0.raw"
+    kitti0.tofile(raw)
+    out = str(tmp_path / "out")
+    r = subprocess.run([exe, str(raw), "1241", "376", out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "FACADE_OK" in r.stdout, r.stdout
+    assert "pattern_sum %d" % int(O.pattern().astype(int).sum()) in r.stdout
+
+    def load(tag):
+        k = np.fromfile(out + "." + tag + ".kps", dtype=V.KP)
+        a = np.fromfile(out + "." + tag + ".ang", dtype=np.float32)
+        d = np.fromfile(out + "." + tag + ".desc", dtype=np.uint8).reshape(-1, 32)
+        return k, a, d
+
+    # ORB() == reference constructor defaults 500 / 1.2 / 8 (thr 20, patch 31, Harris top-N)
+    k, a, d = load("orb")
+    ref = O.detect_and_compute(kitti0, O.params(), cap=500)
+    assert np.array_equal(k, ref["kps"]) and np.array_equal(a.view(np.uint32), ref["angles"].view(np.uint32))
+    assert np.array_equal(d, ref["desc"])
+    # ORBCPU() == the reference's shipped CPU path (single level, thr 50, raster 3000, patch 9)
+    k, a, d = load("cpu")
+    ref = O.detect_and_compute(kitti0, O.params(nfeatures=3000, nlevels=1, fast_threshold=50, orient_patch=9, select_policy=0), cap=3000)
+    assert len(k) == 1178 and np.array_equal(k, ref["kps"]) and np.array_equal(d, ref["desc"])
+    # stage classes
+    k, a, d = load("stage")
+    kr = O.nms(O.fast_scores(kitti0, 20), 3, 700)
+    assert np.array_equal(k, kr)
+    ar = O.orientations(kitti0, kr, 31)
+    assert np.array_equal(a.view(np.uint32), ar.view(np.uint32)) and np.array_equal(d, O.brief(kitti0, kr, ar))

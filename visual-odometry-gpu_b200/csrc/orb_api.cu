@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cstdint>
 #include <cstring>
 #include <vector>
 
@@ -20,13 +21,6 @@
 using orbk::Bufs;
 using orbk::DescribeJob;
 
-#ifndef ORB_TILE_W
-#define ORB_TILE_W 128
-#endif
-#ifndef ORB_TILE_H
-#define ORB_TILE_H 64
-#endif
-typedef orbk::Tile<ORB_TILE_W, ORB_TILE_H> TileT;
 
 // == extern int bit_pattern_31_[256*4] of the reference (include/orb_pattern.hpp:2)
 extern "C" { int bit_pattern_31_[256 * 4]; }
@@ -49,9 +43,9 @@ struct orb_ctx {
   // arena
   uint8_t* d_frames = nullptr; size_t frames_slot_bytes = 0; int frames_pitch = 0;
   uint8_t* d_pyr = nullptr; uint16_t* d_box = nullptr; unsigned long long* d_cand = nullptr;
-  int* d_cand_count = nullptr; uint32_t* d_kept_xy = nullptr; float* d_kept_r = nullptr; int* d_kept_count = nullptr;
+  int* d_cand_count = nullptr; unsigned long long* d_level_sum = nullptr; uint32_t* d_kept_xy = nullptr; float* d_kept_r = nullptr; int* d_kept_count = nullptr;
   OrbTap *d_xtab = nullptr, *d_ytab = nullptr;
-  float* d_harris_w = nullptr; char4* d_pattern = nullptr; int* d_flags = nullptr; int* h_flags = nullptr;
+  float* d_harris_w = nullptr; float4* d_pattern = nullptr; int* d_flags = nullptr; int* h_flags = nullptr;
   orb_keypoint* d_kps = nullptr; float* d_angles = nullptr; orb_descriptor* d_desc = nullptr; int* d_nout = nullptr;
   orb_keypoint* d_side_xy = nullptr; int* d_side_level = nullptr; float* d_side_resp = nullptr;
   orb_keypoint* d_list_kps = nullptr; float* d_list_angles = nullptr; float* d_list_out = nullptr; int list_cap = 0;
@@ -61,6 +55,10 @@ struct orb_ctx {
   const uint8_t* last_frames = nullptr; size_t last_stride = 0; int last_pitch = 0;
   bool last_outputs_ctx = false;
   int launches = 0;
+  // optional per-kernel event timing
+  bool profiling = false;
+  struct Span { int stage; cudaEvent_t a, b; };
+  std::vector<Span> spans; size_t spans_used = 0;
 };
 
 namespace {
@@ -133,7 +131,7 @@ void build_plan(const orb_params& p, int W, int H, int nlevels, int policy, int 
   P->fast_threshold = p.fast_threshold; P->fast_n = p.fast_n;
   P->nms_radius = p.nms_window / 2; P->patch_radius = p.orient_patch / 2;
   P->select_policy = policy; P->blur_levels = p.blur_levels; P->harris_k = p.harris_k;
-  int tile = 0, kept = 0, xo = 0, yo = 0;
+  int tile = 0, atile = 0, kept = 0, xo = 0, yo = 0;
   unsigned long long lv = 0, bx = 0, cd = 0;
   for (int l = 0; l < nlevels; l++) {
     OrbLevel& G = P->lv[l];
@@ -141,9 +139,12 @@ void build_plan(const orb_params& p, int W, int H, int nlevels, int policy, int 
     G.w = std::max(G.w, 1); G.h = std::max(G.h, 1);
     G.pitch = align_up(G.w, 16);
     G.bpitch = align_up(G.w + 1, 8);
-    G.tiles_x = (G.w + TileT::TW - 1) / TileT::TW;
-    G.tiles_y = (G.h + TileT::TH - 1) / TileT::TH;
+    G.tiles_x = (G.w + orbk::B_TW - 1) / orbk::B_TW;
+    G.tiles_y = (G.h + orbk::B_TH - 1) / orbk::B_TH;
     G.tile_ofs = tile; tile += G.tiles_x * G.tiles_y;
+    G.a_tiles_x = (G.w + orbk::A_TW - 1) / orbk::A_TW;
+    G.a_tiles_y = (G.h + orbk::A_TH - 1) / orbk::A_TH;
+    G.a_tile_ofs = atile; if (l > 0) atile += G.a_tiles_x * G.a_tiles_y;
     int q = quota_override >= 0 ? quota_override
             : (policy == ORB_SELECT_HARRIS_TOP_N ? level_quota(p.nfeatures, p.scale_factor, p.nlevels, l) : p.nfeatures);
     G.quota = std::max(0, std::min(q, ORB_SORT_CAP));
@@ -155,7 +156,7 @@ void build_plan(const orb_params& p, int W, int H, int nlevels, int policy, int 
     G.box_ofs = bx; bx += (unsigned long long)align_up((G.h + 1) * G.bpitch, 128);
     G.cand_ofs = cd; cd += (unsigned long long)align_up(G.cand_cap, 32);
   }
-  P->tiles_per_frame = tile; P->kept_per_frame = kept;
+  P->tiles_per_frame = tile; P->a_tiles_per_frame = atile; P->kept_per_frame = kept;
   P->pyr_frame_bytes = std::max<unsigned long long>(lv, 256); P->box_frame_elems = bx; P->cand_frame_elems = cd;
 }
 
@@ -190,17 +191,43 @@ int get_plan(orb_ctx* ctx, int w, int h) {
 void fill_bufs(orb_ctx* ctx, Bufs* B) {
   memset(B, 0, sizeof(*B));
   B->pyr = ctx->d_pyr; B->box = ctx->d_box; B->cand = ctx->d_cand; B->cand_count = ctx->d_cand_count;
-  B->kept_xy = ctx->d_kept_xy; B->kept_r = ctx->d_kept_r; B->kept_count = ctx->d_kept_count;
+  B->level_sum = ctx->d_level_sum; B->kept_xy = ctx->d_kept_xy; B->kept_r = ctx->d_kept_r; B->kept_count = ctx->d_kept_count;
   B->xtab = ctx->d_xtab; B->ytab = ctx->d_ytab; B->harris_w = ctx->d_harris_w; B->pattern = ctx->d_pattern;
   B->flags = ctx->d_flags;
 }
 
+// event bracket around one kernel launch (only when profiling is on)
+struct StageTimer {
+  orb_ctx* c; orb_ctx::Span* sp = nullptr;
+  StageTimer(orb_ctx* ctx, int stage) : c(ctx) {
+    if (!c->profiling) return;
+    if (c->spans_used == c->spans.size()) {
+      orb_ctx::Span n{stage, nullptr, nullptr};
+      if (cudaEventCreate(&n.a) != cudaSuccess || cudaEventCreate(&n.b) != cudaSuccess) return;
+      c->spans.push_back(n);
+    }
+    sp = &c->spans[c->spans_used++];
+    sp->stage = stage;
+    cudaEventRecord(sp->a, c->stream);
+  }
+  ~StageTimer() { if (sp) cudaEventRecord(sp->b, c->stream); }
+};
+
 int launch_pyramid_fast(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, int nframes) {
-  CK(cudaMemsetAsync(ctx->d_cand_count, 0, sizeof(int) * ORB_MAX_LEVELS * nframes, ctx->stream));
-  dim3 grid(P.tiles_per_frame, nframes);
-  orbk::k_pyramid_fast<TileT><<<grid, orbk::K1_THREADS, TileT::SMEM, ctx->stream>>>(P, B);
+  // candidate counters and level totals of the whole chunk arena (one small memset)
+  CK(cudaMemsetAsync(ctx->d_cand_count, 0, (sizeof(int) + sizeof(unsigned long long)) * ORB_MAX_LEVELS * ctx->chunk, ctx->stream));
+  if (P.a_tiles_per_frame > 0) {
+    StageTimer t(ctx, 0);
+    orbk::k_pyramid<<<dim3(P.a_tiles_per_frame, nframes), orbk::A_THREADS, 0, ctx->stream>>>(P, B);
+    ctx->launches += 1;
+  }
   CK(cudaGetLastError());
-  ctx->launches += 2;
+  {
+    StageTimer t(ctx, 1);
+    orbk::k_fast<<<dim3(P.tiles_per_frame, nframes), orbk::B_THREADS, orbk::B_SMEM, ctx->stream>>>(P, B);
+  }
+  CK(cudaGetLastError());
+  ctx->launches += 1;
   return ORB_OK;
 }
 int launch_select(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, int nframes) {
@@ -209,7 +236,10 @@ int launch_select(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, int nframes) {
   int npow2 = 1;
   while (npow2 < mq) npow2 <<= 1;
   dim3 grid(P.nlevels, nframes);
-  orbk::k_select<<<grid, orbk::K2_THREADS, (size_t)npow2 * 8, ctx->stream>>>(P, B);
+  {
+    StageTimer t(ctx, 2);
+    orbk::k_select<<<grid, orbk::K2_THREADS, (size_t)npow2 * 8, ctx->stream>>>(P, B);
+  }
   CK(cudaGetLastError());
   ctx->launches += 1;
   return ORB_OK;
@@ -217,7 +247,10 @@ int launch_select(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, int nframes) {
 int launch_describe(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, const DescribeJob& J, int nwarps, int nframes) {
   if (nwarps <= 0) return ORB_OK;
   dim3 grid((nwarps + orbk::K3_WARPS - 1) / orbk::K3_WARPS, nframes);
-  orbk::k_describe<<<grid, orbk::K3_WARPS * 32, 0, ctx->stream>>>(P, B, J);
+  {
+    StageTimer t(ctx, 3);
+    orbk::k_describe<<<grid, orbk::K3_WARPS * 32, 0, ctx->stream>>>(P, B, J);
+  }
   CK(cudaGetLastError());
   ctx->launches += 1;
   return ORB_OK;
@@ -277,6 +310,7 @@ void orb_destroy(orb_ctx* ctx) {
                   ctx->d_angles, ctx->d_desc, ctx->d_nout, ctx->d_side_xy, ctx->d_side_level, ctx->d_side_resp,
                   ctx->d_list_kps, ctx->d_list_angles, ctx->d_list_out};
   for (void* q : ptrs) if (q) cudaFree(q);
+  for (auto& sp : ctx->spans) { if (sp.a) cudaEventDestroy(sp.a); if (sp.b) cudaEventDestroy(sp.b); }
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -337,7 +371,8 @@ int orb_create(const orb_params* p, orb_ctx** out) {
     CK(cudaMalloc(&ctx->d_pyr, (size_t)M.pyr_frame_bytes * C));
     CK(cudaMalloc(&ctx->d_box, (size_t)M.box_frame_elems * 2 * C));
     CK(cudaMalloc(&ctx->d_cand, (size_t)M.cand_frame_elems * 8 * C));
-    CK(cudaMalloc(&ctx->d_cand_count, sizeof(int) * ORB_MAX_LEVELS * C));
+    CK(cudaMalloc(&ctx->d_cand_count, (sizeof(int) + sizeof(unsigned long long)) * ORB_MAX_LEVELS * C));
+    ctx->d_level_sum = (unsigned long long*)(ctx->d_cand_count + (size_t)ORB_MAX_LEVELS * C);   // zeroed by the same memset
     CK(cudaMalloc(&ctx->d_kept_count, sizeof(int) * ORB_MAX_LEVELS * C));
     CK(cudaMalloc(&ctx->d_kept_xy, sizeof(uint32_t) * (size_t)kept_per_frame * C));
     CK(cudaMalloc(&ctx->d_kept_r, sizeof(float) * (size_t)kept_per_frame * C));
@@ -346,7 +381,7 @@ int orb_create(const orb_params* p, orb_ctx** out) {
     CK(cudaMalloc(&ctx->d_xtab, sizeof(OrbTap) * ctx->xtab_cap));
     CK(cudaMalloc(&ctx->d_ytab, sizeof(OrbTap) * ctx->ytab_cap));
     CK(cudaMalloc(&ctx->d_harris_w, sizeof(float) * 49));
-    CK(cudaMalloc(&ctx->d_pattern, sizeof(char4) * 256));
+    CK(cudaMalloc(&ctx->d_pattern, sizeof(float4) * 256));
     CK(cudaMalloc(&ctx->d_flags, sizeof(int)));
     CK(cudaMallocHost(&ctx->h_flags, sizeof(int)));
     ctx->list_cap = std::max(ORB_SORT_CAP, Bn * ctx->max_kp);
@@ -365,9 +400,13 @@ int orb_create(const orb_params* p, orb_ctx** out) {
     CK(cudaMalloc(&ctx->d_list_out, sizeof(float) * nrec));
     harris_weights(ctx->harris_w);
     CK(cudaMemcpy(ctx->d_harris_w, ctx->harris_w, sizeof(float) * 49, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_pattern, ORB_BRIEF_PATTERN_31, 1024, cudaMemcpyHostToDevice));
+    {
+      float pat[1024];   // the 256 tests as floats (x1,y1,x2,y2): the reference converts them per use (src/orb_cpu.cpp:228)
+      for (int i = 0; i < 1024; i++) pat[i] = (float)ORB_BRIEF_PATTERN_31[i];
+      CK(cudaMemcpy(ctx->d_pattern, pat, sizeof(pat), cudaMemcpyHostToDevice));
+    }
     CK(cudaMemset(ctx->d_flags, 0, sizeof(int)));
-    CK(cudaFuncSetAttribute(orbk::k_pyramid_fast<TileT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileT::SMEM));
+    CK(cudaFuncSetAttribute(orbk::k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, orbk::B_SMEM));
     CK(cudaFuncSetAttribute(orbk::k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, ORB_SORT_CAP * 8));
     return ORB_OK;
   };
@@ -383,7 +422,13 @@ int orb_create(const orb_params* p, orb_ctx** out) {
 
 int orb_set_stream(orb_ctx* ctx, void* s) {
   if (!ctx) return ORB_E_INVALID;
-  ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+  ctx->stream = (cudaStream_t)s;
+  return ORB_OK;
+}
+
+int orb_use_own_stream(orb_ctx* ctx) {
+  if (!ctx) return ORB_E_INVALID;
+  ctx->stream = ctx->own_stream;
   return ORB_OK;
 }
 
@@ -410,6 +455,28 @@ int orb_get_harris_weights(const orb_ctx* ctx, float* w49) {
 }
 int orb_last_launch_count(const orb_ctx* ctx) { return ctx ? ctx->launches : ORB_E_INVALID; }
 
+int orb_set_profiling(orb_ctx* ctx, int enable) {
+  if (!ctx) return ORB_E_INVALID;
+  ctx->profiling = enable != 0;
+  ctx->spans_used = 0;
+  return ORB_OK;
+}
+
+int orb_get_stage_ms(orb_ctx* ctx, float ms[4], int launches[4]) {
+  if (!ctx || !ms || !launches) return ORB_E_INVALID;
+  CK(cudaSetDevice(ctx->p.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < 4; i++) { ms[i] = 0.f; launches[i] = 0; }
+  for (size_t i = 0; i < ctx->spans_used; i++) {
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, ctx->spans[i].a, ctx->spans[i].b));
+    ms[ctx->spans[i].stage] += t;
+    launches[ctx->spans[i].stage]++;
+  }
+  ctx->spans_used = 0;
+  return ORB_OK;
+}
+
 int orb_detect_and_compute_batch(orb_ctx* ctx, const uint8_t* frames, int frames_on_device, int n_frames, int w, int h,
                                  size_t pitch, size_t frame_stride, int cap, orb_keypoint* kps, float* angles,
                                  orb_descriptor* desc, int* n_out, int outputs_on_device) {
@@ -430,15 +497,17 @@ int orb_detect_and_compute_batch(orb_ctx* ctx, const uint8_t* frames, int frames
   const uint8_t* src = frames;
   size_t stride = frame_stride;
   int sp = (int)pitch;
-  if (!frames_on_device) {
-    // host frames -> staging area (pitch re-aligned to 16 B)
+  // the kernels read level 0 with 16-byte loads: frames must be 16-byte aligned with 16-byte multiples as row
+  // pitch and frame stride.  Host frames (and device frames that are not) go through the staging area.
+  const bool aligned = frames_on_device && ((uintptr_t)frames % 16 == 0) && pitch % 16 == 0 && frame_stride % 16 == 0;
+  if (!aligned) {
+    const cudaMemcpyKind kind = frames_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (frame_stride == pitch * (size_t)h && ctx->frames_slot_bytes == (size_t)ctx->frames_pitch * h) {
-      CK(cudaMemcpy2DAsync(ctx->d_frames, ctx->frames_pitch, frames, pitch, w, (size_t)h * n_frames,
-                           cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpy2DAsync(ctx->d_frames, ctx->frames_pitch, frames, pitch, w, (size_t)h * n_frames, kind, ctx->stream));
     } else {
       for (int f = 0; f < n_frames; f++)
         CK(cudaMemcpy2DAsync(ctx->d_frames + (size_t)f * ctx->frames_slot_bytes, ctx->frames_pitch,
-                             frames + (size_t)f * frame_stride, pitch, w, h, cudaMemcpyHostToDevice, ctx->stream));
+                             frames + (size_t)f * frame_stride, pitch, w, h, kind, ctx->stream));
     }
     src = ctx->d_frames; stride = ctx->frames_slot_bytes; sp = ctx->frames_pitch;
   }

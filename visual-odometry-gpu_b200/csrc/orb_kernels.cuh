@@ -1,11 +1,12 @@
 // orb_kernels.cuh -- sm_100a kernels of the ORB hot path (u8 end to end, no tensor cores: nothing
-// here is a dense contraction).  Three launches per chunk of frames:
-//   k_pyramid_fast : per (frame, level, tile): bilinear resize from level 0 + 5x5 Gaussian in shared
-//                    memory, level pixels written once, FAST-n segment test + SAD score + 3x3 NMS on the
-//                    tile still in shared memory, Harris response of the survivors, 5x5 box-sum image
-//                    for BRIEF.  Replaces ref ORB::buildPyramid (src/orb.cpp:111-120 / src/orb_cpu.cpp:
-//                    278-290), d_Fast (src/cuda/Fast.cu:30-209), d_NMS (src/cuda/NMS.cu:21-128),
-//                    HarrisScore (src/cuda/HarrisScore.cu:23-89) and cv::integral (src/cuda/Brief.cu:101-105).
+// here is a dense contraction).  Four launches per chunk of frames:
+//   k_pyramid      : per (frame, level >= 1, 128x32 tile): bilinear resize from level 0 + 5x5 Gaussian in shared
+//                    memory, level pixels written once.  Replaces ref ORB::buildPyramid (src/orb.cpp:111-120 /
+//                    src/orb_cpu.cpp:278-290).
+//   k_fast         : per (frame, level, 128x64 tile): FAST-n segment test + SAD score + 3x3 NMS, Harris response
+//                    of the survivors, 5x5 box-sum image for BRIEF.  Replaces d_Fast (src/cuda/Fast.cu:30-209),
+//                    d_NMS (src/cuda/NMS.cu:21-128), HarrisScore (src/cuda/HarrisScore.cu:23-89) and cv::integral
+//                    (src/cuda/Brief.cu:101-105).
 //   k_select       : per (frame, level): exact top-quota selection under the total order
 //                    (response desc, y asc, x asc) by 64-bit radix select, then raster sort
 //                    (ref std::nth_element at src/orb.cpp:73-86; raster cap at src/orb_cpu.cpp:110).
@@ -13,6 +14,7 @@
 //                    src/cuda/Orientations.cu:22-63 == src/orb_cpu.cpp:139-183) and rotated BRIEF with
 //                    ballot-packed words (ref d_Brief, src/cuda/Brief.cu:40-95 == src/orb_cpu.cpp:203-258).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -30,13 +32,14 @@ struct Bufs {
   uint16_t* box;                 // [chunk][box_frame_elems]
   unsigned long long* cand;      // [chunk][cand_frame_elems]
   int* cand_count;               // [chunk][ORB_MAX_LEVELS]
+  unsigned long long* level_sum; // [chunk][ORB_MAX_LEVELS] sum of all pixels of the level (BRIEF corner boxes)
   uint32_t* kept_xy;             // [chunk][kept_per_frame]   (y << 16 | x), level space
   float* kept_r;                 // [chunk][kept_per_frame]
   int* kept_count;               // [chunk][ORB_MAX_LEVELS]
   const OrbTap* xtab;
   const OrbTap* ytab;
   const float* harris_w;         // 49 window weights
-  const char4* pattern;          // 256 BRIEF tests (x1,y1,x2,y2)
+  const float4* pattern;         // 256 BRIEF tests (x1,y1,x2,y2) as floats
   int* flags;                    // bit 0: candidate overflow
   orb_keypoint* out_kps;         // [chunk][out_cap]
   float* out_angles;
@@ -97,213 +100,361 @@ __device__ __forceinline__ float harris_at(PIX pix, int y, int x, const float* _
   return orbm::fsub(det, orbm::fmul(orbm::fmul(k, tr), tr));
 }
 
-// FAST-n corner score of one pixel (ref src/orb_cpu.cpp:37-100): 0 if not a corner.
-// PIX(dy, dx) returns the pixel at an offset from the centre.
-template <typename PIX>
-__device__ __forceinline__ int fast_score(PIX pix, int thr, int n) {
-  int Ip = pix(0, 0);
-  int hi = Ip + thr, lo = Ip - thr;
-  int v0 = pix(-3, 0), v4 = pix(0, 3), v8 = pix(3, 0), v12 = pix(0, -3);
-  int br = (v0 >= hi) + (v4 >= hi) + (v8 >= hi) + (v12 >= hi);
-  int dk = (v0 < hi && v0 <= lo) + (v4 < hi && v4 <= lo) + (v8 < hi && v8 <= lo) + (v12 < hi && v12 <= lo);
-  if (max(br, dk) < 3) return 0;
+// FAST-n corner score of one pixel (ref src/orb_cpu.cpp:60-100) for a pixel that already passed the
+// compass pretest: 0 if no arc of n contiguous ring pixels is all brighter / all darker, else the SAD score.
+// c points at the centre inside a shared-memory tile of row pitch SP bytes.
+template <int SP>
+__device__ __forceinline__ int fast_ring_score(const uint8_t* __restrict__ c, int thr, int n) {
   // FAST ring in the reference's order (src/orb_cpu.cpp:8-13)
   constexpr int ring_dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
   constexpr int ring_dy[16] = {-3, -3, -2, -1, 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3};
-  uint32_t mb = 0, md = 0;
-  int sad = 0;
+  const int Ip = c[0];
+  const int hi = Ip + thr, lo = Ip - thr;
+  uint32_t mb = 0, md = 0, sad = 0;
 #pragma unroll
   for (int i = 0; i < 16; i++) {
-    int v = pix(ring_dy[i], ring_dx[i]);
-    mb |= (uint32_t)(v >= hi) << i;
-    md |= (uint32_t)(v <= lo) << i;
-    sad += abs(Ip - v);
+    int v = c[ring_dy[i] * SP + ring_dx[i]];
+    if (v >= hi) mb |= 1u << i;
+    if (v <= lo) md |= 1u << i;
+    sad = __usad(v, Ip, sad);
   }
   mb |= mb << 16;
   md |= md << 16;
-  uint32_t rb = mb, rd = md;
-  for (int j = 1; j < n; j++) { rb &= mb >> j; rd &= md >> j; }
-  return ((rb | rd) & 0xffffu) ? sad : 0;
+  uint32_t rb, rd;
+  if (n == 9) {                      // runs of >= 9: doubling steps 2, 4, 8, then one more
+    rb = mb & (mb >> 1); rb &= rb >> 2; rb &= rb >> 4; rb &= mb >> 8;
+    rd = md & (md >> 1); rd &= rd >> 2; rd &= rd >> 4; rd &= md >> 8;
+  } else {
+    rb = mb; rd = md;
+    for (int j = 1; j < n; j++) { rb &= mb >> j; rd &= md >> j; }
+  }
+  return ((rb | rd) & 0xffffu) ? (int)sad : 0;
 }
 
-// ---------------------------------------------------------------------------------------------
-template <int TW_, int TH_>
-struct Tile {
-  static constexpr int TW = TW_, TH = TH_;
-  static constexpr int RW = TW + 12, RH = TH + 12;   // resized pixels, halo 6 (4 + blur 2)
-  static constexpr int PW = TW + 8, PH = TH + 8;     // level pixels, halo 4 (FAST 3 + NMS 1)
-  static constexpr int SW = TW + 2, SH = TH + 2;     // scores, halo 1
-  static constexpr int RWP = (RW + 3) & ~3, PWP = (PW + 3) & ~3;
-  static constexpr int LIST_CAP = 2048;
-  static constexpr int RES_BYTES = RH * RWP;                 // u8
-  static constexpr int TMP_BYTES = RH * PW * 2;              // u16: h-blur, then scores, then box rows
-  static constexpr int PIX_BYTES = PH * PWP;                 // u8
-  static constexpr int SMEM = RES_BYTES + TMP_BYTES + PIX_BYTES + LIST_CAP * 2 + 16;
-  static_assert(SH * SW * 2 <= TMP_BYTES && (TH + 4) * TW * 2 <= TMP_BYTES, "tmp aliasing");
-  static_assert(TW % 4 == 0, "tile width");
-};
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+__device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 
-constexpr int K1_THREADS = 256;
+// =============================================================================================
+// Kernel A: pyramid level l >= 1 = GaussianBlur5x5( resize_linear(level 0) )  (ref src/orb_cpu.cpp:283-290).
+// One CTA per 128x32 output tile.  Bilinear taps come from host tables (no floating point on the device);
+// the blur runs in 16-bit lanes, two pixels per register, and each level is written exactly once.
+constexpr int A_TW = 128, A_TH = 32, A_THREADS = 256;
+constexpr int A_RW = A_TW + 4, A_RH = A_TH + 4;   // resized region incl. blur halo 2
+constexpr int A_RP = 136;                          // shared pitch of resized rows (bytes)
 
-template <class T>
-__global__ void __launch_bounds__(K1_THREADS) k_pyramid_fast(const OrbPlan P, const Bufs B) {
+__global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bufs B) {
+  __shared__ __align__(16) OrbTap s_xt[A_RW];
+  __shared__ __align__(16) OrbTap s_yt[A_RH];
+  __shared__ __align__(16) uint8_t s_res[A_RH * A_RP];
+  __shared__ __align__(16) uint16_t s_h[A_RH * A_TW];
+  const int tid = threadIdx.x, f = blockIdx.y;
+  int t = blockIdx.x, l = 1;
+  while (l + 1 < P.nlevels && t >= P.lv[l + 1].a_tile_ofs) l++;
+  const OrbLevel& G = P.lv[l];
+  t -= G.a_tile_ofs;
+  const int x0 = (t % G.a_tiles_x) * A_TW, y0 = (t / G.a_tiles_x) * A_TH;
+  const int w = G.w, h = G.h;
+  const bool blur = P.blur_levels != 0;
+  const int halo = blur ? 2 : 0;
+  const int rw = A_TW + 2 * halo, rh = A_TH + 2 * halo;
+  const uint8_t* __restrict__ src = B.frames + (size_t)f * B.frame_stride;
+  const int sp = B.pitch0;
+
+  for (int i = tid; i < rw + rh; i += A_THREADS) {
+    if (i < rw) s_xt[i] = B.xtab[G.xtab_ofs + reflect101(x0 - halo + i, w)];
+    else s_yt[i - rw] = B.ytab[G.ytab_ofs + reflect101(y0 - halo + i - rw, h)];
+  }
+  __syncthreads();
+
+  // resize: 4 output pixels per item (cv::resize INTER_LINEAR restated: 11-bit taps, >>4, >>16, +2 >>2)
+  const int nwords = rw >> 2;
+  for (int it = tid; it < rh * nwords; it += A_THREADS) {
+    const int ry = it / nwords, gx = it - ry * nwords;
+    if (y0 - halo + ry >= h + halo || x0 - halo + 4 * gx >= w + halo) continue;
+    const OrbTap ty = s_yt[ry];
+    const uint8_t* r0 = src + (size_t)ty.s0 * sp;
+    const uint8_t* r1 = src + (size_t)ty.s1 * sp;
+    uint32_t word = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const OrbTap tx = s_xt[4 * gx + j];
+      int h0 = __ldg(r0 + tx.s0) * tx.a0 + __ldg(r0 + tx.s1) * tx.a1;
+      int h1 = __ldg(r1 + tx.s0) * tx.a0 + __ldg(r1 + tx.s1) * tx.a1;
+      int v = (((ty.a0 * (h0 >> 4)) >> 16) + ((ty.a1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      word |= (uint32_t)min(v, 255) << (8 * j);
+    }
+    *(uint32_t*)(s_res + ry * A_RP + 4 * gx) = word;
+  }
+  __syncthreads();
+
+  uint8_t* dst = B.pyr + (size_t)f * P.pyr_frame_bytes + G.lvl_ofs;
+  if (!blur) {   // ref src/orb.cpp:119: resize only
+    for (int it = tid; it < A_TH * (A_TW / 8); it += A_THREADS) {
+      const int oy = it / (A_TW / 8), g = it - oy * (A_TW / 8);
+      if (y0 + oy >= h || x0 + 8 * g >= G.pitch) continue;
+      *(uint2*)(dst + (size_t)(y0 + oy) * G.pitch + x0 + 8 * g) = *(const uint2*)(s_res + oy * A_RP + 8 * g);
+    }
+    return;
+  }
+
+  // horizontal [1 4 6 4 1]: 8 outputs per item, lanes hold pixels two apart: (o0,o2) (o1,o3) (o4,o6) (o5,o7)
+  const uint32_t M = 0x00ff00ffu;
+  for (int it = tid; it < A_RH * (A_TW / 8); it += A_THREADS) {
+    const int ry = it / (A_TW / 8), g = it - ry * (A_TW / 8);
+    const uint8_t* r = s_res + ry * A_RP + 8 * g;
+    const uint2 w01 = *(const uint2*)r;
+    const uint32_t w2 = *(const uint32_t*)(r + 8);
+    const uint32_t v1 = prmt(w01.x, w01.y, 0x5432), v2 = prmt(w01.y, w2, 0x5432);
+    const uint32_t q0 = w01.x & M, q1 = (w01.x >> 8) & M, q2 = v1 & M, q3 = (v1 >> 8) & M, q4 = w01.y & M,
+                   q5 = (w01.y >> 8) & M, q6 = v2 & M, q7 = (v2 >> 8) & M, q8 = w2 & M, q9 = (w2 >> 8) & M;
+    uint4 o;
+    o.x = q0 + q4 + 4 * (q1 + q3) + 6 * q2;
+    o.y = q1 + q5 + 4 * (q2 + q4) + 6 * q3;
+    o.z = q4 + q8 + 4 * (q5 + q7) + 6 * q6;
+    o.w = q5 + q9 + 4 * (q6 + q8) + 6 * q7;
+    *(uint4*)(s_h + ry * A_TW + 8 * g) = o;
+  }
+  __syncthreads();
+  // vertical [1 4 6 4 1], one rounding: (sum + 128) >> 8  (cv::GaussianBlur 5x5 sigma 0 on u8)
+  for (int it = tid; it < A_TH * (A_TW / 8); it += A_THREADS) {
+    const int oy = it / (A_TW / 8), g = it - oy * (A_TW / 8);
+    if (y0 + oy >= h || x0 + 8 * g >= G.pitch) continue;
+    const uint16_t* c = s_h + oy * A_TW + 8 * g;
+    const uint4 r0 = *(const uint4*)c, r1 = *(const uint4*)(c + A_TW), r2 = *(const uint4*)(c + 2 * A_TW),
+                r3 = *(const uint4*)(c + 3 * A_TW), r4 = *(const uint4*)(c + 4 * A_TW);
+    const uint32_t R = 0x00800080u;
+    const uint32_t a = r0.x + r4.x + 4 * (r1.x + r3.x) + 6 * r2.x + R;
+    const uint32_t b = r0.y + r4.y + 4 * (r1.y + r3.y) + 6 * r2.y + R;
+    const uint32_t cc = r0.z + r4.z + 4 * (r1.z + r3.z) + 6 * r2.z + R;
+    const uint32_t d = r0.w + r4.w + 4 * (r1.w + r3.w) + 6 * r2.w + R;
+    uint2 out;
+    out.x = prmt(a, b, 0x7351);    // (a>>8 lane0, b>>8 lane0, a>>8 lane1, b>>8 lane1) = pixels 0,1,2,3
+    out.y = prmt(cc, d, 0x7351);
+    *(uint2*)(dst + (size_t)(y0 + oy) * G.pitch + x0 + 8 * g) = out;
+  }
+}
+
+// =============================================================================================
+// Kernel B: FAST-n + SAD score + 3x3 NMS + Harris response + 5x5 box sums on one 128x64 tile of one level.
+//   pretest  : the >=3-of-4 compass test (ref src/orb_cpu.cpp:39-58) on packed half2 (2 pixels / instruction):
+//              second smallest / second largest of the four compass pixels against Ip +- thr;
+//   ring     : passers are compacted into a shared list and finished one pixel per thread (arc + SAD);
+//   NMS      : score == max of its 3x3 window, ties keep both (:126); survivors get their Harris response
+//              from the tile in shared memory and are appended to the level's candidate list;
+//   box sums : 5x5 sums of the level (u16) for BRIEF, 16-bit lanes, written once.
+constexpr int B_TW = 128, B_TH = 64, B_THREADS = 256;
+constexpr int B_SP = 160;              // pixel tile pitch (bytes); pixel x sits at column x - x0 + 16
+constexpr int B_PH = B_TH + 8;         // rows y0-4 .. y0+B_TH+3
+constexpr int B_SCP = 144;             // score pitch (u16); pixel x sits at column x - x0 + 8
+constexpr int B_SH = B_TH + 2;         // rows y0-1 .. y0+B_TH
+constexpr int B_LIST = 8704;           // >= (B_TW+2)*(B_TH+2) pretest positions; also holds the box rows
+constexpr int B_SURV = 1024;
+constexpr int B_PIX_BYTES = B_PH * B_SP, B_SCORE_BYTES = B_SH * B_SCP * 2, B_LIST_BYTES = B_LIST * 2;
+constexpr int B_SMEM = B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES + B_SURV * 2 + 16;
+static_assert((B_TH + 4) * B_TW * 2 <= B_LIST_BYTES, "box rows alias the list");
+static_assert((B_TW + 2) * (B_TH + 2) <= B_LIST, "list capacity");
+
+__global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs B) {
   extern __shared__ __align__(16) uint8_t smem[];
-  uint8_t* s_res = smem;
-  uint16_t* s_tmp = (uint16_t*)(smem + T::RES_BYTES);
-  uint8_t* s_pix = smem + T::RES_BYTES + T::TMP_BYTES;
-  uint16_t* s_list = (uint16_t*)(s_pix + T::PIX_BYTES);
-  int* s_ctr = (int*)(s_list + T::LIST_CAP);   // [0] list count, [1] global base
+  uint8_t* s_pix = smem;
+  uint16_t* s_score = (uint16_t*)(smem + B_PIX_BYTES);
+  uint16_t* s_list = (uint16_t*)(smem + B_PIX_BYTES + B_SCORE_BYTES);
+  uint16_t* s_surv = (uint16_t*)(smem + B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES);
+  int* s_ctr = (int*)(s_surv + B_SURV);   // [0] pretest list, [1] survivor list, [2] global base
 
-  const int tid = threadIdx.x;
-  const int f = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, f = blockIdx.y;
   int t = blockIdx.x, l = 0;
   while (l + 1 < P.nlevels && t >= P.lv[l + 1].tile_ofs) l++;
   const OrbLevel& G = P.lv[l];
   t -= G.tile_ofs;
-  const int x0 = (t % G.tiles_x) * T::TW, y0 = (t / G.tiles_x) * T::TH;
+  const int x0 = (t % G.tiles_x) * B_TW, y0 = (t / G.tiles_x) * B_TH;
   const int w = G.w, h = G.h;
-  const uint8_t* __restrict__ src = B.frames + (size_t)f * B.frame_stride;
-  const int sp = B.pitch0;
-  if (tid == 0) s_ctr[0] = 0;
+  const uint8_t* __restrict__ img;
+  int pitch;
+  if (l == 0) { img = B.frames + (size_t)f * B.frame_stride; pitch = B.pitch0; }
+  else { img = B.pyr + (size_t)f * P.pyr_frame_bytes + G.lvl_ofs; pitch = G.pitch; }
 
-  // ---- phase 1: level pixels with halo into shared memory ---------------------------------
-  if (l == 0) {
-    for (int i = tid; i < T::PH * T::PW; i += K1_THREADS) {
-      int py = i / T::PW, px = i - py * T::PW;
-      int ly = y0 - 4 + py, lx = x0 - 4 + px;
-      if (ly >= h + 4 || lx >= w + 4) continue;
-      s_pix[py * T::PWP + px] = __ldg(src + (size_t)reflect101(ly, h) * sp + reflect101(lx, w));
-    }
-  } else {
-    const OrbTap* __restrict__ xt = B.xtab + G.xtab_ofs;
-    const OrbTap* __restrict__ yt = B.ytab + G.ytab_ofs;
-    const bool blur = P.blur_levels != 0;
-    // resized pixels (cv::resize INTER_LINEAR restated: 11-bit taps, >>4, >>16, +2 >>2)
-    const int halo = blur ? 6 : 4;
-    const int rw = T::TW + 2 * halo, rh = T::TH + 2 * halo;
-    for (int i = tid; i < rw * rh; i += K1_THREADS) {
-      int ry = i / rw, rx = i - ry * rw;
-      int ly = y0 - halo + ry, lx = x0 - halo + rx;
-      if (ly >= h + halo || lx >= w + halo) continue;
-      OrbTap ty = yt[reflect101(ly, h)], tx = xt[reflect101(lx, w)];
-      const uint8_t* r0 = src + (size_t)ty.s0 * sp;
-      const uint8_t* r1 = src + (size_t)ty.s1 * sp;
-      int h0 = __ldg(r0 + tx.s0) * tx.a0 + __ldg(r0 + tx.s1) * tx.a1;
-      int h1 = __ldg(r1 + tx.s0) * tx.a0 + __ldg(r1 + tx.s1) * tx.a1;
-      int v = (((ty.a0 * (h0 >> 4)) >> 16) + ((ty.a1 * (h1 >> 4)) >> 16) + 2) >> 2;
-      v = min(v, 255);
-      if (blur) s_res[ry * T::RWP + rx] = (uint8_t)v;
-      else s_pix[ry * T::PWP + rx] = (uint8_t)v;
-    }
-    if (blur) {
-      __syncthreads();
-      // cv::GaussianBlur 5x5 sigma 0 on u8: [1 4 6 4 1] both ways, one rounding: (sum + 128) >> 8
-      for (int i = tid; i < T::RH * T::PW; i += K1_THREADS) {
-        int ry = i / T::PW, px = i - ry * T::PW;
-        const uint8_t* r = s_res + ry * T::RWP + px;
-        s_tmp[i] = (uint16_t)(r[0] + 4 * r[1] + 6 * r[2] + 4 * r[3] + r[4]);
-      }
-      __syncthreads();
-      for (int i = tid; i < T::PH * T::PW; i += K1_THREADS) {
-        int py = i / T::PW, px = i - py * T::PW;
-        const uint16_t* c = s_tmp + py * T::PW + px;
-        int s = c[0] + 4 * c[T::PW] + 6 * c[2 * T::PW] + 4 * c[3 * T::PW] + c[4 * T::PW];
-        s_pix[py * T::PWP + px] = (uint8_t)((s + 128) >> 8);
+  // ---- phase 0/1: clear the score map, stage the tile (16-byte loads; rows reflect-101) -------
+  for (int i = tid; i < B_SCORE_BYTES / 16; i += B_THREADS) ((uint4*)s_score)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < 3) s_ctr[tid] = 0;
+  unsigned tile_sum = 0;   // sum of the tile's own pixels -> level total (the reference's integral image corner value)
+  for (int it = tid; it < B_PH * (B_SP / 16); it += B_THREADS) {
+    const int py = it / (B_SP / 16), c = it - py * (B_SP / 16);
+    const int xs = x0 - 16 + 16 * c, y = y0 - 4 + py;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (xs >= 0 && xs < pitch) v = __ldg((const uint4*)(img + (size_t)reflect101(y, h) * pitch + xs));
+    *(uint4*)(s_pix + py * B_SP + 16 * c) = v;
+    if (c >= 1 && c <= B_TW / 16 && py >= 4 && py < 4 + B_TH && y < h && xs < w) {
+      const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int nb = min(4, w - (xs + 4 * k));
+        if (nb > 0) tile_sum = __dp4a(nb == 4 ? wd[k] : (wd[k] & ((1u << (8 * nb)) - 1u)), 0x01010101u, tile_sum);
       }
     }
+  }
+  tile_sum = (unsigned)warp_sum((int)tile_sum);
+  if (lane == 0 && tile_sum) atomicAdd(B.level_sum + f * ORB_MAX_LEVELS + l, (unsigned long long)tile_sum);
+  __syncthreads();
+  // columns -1 and w of the reflect-101 extension (Sobel taps of the Harris window reach them)
+  if (tid < B_PH) {
+    uint8_t* r = s_pix + tid * B_SP;
+    if (x0 == 0) r[15] = r[17];
+    const int cw = w - x0 + 16;
+    if (cw < B_SP && cw >= 2) r[cw] = r[cw - 2];
   }
   __syncthreads();
 
-  // ---- phase 2: write the level once (levels >= 1) ----------------------------------------
-  if (l > 0) {
-    uint8_t* dst = B.pyr + (size_t)f * P.pyr_frame_bytes + G.lvl_ofs;
-    const int nrow = min(T::TH, h - y0), nwords = (min(T::TW, w - x0) + 3) >> 2;
-    for (int i = tid; i < nrow * (T::TW / 4); i += K1_THREADS) {
-      int iy = i / (T::TW / 4), wx = i - iy * (T::TW / 4);
-      if (wx >= nwords) continue;
-      uint32_t v = *(const uint32_t*)(s_pix + (iy + 4) * T::PWP + 4 + wx * 4);
-      *(uint32_t*)(dst + (size_t)(y0 + iy) * G.pitch + x0 + wx * 4) = v;
-    }
-  }
-
-  // ---- phase 3: FAST-n score on the tile + 1 halo ------------------------------------------
+  // ---- phase 2: compass pretest, 8 pixels per item -------------------------------------------
   const int thr = P.fast_threshold, fn = P.fast_n;
-  for (int i = tid; i < T::SH * T::SW; i += K1_THREADS) {
-    int sy = i / T::SW, sx = i - sy * T::SW;
-    int cy = y0 - 1 + sy, cx = x0 - 1 + sx;
-    int sc = 0;
-    if (cx >= 3 && cx < w - 3 && cy >= 3 && cy < h - 3) {
-      const uint8_t* c = s_pix + (sy + 3) * T::PWP + (sx + 3);
-      sc = fast_score([&](int dy, int dx) { return (int)c[dy * T::PWP + dx]; }, thr, fn);
+  {
+    const uint32_t K = 0x64646464u;   // half(1024 + p) = 0x6400 | p
+    const __half2 thr2 = __float2half2_rn((float)thr), dthr2 = __float2half2_rn((float)max(thr, 1));
+    constexpr int NG = 18, NIT = B_SH * NG;
+    for (int it0 = 0; it0 < NIT; it0 += B_THREADS) {
+      const int it = it0 + tid;
+      uint32_t flags = 0;
+      int sy = 0, pc = 0;
+      if (it < NIT) {
+        sy = it / NG;
+        const int g = it - sy * NG;
+        pc = 8 + 8 * g;
+        const int y = y0 - 1 + sy, xs = x0 - 8 + 8 * g;
+        // valid centres: 3 <= x < w-3, 3 <= y < h-3 (ref src/orb_cpu.cpp:34-35), inside tile + 1 halo
+        int lo = max(max(0, 3 - xs), x0 - 1 - xs), hi = min(min(8, w - 3 - xs), x0 + B_TW + 1 - xs);
+        if (y >= 3 && y < h - 3 && lo < hi) {
+          const uint8_t* rc = s_pix + (sy + 3) * B_SP + pc;
+          const uint32_t m = *(const uint32_t*)(rc - 4), p = *(const uint32_t*)(rc + 8);
+          const uint2 cc = *(const uint2*)rc, tt = *(const uint2*)(rc - 3 * B_SP), bb = *(const uint2*)(rc + 3 * B_SP);
+          uint32_t C[4] = {prmt(cc.x, K, 0x4140), prmt(cc.x, K, 0x4342), prmt(cc.y, K, 0x4140), prmt(cc.y, K, 0x4342)};
+          uint32_t T[4] = {prmt(tt.x, K, 0x4140), prmt(tt.x, K, 0x4342), prmt(tt.y, K, 0x4140), prmt(tt.y, K, 0x4342)};
+          uint32_t Bm[4] = {prmt(bb.x, K, 0x4140), prmt(bb.x, K, 0x4342), prmt(bb.y, K, 0x4140), prmt(bb.y, K, 0x4342)};
+          // pixel pairs three to the left / right of each centre pair
+          const uint32_t p34 = prmt(prmt(cc.x, cc.y, 0x0043), K, 0x4140);
+          uint32_t Lf[4] = {prmt(m, K, 0x4241), prmt(prmt(m, cc.x, 0x0043), K, 0x4140), prmt(cc.x, K, 0x4241), p34};
+          uint32_t Rt[4] = {p34, prmt(cc.y, K, 0x4241), prmt(prmt(cc.y, p, 0x0043), K, 0x4140), prmt(p, K, 0x4241)};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const __half2 v0 = as_h2(T[k]), v4 = as_h2(Rt[k]), v8 = as_h2(Bm[k]), v12 = as_h2(Lf[k]), c2 = as_h2(C[k]);
+            const __half2 a = __hmin2(v0, v4), b = __hmax2(v0, v4), c = __hmin2(v8, v12), d = __hmax2(v8, v12);
+            const __half2 m1 = __hmax2(a, c), m2 = __hmin2(b, d);
+            const __half2 s2 = __hmin2(m1, m2), l2 = __hmax2(m1, m2);        // 2nd smallest / 2nd largest of the four
+            const uint32_t fb = __hge2_mask(__hsub2(s2, c2), thr2);           // >= 3 of 4 have v >= Ip + thr
+            const uint32_t fd = __hge2_mask(__hsub2(c2, l2), dthr2);          // >= 3 of 4 have v <= Ip - thr (and not brighter)
+            flags |= ((fb | fd) & 0x00020001u) << (2 * k);                    // pixel 2k -> bit 2k, pixel 2k+1 -> bit 17+2k
+          }
+          const uint32_t v8m = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+          flags &= (v8m & 0x55u) | ((v8m & 0xaau) << 16);
+        }
+      }
+      // warp-aggregated append of the passers
+      const int cnt = __popc(flags);
+      int incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total) {
+        int base = 0;
+        if (lane == 31) base = atomicAdd(&s_ctr[0], total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int off = base + incl - cnt;
+        while (flags) {
+          const int b = __ffs(flags) - 1;
+          flags &= flags - 1;
+          s_list[off++] = (uint16_t)(sy * B_SP + pc + (b & 15));
+        }
+      }
     }
-    s_tmp[i] = (uint16_t)sc;
   }
   __syncthreads();
 
-  // ---- phase 4: NMS (ties keep both, ref src/orb_cpu.cpp:126) + candidate emission ---------
+  // ---- phase 3: ring test + SAD score for the passers, one pixel per thread --------------------
+  const int n1 = s_ctr[0];
+  for (int j = tid; j < n1; j += B_THREADS) {
+    const int idx = s_list[j];
+    const int sy = idx / B_SP, pcx = idx - sy * B_SP;
+    const int sc = fast_ring_score<B_SP>(s_pix + (sy + 3) * B_SP + pcx, thr, fn);
+    if (sc) s_score[sy * B_SCP + pcx - 8] = (uint16_t)sc;
+  }
+  __syncthreads();
+
+  // ---- phase 4: NMS over the corners of the tile interior ---------------------------------------
   unsigned long long* cand = B.cand + (size_t)f * P.cand_frame_elems + G.cand_ofs;
   int* gcount = B.cand_count + f * ORB_MAX_LEVELS + l;
   const int nmsr = P.nms_radius;
-  auto pixat = [&](int yy, int xx) { return (int)s_pix[yy * T::PWP + xx]; };
-  auto emit = [&](int iy, int ix, int slot) {
-    int lx = x0 + ix, ly = y0 + iy;
+  auto pixat = [&](int yy, int xx) { return (int)s_pix[yy * B_SP + xx]; };
+  auto emit = [&](int idx, int slot) {
+    const int sy = idx / B_SP, pcx = idx - sy * B_SP;
+    const int lx = x0 + pcx - 16, ly = y0 - 1 + sy;
     uint32_t hi = 0;
-    if (P.select_policy == ORB_SELECT_HARRIS_TOP_N) {
-      float r = harris_at(pixat, iy + 4, ix + 4, B.harris_w, P.harris_k);
-      hi = ~f2ord(r);
-    }
-    if (slot < G.cand_cap)
-      cand[slot] = ((unsigned long long)hi << 32) | (unsigned)((ly << 16) | lx);
+    if (P.select_policy == ORB_SELECT_HARRIS_TOP_N) hi = ~f2ord(harris_at(pixat, sy + 3, pcx, B.harris_w, P.harris_k));
+    if (slot < G.cand_cap) cand[slot] = ((unsigned long long)hi << 32) | (unsigned)((ly << 16) | lx);
   };
-  for (int i = tid; i < T::TH * T::TW; i += K1_THREADS) {
-    int iy = i / T::TW, ix = i - iy * T::TW;
-    if (y0 + iy >= h || x0 + ix >= w) continue;
-    const uint16_t* s = s_tmp + (iy + 1) * T::SW + (ix + 1);
-    int v = s[0];
+  for (int j = tid; j < n1; j += B_THREADS) {
+    const int idx = s_list[j];
+    const int sy = idx / B_SP, pcx = idx - sy * B_SP;
+    if (sy < 1 || sy > B_TH || pcx < 16 || pcx >= 16 + B_TW) continue;   // halo positions belong to neighbours
+    const uint16_t* s = s_score + sy * B_SCP + pcx - 8;
+    const int v = s[0];
     if (v == 0) continue;
-    bool keep = true;
     if (nmsr) {
-      int m = max(max(max(s[-T::SW - 1], s[-T::SW]), max(s[-T::SW + 1], s[-1])),
-                  max(max(s[1], s[T::SW - 1]), max(s[T::SW], s[T::SW + 1])));
-      keep = v >= m;
+      int mx = max(max(max(s[-B_SCP - 1], s[-B_SCP]), max(s[-B_SCP + 1], s[-1])),
+                   max(max(s[1], s[B_SCP - 1]), max(s[B_SCP], s[B_SCP + 1])));
+      if (v < mx) continue;
     }
-    if (!keep) continue;
-    int slot = atomicAdd(&s_ctr[0], 1);
-    if (slot < T::LIST_CAP) s_list[slot] = (uint16_t)i;
-    else emit(iy, ix, atomicAdd(gcount, 1));   // list full: finish this survivor inline
+    const int slot = atomicAdd(&s_ctr[1], 1);
+    if (slot < B_SURV) s_surv[slot] = (uint16_t)idx;
+    else emit(idx, atomicAdd(gcount, 1));   // list full: finish this survivor inline
   }
   __syncthreads();
-  const int nlist = min(s_ctr[0], T::LIST_CAP);
-  if (nlist > 0) {
-    if (tid == 0) s_ctr[1] = atomicAdd(gcount, nlist);
+  const int nsurv = min(s_ctr[1], B_SURV);
+  if (nsurv > 0) {
+    if (tid == 0) s_ctr[2] = atomicAdd(gcount, nsurv);
     __syncthreads();
-    const int base = s_ctr[1];
-    for (int j = tid; j < nlist; j += K1_THREADS) {
-      int i = s_list[j];
-      int iy = i / T::TW, ix = i - iy * T::TW;
-      emit(iy, ix, base + j);
-    }
+    const int base = s_ctr[2];
+    for (int j = tid; j < nsurv; j += B_THREADS) emit(s_surv[j], base + j);
   }
   __syncthreads();
 
-  // ---- phase 5: 5x5 box sums of the level for BRIEF (replaces the int32 integral image) ----
-  for (int i = tid; i < (T::TH + 4) * T::TW; i += K1_THREADS) {
-    int r = i / T::TW, ix = i - r * T::TW;
-    const uint8_t* p = s_pix + (r + 2) * T::PWP + ix + 2;
-    s_tmp[i] = (uint16_t)(p[0] + p[1] + p[2] + p[3] + p[4]);
+  // ---- phase 5: 5x5 box sums (replaces the int32 integral image of ref src/orb_cpu.cpp:207-208) ----
+  uint16_t* s_bh = s_list;
+  const uint32_t M = 0x00ff00ffu;
+  for (int it = tid; it < (B_TH + 4) * (B_TW / 8); it += B_THREADS) {
+    const int r = it / (B_TW / 8), g = it - r * (B_TW / 8);
+    const uint8_t* rc = s_pix + (r + 2) * B_SP + 16 + 8 * g;
+    const uint32_t m = *(const uint32_t*)(rc - 4), p = *(const uint32_t*)(rc + 8);
+    const uint2 cc = *(const uint2*)rc;
+    const uint32_t w0 = prmt(m, cc.x, 0x5432), w1 = prmt(cc.x, cc.y, 0x5432), w2 = prmt(cc.y, p, 0x5432);
+    const uint32_t q0 = w0 & M, q1 = (w0 >> 8) & M, q2 = cc.x & M, q3 = (cc.x >> 8) & M, q4 = w1 & M, q5 = (w1 >> 8) & M,
+                   q6 = cc.y & M, q7 = (cc.y >> 8) & M, q8 = w2 & M, q9 = (w2 >> 8) & M;
+    uint4 o;
+    o.x = q0 + q1 + q2 + q3 + q4;
+    o.y = q1 + q2 + q3 + q4 + q5;
+    o.z = q4 + q5 + q6 + q7 + q8;
+    o.w = q5 + q6 + q7 + q8 + q9;
+    *(uint4*)(s_bh + r * B_TW + 8 * g) = o;
   }
   __syncthreads();
   uint16_t* box = B.box + (size_t)f * P.box_frame_elems + G.box_ofs;
-  {
-    const int nrow = min(T::TH, h - y0), npair = (min(T::TW, w - x0) + 1) >> 1;
-    for (int i = tid; i < nrow * (T::TW / 2); i += K1_THREADS) {
-      int iy = i / (T::TW / 2), px = i - iy * (T::TW / 2);
-      if (px >= npair) continue;
-      const uint16_t* c = s_tmp + iy * T::TW + px * 2;
-      uint32_t lo = c[0] + c[T::TW] + c[2 * T::TW] + c[3 * T::TW] + c[4 * T::TW];
-      uint32_t hi = c[1] + c[T::TW + 1] + c[2 * T::TW + 1] + c[3 * T::TW + 1] + c[4 * T::TW + 1];
-      *(uint32_t*)(box + (size_t)(y0 + iy) * G.bpitch + x0 + px * 2) = lo | (hi << 16);
-    }
+  for (int it = tid; it < B_TH * (B_TW / 8); it += B_THREADS) {
+    const int iy = it / (B_TW / 8), g = it - iy * (B_TW / 8);
+    if (y0 + iy >= h || x0 + 8 * g >= G.bpitch) continue;
+    const uint16_t* c = s_bh + iy * B_TW + 8 * g;
+    const uint4 r0 = *(const uint4*)c, r1 = *(const uint4*)(c + B_TW), r2 = *(const uint4*)(c + 2 * B_TW),
+                r3 = *(const uint4*)(c + 3 * B_TW), r4 = *(const uint4*)(c + 4 * B_TW);
+    const uint32_t a = r0.x + r1.x + r2.x + r3.x + r4.x, b = r0.y + r1.y + r2.y + r3.y + r4.y;
+    const uint32_t cc = r0.z + r1.z + r2.z + r3.z + r4.z, d = r0.w + r1.w + r2.w + r3.w + r4.w;
+    uint4 o;   // lanes (o0,o2)(o1,o3) -> natural order
+    o.x = prmt(a, b, 0x5410); o.y = prmt(a, b, 0x7632); o.z = prmt(cc, d, 0x5410); o.w = prmt(cc, d, 0x7632);
+    *(uint4*)(box + (size_t)(y0 + iy) * G.bpitch + x0 + 8 * g) = o;
   }
 }
 
@@ -403,38 +554,83 @@ __global__ void __launch_bounds__(K2_THREADS) k_select(const OrbPlan P, const Bu
 // Orientation + rotated BRIEF: one warp per keypoint.
 constexpr int K3_WARPS = 8;
 
-__device__ __forceinline__ int warp_sum(int v) {
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-  return v;
-}
-
-// sum of the u8 image over rows [ya,yb) x cols [xa,xb), whole warp cooperates
-__device__ __forceinline__ int warp_rect_sum(const uint8_t* __restrict__ img, int pitch, int xa, int xb, int ya, int yb, int lane) {
+// ---- BRIEF boxes that leave the image on the right / bottom ---------------------------------------
+// The reference's sum5x5 (src/orb_cpu.cpp:190-201) indexes its (H+1)x(W+1) integral image flat, so for centres
+// in the last two columns / rows the column overruns wrap into the next row and the row overruns fall off the
+// end (decision D7: those read 0).  What it then computes are *strip* sums of the image.  They are rebuilt here
+// from the 5x5 box-sum image (every 5th box tiles a strip) plus at most 20 remainder pixels, the whole warp
+// cooperating.  The lane_* helpers return per-lane partial sums; the caller reduces once.
+struct EdgeSrc {
+  const uint8_t* __restrict__ img; int pitch;
+  const uint16_t* __restrict__ box; int bpitch;
+  int W, H;
+  long long total;   // sum of all pixels of the level (accumulated by k_fast)
+};
+// rows [0,yb) x cols [cx-2,cx+2], 2 <= cx <= W-3, yb <= H-3
+__device__ __forceinline__ int lane_col_strip5(const EdgeSrc& E, int cx, int yb, int lane) {
+  const int J = yb / 5, rem = yb - 5 * J;
   int s = 0;
-  for (int y = ya; y < yb; y++)
-    for (int x = xa + lane; x < xb; x += 32) s += img[(size_t)y * pitch + x];
-  return warp_sum(s);
+  for (int j = lane; j < J; j += 32) s += E.box[(size_t)(5 * j + 2) * E.bpitch + cx];
+  if (lane < rem * 5) s += E.img[(size_t)(5 * J + lane / 5) * E.pitch + cx - 2 + lane % 5];
+  return s;
+}
+// rows [cy-2,cy+2] x cols [0,xb), 2 <= cy <= H-3, xb <= W-3
+__device__ __forceinline__ int lane_row_strip5(const EdgeSrc& E, int cy, int xb, int lane) {
+  const int J = xb / 5, rem = xb - 5 * J;
+  int s = 0;
+  for (int j = lane; j < J; j += 32) s += E.box[(size_t)cy * E.bpitch + 5 * j + 2];
+  if (lane < rem * 5) s += E.img[(size_t)(cy - 2 + lane % 5) * E.pitch + 5 * J + lane / 5];
+  return s;
+}
+// column 0, rows [ya,yb)
+__device__ __forceinline__ int lane_col0(const EdgeSrc& E, int ya, int yb, int lane) {
+  int s = 0;
+  for (int y = ya + lane; y < yb; y += 32) s += E.img[(size_t)y * E.pitch];
+  return s;
+}
+// full rows [ya,yb) over all W columns (rows are 16-byte aligned: 4 pixels per load, masked tail)
+__device__ __forceinline__ int lane_rows_full(const EdgeSrc& E, int ya, int yb, int lane) {
+  unsigned s = 0;
+  const int nw = (E.W + 3) >> 2;
+  for (int y = ya; y < yb; y++) {
+    const uint32_t* row = (const uint32_t*)(E.img + (size_t)y * E.pitch);
+    for (int i = lane; i < nw; i += 32) {
+      uint32_t v = row[i];
+      const int nb = E.W - 4 * i;
+      if (nb < 4) v &= (1u << (8 * nb)) - 1u;
+      s = __dp4a(v, 0x01010101u, s);
+    }
+  }
+  return (int)s;
+}
+// rows [0,yb) x cols [xa, W)  (at most 4 columns)
+__device__ __forceinline__ int lane_cols_right(const EdgeSrc& E, int xa, int yb, int lane) {
+  int s = 0;
+  for (int y = lane; y < yb; y += 32)
+    for (int x = xa; x < E.W; x++) s += E.img[(size_t)y * E.pitch + x];
+  return s;
 }
 
-// 5x5 box value of the reference's sum5x5 (src/orb_cpu.cpp:190-201) for a centre whose box leaves the
-// image on the right / bottom: the reference indexes its (H+1)x(W+1) integral image flat, so column
-// overruns wrap into the next row and row overruns fall off the end (decision D7: those read 0).
-__device__ __forceinline__ int box_edge(const uint8_t* __restrict__ img, int pitch, int W, int H, int cx, int cy, int lane) {
+__device__ __noinline__ int box_edge(const EdgeSrc& E, int cx, int cy, int lane) {
+  const int W = E.W, H = E.H;
   const int x0 = cx - 2, y0 = cy - 2, x1 = cx + 3, y1 = cy + 3;
   const bool xo = x1 > W, yo = y1 > H;
-  if (!xo) return -warp_rect_sum(img, pitch, x0, x1, 0, y0, lane);   // yo only
-  const int col = x1 - W - 1;                                        // wrapped column: 0 or 1
-  if (!yo) {
-    int s = -warp_rect_sum(img, pitch, 0, x0, y0, y1, lane);
-    if (col == 1)
-      s += (y1 + 1 <= H) ? warp_rect_sum(img, pitch, 0, 1, y0 + 1, y1 + 1, lane)
-                         : -warp_rect_sum(img, pitch, 0, 1, 0, y0 + 1, lane);
-    return s;
+  int s;
+  if (!xo) {                       // bottom rows only: -(rows [0,y0) x cols [x0,x1))
+    s = -lane_col_strip5(E, cx, y0, lane);
+  } else {
+    const int col = x1 - W - 1;    // wrapped column of the right-hand taps: 0 (reads 0) or 1 (column-0 prefix)
+    if (!yo) {                     // -(rows [y0,y1) x cols [0,x0)) + wrapped column-0 taps
+      s = -lane_row_strip5(E, cy, x0, lane);
+      if (col == 1) s += (y1 + 1 <= H) ? lane_col0(E, y0 + 1, y1 + 1, lane) : -lane_col0(E, 0, y0 + 1, lane);
+    } else {                       // bottom-right corner: +(rows [0,y0) x cols [0,x0)) - column-0 prefix, with
+      // rows [0,y0) x cols [0,x0) = level total - rows [y0,H) - (rows [0,y0) x cols [x0,W))
+      s = -lane_rows_full(E, y0, H, lane) - lane_cols_right(E, x0, y0, lane);
+      if (col == 1) s -= lane_col0(E, 0, y0 + 1, lane);
+      return (int)(E.total + (long long)warp_sum(s));
+    }
   }
-  int s = warp_rect_sum(img, pitch, 0, x0, 0, y0, lane);
-  if (col == 1) s -= warp_rect_sum(img, pitch, 0, 1, 0, y0 + 1, lane);
-  return s;
+  return warp_sum(s);
 }
 
 struct DescribeJob {             // where the keypoints of this launch come from
@@ -448,16 +644,20 @@ struct DescribeJob {             // where the keypoints of this launch come from
 __device__ __forceinline__ float orientation_of(const uint8_t* __restrict__ img, int pitch, int w, int h, int x, int y,
                                                 int pr, int lane) {
   // ref src/orb_cpu.cpp:152-178; moments are exact integers (|m| < 2^24), so integer accumulation in any
-  // order equals the reference's float accumulation
+  // order equals the reference's float accumulation.  Lane j owns patch column j - pr (and j + 32 - pr):
+  // m10 = sum_c c * colsum(c), m01 = sum_r r * I.
   if (x - pr < 0 || x + pr >= w || y - pr < 0 || y + pr >= h) return 0.0f;
   int m10 = 0, m01 = 0;
-  for (int r = -pr; r <= pr; r++) {
-    const uint8_t* row = img + (size_t)(y + r) * pitch + x;
-    for (int c = -pr + lane; c <= pr; c += 32) {
-      int I = row[c];
-      m10 += c * I;
+  for (int c = lane - pr; c <= pr; c += 32) {
+    const uint8_t* p = img + (size_t)(y - pr) * pitch + x + c;
+    int colsum = 0;
+#pragma unroll 8
+    for (int r = -pr; r <= pr; r++, p += pitch) {
+      const int I = *p;
+      colsum += I;
       m01 += r * I;
     }
+    m10 += c * colsum;
   }
   m10 = warp_sum(m10);
   m01 = warp_sum(m01);
@@ -465,17 +665,36 @@ __device__ __forceinline__ float orientation_of(const uint8_t* __restrict__ img,
 }
 
 __device__ __forceinline__ void brief_of(const uint8_t* __restrict__ img, int pitch, const uint16_t* __restrict__ box,
-                                         int bpitch, int W, int H, int kx, int ky, float angle,
-                                         const char4* __restrict__ pattern, int lane, uint32_t* out_words) {
+                                         int bpitch, int W, int H, long long total, int kx, int ky, float angle,
+                                         const float4* __restrict__ pattern, int lane, uint32_t* out_words) {
   const float c = orbm::cosf_glibc(angle), s = orbm::sinf_glibc(angle);   // ref src/orb_cpu.cpp:217-218
   uint32_t mine = 0;
+  // rotated offsets stay within +-19 (pattern radius 18.4): if every box is interior the bound rule of
+  // src/orb_cpu.cpp:240-245 can never fire and the sums are plain box-sum lookups
+  const bool interior = kx - 19 >= 2 && kx + 19 <= W - 3 && ky - 19 >= 2 && ky + 19 <= H - 3;
+  if (interior) {
+    const uint16_t* bc = box + (size_t)ky * bpitch + kx;
+#pragma unroll
+    for (int wd = 0; wd < 8; wd++) {
+      const float4 t = __ldg(pattern + wd * 32 + lane);
+      const int dx1 = orbm::lround_f(orbm::fsub(orbm::fmul(c, t.x), orbm::fmul(s, t.y)));   // :228-232
+      const int dy1 = orbm::lround_f(orbm::fadd(orbm::fmul(s, t.x), orbm::fmul(c, t.y)));
+      const int dx2 = orbm::lround_f(orbm::fsub(orbm::fmul(c, t.z), orbm::fmul(s, t.w)));
+      const int dy2 = orbm::lround_f(orbm::fadd(orbm::fmul(s, t.z), orbm::fmul(c, t.w)));
+      const int s1 = bc[dy1 * bpitch + dx1], s2 = bc[dy2 * bpitch + dx2];
+      const uint32_t word = __ballot_sync(0xffffffffu, s1 < s2);   // bit i of word wd == test 32*wd + i
+      if (lane == wd) mine = word;
+    }
+    *out_words = mine;
+    return;
+  }
+  const EdgeSrc E{img, pitch, box, bpitch, W, H, total};
   for (int wd = 0; wd < 8; wd++) {
-    char4 t = __ldg(pattern + wd * 32 + lane);
-    float x1 = (float)t.x, y1 = (float)t.y, x2 = (float)t.z, y2 = (float)t.w;
-    int cx1 = kx + orbm::lround_f(orbm::fsub(orbm::fmul(c, x1), orbm::fmul(s, y1)));   // :228-237
-    int cy1 = ky + orbm::lround_f(orbm::fadd(orbm::fmul(s, x1), orbm::fmul(c, y1)));
-    int cx2 = kx + orbm::lround_f(orbm::fsub(orbm::fmul(c, x2), orbm::fmul(s, y2)));
-    int cy2 = ky + orbm::lround_f(orbm::fadd(orbm::fmul(s, x2), orbm::fmul(c, y2)));
+    const float4 t = __ldg(pattern + wd * 32 + lane);
+    int cx1 = kx + orbm::lround_f(orbm::fsub(orbm::fmul(c, t.x), orbm::fmul(s, t.y)));
+    int cy1 = ky + orbm::lround_f(orbm::fadd(orbm::fmul(s, t.x), orbm::fmul(c, t.y)));
+    int cx2 = kx + orbm::lround_f(orbm::fsub(orbm::fmul(c, t.z), orbm::fmul(s, t.w)));
+    int cy2 = ky + orbm::lround_f(orbm::fadd(orbm::fmul(s, t.z), orbm::fmul(c, t.w)));
     // bound rule of :240-245 against the integral image dims (W+1, H+1)
     bool skip = cx1 < 2 || cy1 < 2 || cx1 > W - 1 || cy1 > H - 1 || cx2 < 2 || cy2 < 2 || cx2 > W - 1 || cy2 > H - 1;
     bool e1 = !skip && (cx1 > W - 3 || cy1 > H - 3), e2 = !skip && (cx2 > W - 3 || cy2 > H - 3);
@@ -488,17 +707,17 @@ __device__ __forceinline__ void brief_of(const uint8_t* __restrict__ img, int pi
     while (pend) {
       int src = __ffs(pend) - 1;
       pend &= pend - 1;
-      int v = box_edge(img, pitch, W, H, __shfl_sync(0xffffffffu, cx1, src), __shfl_sync(0xffffffffu, cy1, src), lane);
+      int v = box_edge(E, __shfl_sync(0xffffffffu, cx1, src), __shfl_sync(0xffffffffu, cy1, src), lane);
       if (lane == src) s1 = v;
     }
     pend = __ballot_sync(0xffffffffu, e2);
     while (pend) {
       int src = __ffs(pend) - 1;
       pend &= pend - 1;
-      int v = box_edge(img, pitch, W, H, __shfl_sync(0xffffffffu, cx2, src), __shfl_sync(0xffffffffu, cy2, src), lane);
+      int v = box_edge(E, __shfl_sync(0xffffffffu, cx2, src), __shfl_sync(0xffffffffu, cy2, src), lane);
       if (lane == src) s2 = v;
     }
-    uint32_t word = __ballot_sync(0xffffffffu, !skip && s1 < s2);   // bit i of word wd == test 32*wd + i
+    uint32_t word = __ballot_sync(0xffffffffu, !skip && s1 < s2);
     if (lane == wd) mine = word;
   }
   *out_words = mine;
@@ -539,7 +758,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_describe(const OrbPlan P, con
   if (J.mode != 2 && lane == 0) B.out_angles[o] = angle;
   if (J.mode != 1) {
     uint32_t word;
-    brief_of(img, pitch, box, G.bpitch, G.w, G.h, x, y, angle, B.pattern, lane, &word);
+    brief_of(img, pitch, box, G.bpitch, G.w, G.h, (long long)B.level_sum[f * ORB_MAX_LEVELS + l], x, y, angle, B.pattern, lane, &word);
     if (lane < 8) ((uint32_t*)B.out_desc)[o * 8 + lane] = word;
   }
   if (J.mode == 0 && lane == 0) {

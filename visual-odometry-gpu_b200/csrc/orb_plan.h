@@ -10,8 +10,9 @@ struct OrbLevel {
   int w, h;              // level size: round(W/s), round(H/s), s = (float)pow(f, l)  (ref src/orb_cpu.cpp:284-285)
   int pitch;             // bytes between rows of the u8 level image in the scratch arena (multiple of 16)
   int bpitch;            // elements between rows of the u16 5x5 box-sum image (multiple of 8)
-  int tiles_x, tiles_y;  // tile grid of the fused pyramid+FAST kernel
+  int tiles_x, tiles_y;  // tile grid of the FAST kernel (128x64 tiles)
   int tile_ofs;          // first flattened tile id of this level inside a frame
+  int a_tiles_x, a_tiles_y, a_tile_ofs;   // tile grid of the pyramid kernel (128x32 tiles, levels >= 1)
   int quota;             // keypoints kept on this level (ref src/orb.cpp:62, or nfeatures for raster-first-N)
   int cand_cap;          // candidate slots of this level
   int kept_ofs;          // offset of this level's kept list inside a frame's kept arrays
@@ -26,6 +27,7 @@ struct OrbPlan {
   int nlevels;
   int W, H;                  // level-0 size
   int tiles_per_frame;
+  int a_tiles_per_frame;
   int kept_per_frame;        // sum of kept slots over levels
   int fast_threshold, fast_n, nms_radius, patch_radius;
   int select_policy, blur_levels;

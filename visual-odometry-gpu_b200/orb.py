@@ -41,10 +41,10 @@ class Params(C.Structure):
 
 
 EXPORTS = [
-    "orb_abi_version", "orb_default_params", "orb_create", "orb_destroy", "orb_last_error", "orb_set_stream",
+    "orb_abi_version", "orb_default_params", "orb_create", "orb_destroy", "orb_last_error", "orb_set_stream", "orb_use_own_stream",
     "orb_synchronize", "orb_detect_and_compute", "orb_detect_and_compute_batch", "orb_get_level", "orb_level_size",
     "orb_level_quota", "orb_fast_detect", "orb_harris", "orb_orientations", "orb_brief", "orb_get_side_arrays",
-    "orb_get_candidates", "orb_get_harris_weights", "orb_last_launch_count", "orb_debug_eval_math", "bit_pattern_31_",
+    "orb_get_candidates", "orb_get_harris_weights", "orb_last_launch_count", "orb_set_profiling", "orb_get_stage_ms", "orb_debug_eval_math", "bit_pattern_31_",
 ]
 
 _lib = None
@@ -71,6 +71,7 @@ def load_library():
     L.orb_last_error.argtypes = [vp]
     L.orb_last_error.restype = C.c_char_p
     L.orb_set_stream.argtypes = [vp, vp]
+    L.orb_use_own_stream.argtypes = [vp]
     L.orb_synchronize.argtypes = [vp]
     L.orb_detect_and_compute.argtypes = [vp, vp, i, i, sz, i, vp, vp, vp, vp, vp]
     L.orb_detect_and_compute_batch.argtypes = [vp, vp, i, i, i, i, sz, sz, i, vp, vp, vp, vp, i]
@@ -86,6 +87,8 @@ def load_library():
     L.orb_get_harris_weights.argtypes = [vp, vp]
     L.orb_last_launch_count.argtypes = [vp]
     L.orb_debug_eval_math.argtypes = [vp, i, vp, vp, i, vp]
+    L.orb_set_profiling.argtypes = [vp, i]
+    L.orb_get_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 4), C.POINTER(C.c_int * 4)]
     _lib = L
     return L
 
@@ -137,6 +140,9 @@ class Context:
     def set_stream(self, cuda_stream):
         self._ck(self.lib.orb_set_stream(self.h, C.c_void_p(cuda_stream)))
 
+    def use_own_stream(self):
+        self._ck(self.lib.orb_use_own_stream(self.h))
+
     def synchronize(self):
         self._ck(self.lib.orb_synchronize(self.h))
 
@@ -150,6 +156,15 @@ class Context:
 
     def launch_count(self):
         return self.lib.orb_last_launch_count(self.h)
+
+    def set_profiling(self, on):
+        self._ck(self.lib.orb_set_profiling(self.h, int(on)))
+
+    def stage_ms(self):
+        """(ms[4], launches[4]) per kernel (pyramid, FAST, select, describe) since the last call; needs set_profiling(True)."""
+        ms, n = (C.c_float * 4)(), (C.c_int * 4)()
+        self._ck(self.lib.orb_get_stage_ms(self.h, C.byref(ms), C.byref(n)))
+        return list(ms), list(n)
 
     # ---- whole path -----------------------------------------------------------------------
     def detect_and_compute(self, image, cap=None):
