@@ -55,6 +55,10 @@ struct orb_ctx {
   const uint8_t* last_frames = nullptr; size_t last_stride = 0; int last_pitch = 0;
   bool last_outputs_ctx = false;
   int launches = 0;
+  // chunk pipeline: staging copies and result copies run on their own streams
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_start = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_done;
   // optional per-kernel event timing
   bool profiling = false;
   struct Span { int stage; cudaEvent_t a, b; };
@@ -312,6 +316,11 @@ void orb_destroy(orb_ctx* ctx) {
   for (void* q : ptrs) if (q) cudaFree(q);
   for (auto& sp : ctx->spans) { if (sp.a) cudaEventDestroy(sp.a); if (sp.b) cudaEventDestroy(sp.b); }
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->ev_done) cudaEventDestroy(e);
+  if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+  if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+  if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -350,6 +359,9 @@ int orb_create(const orb_params* p, orb_ctx** out) {
     CK(cudaSetDevice(p->device));
     CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
+    CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
     build_plan(ctx->p, p->max_width, p->max_height, p->nlevels, p->select_policy, -1, &ctx->max_plan);
     const OrbPlan& M = ctx->max_plan;
     // single-image stages reuse slot 0 with a 1-level plan whose kept list may hold ORB_SORT_CAP entries
@@ -494,23 +506,14 @@ int orb_detect_and_compute_batch(orb_ctx* ctx, const uint8_t* frames, int frames
   const OrbPlan& P = ctx->plan;
   ctx->launches = 0;
 
-  const uint8_t* src = frames;
-  size_t stride = frame_stride;
-  int sp = (int)pitch;
-  // the kernels read level 0 with 16-byte loads: frames must be 16-byte aligned with 16-byte multiples as row
-  // pitch and frame stride.  Host frames (and device frames that are not) go through the staging area.
-  const bool aligned = frames_on_device && ((uintptr_t)frames % 16 == 0) && pitch % 16 == 0 && frame_stride % 16 == 0;
-  if (!aligned) {
-    const cudaMemcpyKind kind = frames_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    if (frame_stride == pitch * (size_t)h && ctx->frames_slot_bytes == (size_t)ctx->frames_pitch * h) {
-      CK(cudaMemcpy2DAsync(ctx->d_frames, ctx->frames_pitch, frames, pitch, w, (size_t)h * n_frames, kind, ctx->stream));
-    } else {
-      for (int f = 0; f < n_frames; f++)
-        CK(cudaMemcpy2DAsync(ctx->d_frames + (size_t)f * ctx->frames_slot_bytes, ctx->frames_pitch,
-                             frames + (size_t)f * frame_stride, pitch, w, h, kind, ctx->stream));
-    }
-    src = ctx->d_frames; stride = ctx->frames_slot_bytes; sp = ctx->frames_pitch;
-  }
+  // The kernels read level 0 with 16-byte loads: frames must be 16-byte aligned with 16-byte multiples as row pitch
+  // and frame stride.  Host frames (and device frames that are not) go through the staging area, chunk by chunk on a
+  // copy stream so that the transfer of chunk i+1 overlaps the kernels of chunk i; host outputs leave on a third
+  // stream as soon as their chunk is described.
+  const bool direct = frames_on_device && ((uintptr_t)frames % 16 == 0) && pitch % 16 == 0 && frame_stride % 16 == 0;
+  const uint8_t* src = direct ? frames : ctx->d_frames;
+  const size_t stride = direct ? frame_stride : ctx->frames_slot_bytes;
+  const int sp = direct ? (int)pitch : ctx->frames_pitch;
   orb_keypoint* o_kps = outputs_on_device ? kps : ctx->d_kps;
   float* o_ang = outputs_on_device ? angles : ctx->d_angles;
   orb_descriptor* o_desc = outputs_on_device ? desc : ctx->d_desc;
@@ -519,9 +522,42 @@ int orb_detect_and_compute_batch(orb_ctx* ctx, const uint8_t* frames, int frames
   int total_quota = 0;
   for (int l = 0; l < P.nlevels; l++) total_quota += P.lv[l].quota;
   const int nwarps = std::min(total_quota, cap);
+  const int nchunks = (n_frames + ctx->chunk - 1) / ctx->chunk;
+  const bool piped = !direct || !outputs_on_device;
+  if (piped) {
+    while ((int)ctx->ev_in.size() < nchunks) {
+      cudaEvent_t a = nullptr, b = nullptr;
+      CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+      ctx->ev_in.push_back(a); ctx->ev_done.push_back(b);
+    }
+    // the copy streams start after whatever the caller's stream has queued so far (it may still use the staging area)
+    CK(cudaEventRecord(ctx->ev_start, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_start, 0));
+    CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_start, 0));
+  }
+  if (!direct) {
+    const cudaMemcpyKind kind = frames_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    for (int ci = 0; ci < nchunks; ci++) {
+      const int c0 = ci * ctx->chunk, nc = std::min(ctx->chunk, n_frames - c0);
+      uint8_t* dst = ctx->d_frames + (size_t)c0 * ctx->frames_slot_bytes;
+      const uint8_t* from = frames + (size_t)c0 * frame_stride;
+      if (pitch == (size_t)ctx->frames_pitch && frame_stride == ctx->frames_slot_bytes) {
+        CK(cudaMemcpyAsync(dst, from, ctx->frames_slot_bytes * nc, kind, ctx->s_h2d));      // identical layout: one linear copy
+      } else if (frame_stride == pitch * (size_t)h && ctx->frames_slot_bytes == (size_t)ctx->frames_pitch * h) {
+        CK(cudaMemcpy2DAsync(dst, ctx->frames_pitch, from, pitch, w, (size_t)h * nc, kind, ctx->s_h2d));
+      } else {
+        for (int f = 0; f < nc; f++)
+          CK(cudaMemcpy2DAsync(dst + (size_t)f * ctx->frames_slot_bytes, ctx->frames_pitch, from + (size_t)f * frame_stride,
+                               pitch, w, h, kind, ctx->s_h2d));
+      }
+      CK(cudaEventRecord(ctx->ev_in[ci], ctx->s_h2d));
+    }
+  }
 
-  for (int c0 = 0; c0 < n_frames; c0 += ctx->chunk) {
-    const int nc = std::min(ctx->chunk, n_frames - c0);
+  for (int ci = 0; ci < nchunks; ci++) {
+    const int c0 = ci * ctx->chunk, nc = std::min(ctx->chunk, n_frames - c0);
+    if (!direct) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[ci], 0));
     Bufs B;
     fill_bufs(ctx, &B);
     B.frames = src + (size_t)c0 * stride; B.frame_stride = stride; B.pitch0 = sp;
@@ -537,17 +573,22 @@ int orb_detect_and_compute_batch(orb_ctx* ctx, const uint8_t* frames, int frames
     if ((rc = launch_describe(ctx, P, B, J, nwarps, nc))) return rc;
     if (nwarps == 0) CK(cudaMemsetAsync(B.out_n, 0, sizeof(int) * nc, ctx->stream));
     ctx->last_chunk_start = c0; ctx->last_chunk_n = nc;
+    if (!outputs_on_device) {
+      CK(cudaEventRecord(ctx->ev_done[ci], ctx->stream));
+      CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[ci], 0));
+      const size_t o = (size_t)c0 * cap, nrec = (size_t)nc * cap;
+      CK(cudaMemcpyAsync(kps + o, ctx->d_kps + o, sizeof(orb_keypoint) * nrec, cudaMemcpyDeviceToHost, ctx->s_d2h));
+      CK(cudaMemcpyAsync(angles + o, ctx->d_angles + o, sizeof(float) * nrec, cudaMemcpyDeviceToHost, ctx->s_d2h));
+      CK(cudaMemcpyAsync(desc + o, ctx->d_desc + o, sizeof(orb_descriptor) * nrec, cudaMemcpyDeviceToHost, ctx->s_d2h));
+      CK(cudaMemcpyAsync(n_out + c0, ctx->d_nout + c0, sizeof(int) * nc, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    }
   }
   ctx->last_n = n_frames; ctx->last_cap = cap;
   ctx->last_frames = src; ctx->last_stride = stride; ctx->last_pitch = sp;
   ctx->last_outputs_ctx = !outputs_on_device;
 
   if (!outputs_on_device) {
-    size_t nrec = (size_t)n_frames * cap;
-    CK(cudaMemcpyAsync(kps, ctx->d_kps, sizeof(orb_keypoint) * nrec, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(angles, ctx->d_angles, sizeof(float) * nrec, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(desc, ctx->d_desc, sizeof(orb_descriptor) * nrec, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(n_out, ctx->d_nout, sizeof(int) * n_frames, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->s_d2h));
     return check_flags(ctx);
   }
   return ORB_OK;

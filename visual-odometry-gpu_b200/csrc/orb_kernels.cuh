@@ -148,7 +148,8 @@ constexpr int A_RW = A_TW + 4, A_RH = A_TH + 4;   // resized region incl. blur h
 constexpr int A_RP = 136;                          // shared pitch of resized rows (bytes)
 
 __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bufs B) {
-  __shared__ __align__(16) OrbTap s_xt[A_RW];
+  __shared__ __align__(16) uint32_t s_xs[A_RW];    // column taps, struct-of-arrays so that a thread's 4 taps are one
+  __shared__ __align__(16) uint32_t s_xa[A_RW];    // conflict-free 16-byte load: s0 | s1 << 16 and a0 | a1 << 16
   __shared__ __align__(16) OrbTap s_yt[A_RH];
   __shared__ __align__(16) uint8_t s_res[A_RH * A_RP];
   __shared__ __align__(16) uint16_t s_h[A_RH * A_TW];
@@ -166,8 +167,13 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
   const int sp = B.pitch0;
 
   for (int i = tid; i < rw + rh; i += A_THREADS) {
-    if (i < rw) s_xt[i] = B.xtab[G.xtab_ofs + reflect101(x0 - halo + i, w)];
-    else s_yt[i - rw] = B.ytab[G.ytab_ofs + reflect101(y0 - halo + i - rw, h)];
+    if (i < rw) {
+      const OrbTap tx = B.xtab[G.xtab_ofs + reflect101(x0 - halo + i, w)];
+      s_xs[i] = (uint32_t)tx.s0 | ((uint32_t)tx.s1 << 16);
+      s_xa[i] = (uint32_t)(uint16_t)tx.a0 | ((uint32_t)(uint16_t)tx.a1 << 16);
+    } else {
+      s_yt[i - rw] = B.ytab[G.ytab_ofs + reflect101(y0 - halo + i - rw, h)];
+    }
   }
   __syncthreads();
 
@@ -179,12 +185,14 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
     const OrbTap ty = s_yt[ry];
     const uint8_t* r0 = src + (size_t)ty.s0 * sp;
     const uint8_t* r1 = src + (size_t)ty.s1 * sp;
+    const uint4 xs4 = *(const uint4*)(s_xs + 4 * gx), xa4 = *(const uint4*)(s_xa + 4 * gx);
+    const uint32_t xs[4] = {xs4.x, xs4.y, xs4.z, xs4.w}, xa[4] = {xa4.x, xa4.y, xa4.z, xa4.w};
     uint32_t word = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const OrbTap tx = s_xt[4 * gx + j];
-      int h0 = __ldg(r0 + tx.s0) * tx.a0 + __ldg(r0 + tx.s1) * tx.a1;
-      int h1 = __ldg(r1 + tx.s0) * tx.a0 + __ldg(r1 + tx.s1) * tx.a1;
+      const int s0 = xs[j] & 0xffff, s1 = xs[j] >> 16, a0 = xa[j] & 0xffff, a1 = xa[j] >> 16;
+      int h0 = __ldg(r0 + s0) * a0 + __ldg(r0 + s1) * a1;
+      int h1 = __ldg(r1 + s0) * a0 + __ldg(r1 + s1) * a1;
       int v = (((ty.a0 * (h0 >> 4)) >> 16) + ((ty.a1 * (h1 >> 4)) >> 16) + 2) >> 2;
       word |= (uint32_t)min(v, 255) << (8 * j);
     }
@@ -311,65 +319,74 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
   __syncthreads();
 
   // ---- phase 2: compass pretest, 8 pixels per item -------------------------------------------
+  // Thread (g, rt) owns column group g (8 pixels from x0 - 8 + 8g) on rows rt, rt+14, ...; the column validity mask
+  // is loop invariant.  Passers of all its rows are appended with one warp scan + one shared atomic per warp.
   const int thr = P.fast_threshold, fn = P.fast_n;
   {
+    constexpr int NG = 18, NRT = 14, NK = (B_SH + NRT - 1) / NRT;
     const uint32_t K = 0x64646464u;   // half(1024 + p) = 0x6400 | p
     const __half2 thr2 = __float2half2_rn((float)thr), dthr2 = __float2half2_rn((float)max(thr, 1));
-    constexpr int NG = 18, NIT = B_SH * NG;
-    for (int it0 = 0; it0 < NIT; it0 += B_THREADS) {
-      const int it = it0 + tid;
+    const int g = tid % NG, rt = tid / NG;
+    const int pc = 8 + 8 * g, xs = x0 - 8 + 8 * g;
+    // valid centres: 3 <= x < w-3 (ref src/orb_cpu.cpp:35), inside tile + 1 halo column on each side
+    const int lo = max(max(0, 3 - xs), x0 - 1 - xs), hi = min(min(8, w - 3 - xs), x0 + B_TW + 1 - xs);
+    uint32_t vmask = 0;
+    if (lo < hi && rt < NRT) {
+      const uint32_t v8m = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+      vmask = (v8m & 0x55u) | ((v8m & 0xaau) << 16);       // pixel 2k -> bit 2k, pixel 2k+1 -> bit 17+2k
+    }
+    uint32_t fl[NK];
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+      const int sy = rt + NRT * k, y = y0 - 1 + sy;
       uint32_t flags = 0;
-      int sy = 0, pc = 0;
-      if (it < NIT) {
-        sy = it / NG;
-        const int g = it - sy * NG;
-        pc = 8 + 8 * g;
-        const int y = y0 - 1 + sy, xs = x0 - 8 + 8 * g;
-        // valid centres: 3 <= x < w-3, 3 <= y < h-3 (ref src/orb_cpu.cpp:34-35), inside tile + 1 halo
-        int lo = max(max(0, 3 - xs), x0 - 1 - xs), hi = min(min(8, w - 3 - xs), x0 + B_TW + 1 - xs);
-        if (y >= 3 && y < h - 3 && lo < hi) {
-          const uint8_t* rc = s_pix + (sy + 3) * B_SP + pc;
-          const uint32_t m = *(const uint32_t*)(rc - 4), p = *(const uint32_t*)(rc + 8);
-          const uint2 cc = *(const uint2*)rc, tt = *(const uint2*)(rc - 3 * B_SP), bb = *(const uint2*)(rc + 3 * B_SP);
-          uint32_t C[4] = {prmt(cc.x, K, 0x4140), prmt(cc.x, K, 0x4342), prmt(cc.y, K, 0x4140), prmt(cc.y, K, 0x4342)};
-          uint32_t T[4] = {prmt(tt.x, K, 0x4140), prmt(tt.x, K, 0x4342), prmt(tt.y, K, 0x4140), prmt(tt.y, K, 0x4342)};
-          uint32_t Bm[4] = {prmt(bb.x, K, 0x4140), prmt(bb.x, K, 0x4342), prmt(bb.y, K, 0x4140), prmt(bb.y, K, 0x4342)};
-          // pixel pairs three to the left / right of each centre pair
-          const uint32_t p34 = prmt(prmt(cc.x, cc.y, 0x0043), K, 0x4140);
-          uint32_t Lf[4] = {prmt(m, K, 0x4241), prmt(prmt(m, cc.x, 0x0043), K, 0x4140), prmt(cc.x, K, 0x4241), p34};
-          uint32_t Rt[4] = {p34, prmt(cc.y, K, 0x4241), prmt(prmt(cc.y, p, 0x0043), K, 0x4140), prmt(p, K, 0x4241)};
+      if (vmask && sy < B_SH && y >= 3 && y < h - 3) {      // 3 <= y < h-3 (ref src/orb_cpu.cpp:34)
+        const uint8_t* rc = s_pix + (sy + 3) * B_SP + pc;
+        const uint32_t m = *(const uint32_t*)(rc - 4), p = *(const uint32_t*)(rc + 8);
+        const uint2 cc = *(const uint2*)rc, tt = *(const uint2*)(rc - 3 * B_SP), bb = *(const uint2*)(rc + 3 * B_SP);
+        const uint32_t C[4] = {prmt(cc.x, K, 0x4140), prmt(cc.x, K, 0x4342), prmt(cc.y, K, 0x4140), prmt(cc.y, K, 0x4342)};
+        const uint32_t T[4] = {prmt(tt.x, K, 0x4140), prmt(tt.x, K, 0x4342), prmt(tt.y, K, 0x4140), prmt(tt.y, K, 0x4342)};
+        const uint32_t Bm[4] = {prmt(bb.x, K, 0x4140), prmt(bb.x, K, 0x4342), prmt(bb.y, K, 0x4140), prmt(bb.y, K, 0x4342)};
+        // pixel pairs three to the left / right of each centre pair
+        const uint32_t p34 = prmt(prmt(cc.x, cc.y, 0x0043), K, 0x4140);
+        const uint32_t Lf[4] = {prmt(m, K, 0x4241), prmt(prmt(m, cc.x, 0x0043), K, 0x4140), prmt(cc.x, K, 0x4241), p34};
+        const uint32_t Rt[4] = {p34, prmt(cc.y, K, 0x4241), prmt(prmt(cc.y, p, 0x0043), K, 0x4140), prmt(p, K, 0x4241)};
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const __half2 v0 = as_h2(T[k]), v4 = as_h2(Rt[k]), v8 = as_h2(Bm[k]), v12 = as_h2(Lf[k]), c2 = as_h2(C[k]);
-            const __half2 a = __hmin2(v0, v4), b = __hmax2(v0, v4), c = __hmin2(v8, v12), d = __hmax2(v8, v12);
-            const __half2 m1 = __hmax2(a, c), m2 = __hmin2(b, d);
-            const __half2 s2 = __hmin2(m1, m2), l2 = __hmax2(m1, m2);        // 2nd smallest / 2nd largest of the four
-            const uint32_t fb = __hge2_mask(__hsub2(s2, c2), thr2);           // >= 3 of 4 have v >= Ip + thr
-            const uint32_t fd = __hge2_mask(__hsub2(c2, l2), dthr2);          // >= 3 of 4 have v <= Ip - thr (and not brighter)
-            flags |= ((fb | fd) & 0x00020001u) << (2 * k);                    // pixel 2k -> bit 2k, pixel 2k+1 -> bit 17+2k
-          }
-          const uint32_t v8m = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-          flags &= (v8m & 0x55u) | ((v8m & 0xaau) << 16);
+        for (int q = 0; q < 4; q++) {
+          const __half2 v0 = as_h2(T[q]), v4 = as_h2(Rt[q]), v8 = as_h2(Bm[q]), v12 = as_h2(Lf[q]), c2 = as_h2(C[q]);
+          const __half2 a = __hmin2(v0, v4), b = __hmax2(v0, v4), c = __hmin2(v8, v12), d = __hmax2(v8, v12);
+          const __half2 m1 = __hmax2(a, c), m2 = __hmin2(b, d);
+          const __half2 s2 = __hmin2(m1, m2), l2 = __hmax2(m1, m2);        // 2nd smallest / 2nd largest of the four
+          const uint32_t fb = __hge2_mask(__hsub2(s2, c2), thr2);           // >= 3 of 4 have v >= Ip + thr
+          const uint32_t fd = __hge2_mask(__hsub2(c2, l2), dthr2);          // >= 3 of 4 have v <= Ip - thr (and not brighter)
+          flags |= ((fb | fd) & 0x00020001u) << (2 * q);
         }
+        flags &= vmask;
       }
-      // warp-aggregated append of the passers
-      const int cnt = __popc(flags);
-      int incl = cnt;
+      fl[k] = flags;
+      cnt += __popc(flags);
+    }
+    int incl = cnt;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
-      }
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      if (total) {
-        int base = 0;
-        if (lane == 31) base = atomicAdd(&s_ctr[0], total);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        int off = base + incl - cnt;
+    for (int d = 1; d < 32; d <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total) {
+      int base = 0;
+      if (lane == 31) base = atomicAdd(&s_ctr[0], total);
+      base = __shfl_sync(0xffffffffu, base, 31);
+      int off = base + incl - cnt;
+#pragma unroll
+      for (int k = 0; k < NK; k++) {
+        uint32_t flags = fl[k];
+        const int rowbase = (rt + NRT * k) * B_SP + pc;
         while (flags) {
           const int b = __ffs(flags) - 1;
           flags &= flags - 1;
-          s_list[off++] = (uint16_t)(sy * B_SP + pc + (b & 15));
+          s_list[off++] = (uint16_t)(rowbase + (b & 15));
         }
       }
     }
@@ -641,27 +658,47 @@ struct DescribeJob {             // where the keypoints of this launch come from
   int list_n;
 };
 
-__device__ __forceinline__ float orientation_of(const uint8_t* __restrict__ img, int pitch, int w, int h, int x, int y,
-                                                int pr, int lane) {
-  // ref src/orb_cpu.cpp:152-178; moments are exact integers (|m| < 2^24), so integer accumulation in any
-  // order equals the reference's float accumulation.  Lane j owns patch column j - pr (and j + 32 - pr):
-  // m10 = sum_c c * colsum(c), m01 = sum_r r * I.
-  if (x - pr < 0 || x + pr >= w || y - pr < 0 || y + pr >= h) return 0.0f;
+// Intensity-centroid moments of the (2*pr+1)^2 patch, ref src/orb_cpu.cpp:158-176.  Moments are exact integers
+// (|m| < 2^24), so integer accumulation in any order equals the reference's float accumulation.  Lane j owns patch
+// column j - pr (and j + 32 - pr): m10 = sum_c c * colsum(c), m01 = sum_r r * I.  PR > 0 fixes the radius at
+// compile time so that all row loads of a lane are independent and in flight together.
+template <int PR>
+__device__ __forceinline__ void patch_moments(const uint8_t* __restrict__ img, int pitch, int x, int y, int pr_rt, int lane,
+                                              int* m10_out, int* m01_out) {
+  const int pr = PR > 0 ? PR : pr_rt;
   int m10 = 0, m01 = 0;
   for (int c = lane - pr; c <= pr; c += 32) {
     const uint8_t* p = img + (size_t)(y - pr) * pitch + x + c;
     int colsum = 0;
-#pragma unroll 8
-    for (int r = -pr; r <= pr; r++, p += pitch) {
-      const int I = *p;
-      colsum += I;
-      m01 += r * I;
+    if (PR > 0) {
+#pragma unroll
+      for (int r = -PR; r <= PR; r++) {
+        const int I = p[(size_t)(r + PR) * pitch];
+        colsum += I;
+        m01 += r * I;
+      }
+    } else {
+#pragma unroll 4
+      for (int r = -pr; r <= pr; r++, p += pitch) {
+        const int I = *p;
+        colsum += I;
+        m01 += r * I;
+      }
     }
     m10 += c * colsum;
   }
-  m10 = warp_sum(m10);
-  m01 = warp_sum(m01);
-  return orbm::atan2f_glibc((float)m01, (float)m10);
+  *m10_out = warp_sum(m10);
+  *m01_out = warp_sum(m01);
+}
+
+__device__ __forceinline__ float orientation_of(const uint8_t* __restrict__ img, int pitch, int w, int h, int x, int y,
+                                                int pr, int lane) {
+  if (x - pr < 0 || x + pr >= w || y - pr < 0 || y + pr >= h) return 0.0f;   // ref src/orb_cpu.cpp:152-156
+  int m10, m01;
+  if (pr == 15) patch_moments<15>(img, pitch, x, y, pr, lane, &m10, &m01);      // patch 31 (include/orb.hpp:12)
+  else if (pr == 4) patch_moments<4>(img, pitch, x, y, pr, lane, &m10, &m01);   // patch 9 (include/orb_cpu.hpp:6)
+  else patch_moments<0>(img, pitch, x, y, pr, lane, &m10, &m01);
+  return orbm::atan2f_glibc((float)m01, (float)m10);                            // :178
 }
 
 __device__ __forceinline__ void brief_of(const uint8_t* __restrict__ img, int pitch, const uint16_t* __restrict__ box,
