@@ -43,7 +43,7 @@ struct orb_ctx {
   // arena
   uint8_t* d_frames = nullptr; size_t frames_slot_bytes = 0; int frames_pitch = 0;
   uint8_t* d_pyr = nullptr; uint16_t* d_box = nullptr; unsigned long long* d_cand = nullptr;
-  int* d_cand_count = nullptr; unsigned long long* d_level_sum = nullptr; uint32_t* d_kept_xy = nullptr; float* d_kept_r = nullptr; int* d_kept_count = nullptr;
+  int* d_cand_count = nullptr; unsigned long long* d_level_sum = nullptr; int* d_edge = nullptr; size_t zero_bytes_per_frame = 0; uint32_t* d_kept_xy = nullptr; float* d_kept_r = nullptr; int* d_kept_count = nullptr;
   OrbTap *d_xtab = nullptr, *d_ytab = nullptr;
   float* d_harris_w = nullptr; float4* d_pattern = nullptr; int* d_flags = nullptr; int* h_flags = nullptr;
   orb_keypoint* d_kps = nullptr; float* d_angles = nullptr; orb_descriptor* d_desc = nullptr; int* d_nout = nullptr;
@@ -135,7 +135,7 @@ void build_plan(const orb_params& p, int W, int H, int nlevels, int policy, int 
   P->fast_threshold = p.fast_threshold; P->fast_n = p.fast_n;
   P->nms_radius = p.nms_window / 2; P->patch_radius = p.orient_patch / 2;
   P->select_policy = policy; P->blur_levels = p.blur_levels; P->harris_k = p.harris_k;
-  int tile = 0, atile = 0, kept = 0, xo = 0, yo = 0;
+  int tile = 0, atile = 0, kept = 0, xo = 0, yo = 0, eo = 0;
   unsigned long long lv = 0, bx = 0, cd = 0;
   for (int l = 0; l < nlevels; l++) {
     OrbLevel& G = P->lv[l];
@@ -155,12 +155,13 @@ void build_plan(const orb_params& p, int W, int H, int nlevels, int policy, int 
     G.cand_cap = std::max(2048, G.w * G.h / 8);
     G.kept_ofs = kept; kept += align_up(std::max(G.quota, 1), 4);
     G.xtab_ofs = xo; G.ytab_ofs = yo; xo += G.w; yo += G.h;
+    G.edge_ofs = eo; G.edge_w = align_up(G.w, 4); eo += G.edge_w + align_up(G.h, 4);
     G.scale = level_scale(p.scale_factor, l);
     G.lvl_ofs = lv; if (l > 0) lv += (unsigned long long)align_up(G.h * G.pitch, 256);
     G.box_ofs = bx; bx += (unsigned long long)align_up((G.h + 1) * G.bpitch, 128);
     G.cand_ofs = cd; cd += (unsigned long long)align_up(G.cand_cap, 32);
   }
-  P->tiles_per_frame = tile; P->a_tiles_per_frame = atile; P->kept_per_frame = kept;
+  P->tiles_per_frame = tile; P->a_tiles_per_frame = atile; P->kept_per_frame = kept; P->edge_frame_elems = eo;
   P->pyr_frame_bytes = std::max<unsigned long long>(lv, 256); P->box_frame_elems = bx; P->cand_frame_elems = cd;
 }
 
@@ -195,7 +196,7 @@ int get_plan(orb_ctx* ctx, int w, int h) {
 void fill_bufs(orb_ctx* ctx, Bufs* B) {
   memset(B, 0, sizeof(*B));
   B->pyr = ctx->d_pyr; B->box = ctx->d_box; B->cand = ctx->d_cand; B->cand_count = ctx->d_cand_count;
-  B->level_sum = ctx->d_level_sum; B->kept_xy = ctx->d_kept_xy; B->kept_r = ctx->d_kept_r; B->kept_count = ctx->d_kept_count;
+  B->level_sum = ctx->d_level_sum; B->edge = ctx->d_edge; B->kept_xy = ctx->d_kept_xy; B->kept_r = ctx->d_kept_r; B->kept_count = ctx->d_kept_count;
   B->xtab = ctx->d_xtab; B->ytab = ctx->d_ytab; B->harris_w = ctx->d_harris_w; B->pattern = ctx->d_pattern;
   B->flags = ctx->d_flags;
 }
@@ -219,7 +220,7 @@ struct StageTimer {
 
 int launch_pyramid_fast(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, int nframes) {
   // candidate counters and level totals of the whole chunk arena (one small memset)
-  CK(cudaMemsetAsync(ctx->d_cand_count, 0, (sizeof(int) + sizeof(unsigned long long)) * ORB_MAX_LEVELS * ctx->chunk, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_cand_count, 0, ctx->zero_bytes_per_frame * ctx->chunk, ctx->stream));
   if (P.a_tiles_per_frame > 0) {
     StageTimer t(ctx, 0);
     orbk::k_pyramid<<<dim3(P.a_tiles_per_frame, nframes), orbk::A_THREADS, 0, ctx->stream>>>(P, B);
@@ -383,8 +384,14 @@ int orb_create(const orb_params* p, orb_ctx** out) {
     CK(cudaMalloc(&ctx->d_pyr, (size_t)M.pyr_frame_bytes * C));
     CK(cudaMalloc(&ctx->d_box, (size_t)M.box_frame_elems * 2 * C));
     CK(cudaMalloc(&ctx->d_cand, (size_t)M.cand_frame_elems * 8 * C));
-    CK(cudaMalloc(&ctx->d_cand_count, (sizeof(int) + sizeof(unsigned long long)) * ORB_MAX_LEVELS * C));
-    ctx->d_level_sum = (unsigned long long*)(ctx->d_cand_count + (size_t)ORB_MAX_LEVELS * C);   // zeroed by the same memset
+    // per-chunk accumulators, zeroed by one memset per chunk: candidate counters | level totals | BRIEF border tables
+    {
+      const int edge_max = std::max(M.edge_frame_elems, S.edge_frame_elems);
+      ctx->zero_bytes_per_frame = (sizeof(int) + sizeof(unsigned long long)) * ORB_MAX_LEVELS + sizeof(int) * (size_t)edge_max;
+      CK(cudaMalloc(&ctx->d_cand_count, ctx->zero_bytes_per_frame * C));
+      ctx->d_level_sum = (unsigned long long*)(ctx->d_cand_count + (size_t)ORB_MAX_LEVELS * C);
+      ctx->d_edge = (int*)(ctx->d_level_sum + (size_t)ORB_MAX_LEVELS * C);
+    }
     CK(cudaMalloc(&ctx->d_kept_count, sizeof(int) * ORB_MAX_LEVELS * C));
     CK(cudaMalloc(&ctx->d_kept_xy, sizeof(uint32_t) * (size_t)kept_per_frame * C));
     CK(cudaMalloc(&ctx->d_kept_r, sizeof(float) * (size_t)kept_per_frame * C));

@@ -33,6 +33,7 @@ struct Bufs {
   unsigned long long* cand;      // [chunk][cand_frame_elems]
   int* cand_count;               // [chunk][ORB_MAX_LEVELS]
   unsigned long long* level_sum; // [chunk][ORB_MAX_LEVELS] sum of all pixels of the level (BRIEF corner boxes)
+  int* edge;                     // [chunk][edge_frame_elems] strip sums for BRIEF boxes that leave the image
   uint32_t* kept_xy;             // [chunk][kept_per_frame]   (y << 16 | x), level space
   float* kept_r;                 // [chunk][kept_per_frame]
   int* kept_count;               // [chunk][ORB_MAX_LEVELS]
@@ -460,6 +461,38 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
     *(uint4*)(s_bh + r * B_TW + 8 * g) = o;
   }
   __syncthreads();
+  // ---- phase 6: strip sums for BRIEF boxes that leave the image on the right / bottom (decision D7) ------
+  //   ey[cx] = sum of rows [0,h-4) x cols [cx-2,cx+2]   (ey[0] instead holds column 0 over rows [0,h-4))
+  //   rs[y]  = sum of row y over cols [0,w-4)
+  // each tile adds its share; k_describe turns them into the values of the reference's wrapped integral taps.
+  {
+    int* ey = B.edge + (size_t)f * P.edge_frame_elems + G.edge_ofs;
+    int* rs = ey + G.edge_w;
+    if (tid < B_TW) {
+      const int x = x0 + tid, rows = min(B_TH, h - 4 - y0);
+      if (rows > 0 && x >= 2 && x <= w - 3) {
+        const int j = tid & 7;   // u16 slot of pixel j inside its group of 8: lanes (o0,o2)(o1,o3)(o4,o6)(o5,o7)
+        const uint16_t* c = s_bh + 2 * B_TW + (tid & ~7) + ((j >> 2) * 2 + (j & 1)) * 2 + ((j >> 1) & 1);
+        int acc = 0;
+        for (int r = 0; r < rows; r++) acc += c[r * B_TW];
+        atomicAdd(ey + x, acc);
+      }
+    } else if (tid < B_TW + B_TH) {
+      const int iy = tid - B_TW, y = y0 + iy;
+      if (y < h) {
+        const int ncol = min(B_TW, w - 4 - x0);
+        const uint8_t* r = s_pix + (iy + 4) * B_SP + 16;
+        unsigned acc = 0;
+        for (int c = 0; c < ncol; c += 4) {
+          uint32_t v = *(const uint32_t*)(r + c);
+          if (ncol - c < 4) v &= (1u << (8 * (ncol - c))) - 1u;
+          acc = __dp4a(v, 0x01010101u, acc);
+        }
+        if (ncol > 0) atomicAdd(rs + y, (int)acc);
+        if (x0 == 0 && y < h - 4) atomicAdd(ey, (int)r[0]);
+      }
+    }
+  }
   uint16_t* box = B.box + (size_t)f * P.box_frame_elems + G.box_ofs;
   for (int it = tid; it < B_TH * (B_TW / 8); it += B_THREADS) {
     const int iy = it / (B_TW / 8), g = it - iy * (B_TW / 8);
@@ -579,26 +612,39 @@ constexpr int K3_WARPS = 8;
 // cooperating.  The lane_* helpers return per-lane partial sums; the caller reduces once.
 struct EdgeSrc {
   const uint8_t* __restrict__ img; int pitch;
-  const uint16_t* __restrict__ box; int bpitch;
   int W, H;
-  long long total;   // sum of all pixels of the level (accumulated by k_fast)
+  long long total;              // sum of all pixels of the level            (accumulated by k_fast)
+  const int* __restrict__ ey;   // ey[cx]: rows [0,H-4) x cols [cx-2,cx+2]; ey[0]: column 0 over rows [0,H-4)
+  const int* __restrict__ rs;   // rs[y]: row y over cols [0,W-4)
 };
-// rows [0,yb) x cols [cx-2,cx+2], 2 <= cx <= W-3, yb <= H-3
-__device__ __forceinline__ int lane_col_strip5(const EdgeSrc& E, int cx, int yb, int lane) {
-  const int J = yb / 5, rem = yb - 5 * J;
-  int s = 0;
-  for (int j = lane; j < J; j += 32) s += E.box[(size_t)(5 * j + 2) * E.bpitch + cx];
-  if (lane < rem * 5) s += E.img[(size_t)(5 * J + lane / 5) * E.pitch + cx - 2 + lane % 5];
-  return s;
+
+// ---- BRIEF boxes that leave the image on the right / bottom ---------------------------------------
+// The reference's sum5x5 (src/orb_cpu.cpp:190-201) indexes its (H+1)x(W+1) integral image flat, so for centres
+// in the last two columns / rows the column overruns wrap into the next row and the row overruns fall off the
+// end (decision D7: those read 0).  What its four taps then add up to are *strip* sums of the image:
+//   bottom rows only : -(rows [0,cy-2) x cols [cx-2,cx+2])
+//   right cols only  : -(rows [cy-2,cy+2] x cols [0,cx-2)) + wrapped column-0 taps (when cx == W-1)
+//   corner           : +(rows [0,cy-2) x cols [0,cx-2)) - column-0 prefix
+// The first two come from the strip tables k_fast accumulates (+ at most 15 pixels), one lane per box.
+__device__ __forceinline__ int box_edge_lane(const EdgeSrc& E, int cx, int cy) {
+  const int W = E.W, H = E.H, p = E.pitch;
+  if (cx <= W - 3) {
+    int s = E.ey[cx];
+    if (cy == H - 1) { const uint8_t* r = E.img + (size_t)(H - 4) * p + cx - 2; s += r[0] + r[1] + r[2] + r[3] + r[4]; }
+    return -s;
+  }
+  int s = E.rs[cy - 2] + E.rs[cy - 1] + E.rs[cy] + E.rs[cy + 1] + E.rs[cy + 2];
+  if (cx == W - 1) {
+    const uint8_t* c = E.img + (size_t)(cy - 2) * p + (W - 4);
+    s += c[0] + c[p] + c[2 * p] + c[3 * p] + c[4 * p];
+    int t;
+    if (cy + 4 <= H) { const uint8_t* z = E.img + (size_t)(cy - 1) * p; t = z[0] + z[p] + z[2 * p] + z[3 * p] + z[4 * p]; }
+    else t = -E.ey[0];
+    return t - s;
+  }
+  return -s;
 }
-// rows [cy-2,cy+2] x cols [0,xb), 2 <= cy <= H-3, xb <= W-3
-__device__ __forceinline__ int lane_row_strip5(const EdgeSrc& E, int cy, int xb, int lane) {
-  const int J = xb / 5, rem = xb - 5 * J;
-  int s = 0;
-  for (int j = lane; j < J; j += 32) s += E.box[(size_t)cy * E.bpitch + 5 * j + 2];
-  if (lane < rem * 5) s += E.img[(size_t)(cy - 2 + lane % 5) * E.pitch + 5 * J + lane / 5];
-  return s;
-}
+
 // column 0, rows [ya,yb)
 __device__ __forceinline__ int lane_col0(const EdgeSrc& E, int ya, int yb, int lane) {
   int s = 0;
@@ -627,27 +673,13 @@ __device__ __forceinline__ int lane_cols_right(const EdgeSrc& E, int xa, int yb,
     for (int x = xa; x < E.W; x++) s += E.img[(size_t)y * E.pitch + x];
   return s;
 }
-
-__device__ __noinline__ int box_edge(const EdgeSrc& E, int cx, int cy, int lane) {
-  const int W = E.W, H = E.H;
-  const int x0 = cx - 2, y0 = cy - 2, x1 = cx + 3, y1 = cy + 3;
-  const bool xo = x1 > W, yo = y1 > H;
-  int s;
-  if (!xo) {                       // bottom rows only: -(rows [0,y0) x cols [x0,x1))
-    s = -lane_col_strip5(E, cx, y0, lane);
-  } else {
-    const int col = x1 - W - 1;    // wrapped column of the right-hand taps: 0 (reads 0) or 1 (column-0 prefix)
-    if (!yo) {                     // -(rows [y0,y1) x cols [0,x0)) + wrapped column-0 taps
-      s = -lane_row_strip5(E, cy, x0, lane);
-      if (col == 1) s += (y1 + 1 <= H) ? lane_col0(E, y0 + 1, y1 + 1, lane) : -lane_col0(E, 0, y0 + 1, lane);
-    } else {                       // bottom-right corner: +(rows [0,y0) x cols [0,x0)) - column-0 prefix, with
-      // rows [0,y0) x cols [0,x0) = level total - rows [y0,H) - (rows [0,y0) x cols [x0,W))
-      s = -lane_rows_full(E, y0, H, lane) - lane_cols_right(E, x0, y0, lane);
-      if (col == 1) s -= lane_col0(E, 0, y0 + 1, lane);
-      return (int)(E.total + (long long)warp_sum(s));
-    }
-  }
-  return warp_sum(s);
+// bottom-right corner box (cx > W-3 and cy > H-3), whole warp cooperates:
+// rows [0,y0) x cols [0,x0) = level total - rows [y0,H) - (rows [0,y0) x cols [x0,W))
+__device__ __noinline__ int box_corner(const EdgeSrc& E, int cx, int cy, int lane) {
+  const int x0 = cx - 2, y0 = cy - 2, col = cx + 3 - E.W - 1;
+  int s = -lane_rows_full(E, y0, E.H, lane) - lane_cols_right(E, x0, y0, lane);
+  if (col == 1) s -= lane_col0(E, 0, y0 + 1, lane);
+  return (int)(E.total + (long long)warp_sum(s));
 }
 
 struct DescribeJob {             // where the keypoints of this launch come from
@@ -702,8 +734,9 @@ __device__ __forceinline__ float orientation_of(const uint8_t* __restrict__ img,
 }
 
 __device__ __forceinline__ void brief_of(const uint8_t* __restrict__ img, int pitch, const uint16_t* __restrict__ box,
-                                         int bpitch, int W, int H, long long total, int kx, int ky, float angle,
+                                         int bpitch, const EdgeSrc& E, int kx, int ky, float angle,
                                          const float4* __restrict__ pattern, int lane, uint32_t* out_words) {
+  const int W = E.W, H = E.H;
   const float c = orbm::cosf_glibc(angle), s = orbm::sinf_glibc(angle);   // ref src/orb_cpu.cpp:217-218
   uint32_t mine = 0;
   // rotated offsets stay within +-19 (pattern radius 18.4): if every box is interior the bound rule of
@@ -725,7 +758,6 @@ __device__ __forceinline__ void brief_of(const uint8_t* __restrict__ img, int pi
     *out_words = mine;
     return;
   }
-  const EdgeSrc E{img, pitch, box, bpitch, W, H, total};
   for (int wd = 0; wd < 8; wd++) {
     const float4 t = __ldg(pattern + wd * 32 + lane);
     int cx1 = kx + orbm::lround_f(orbm::fsub(orbm::fmul(c, t.x), orbm::fmul(s, t.y)));
@@ -733,25 +765,25 @@ __device__ __forceinline__ void brief_of(const uint8_t* __restrict__ img, int pi
     int cx2 = kx + orbm::lround_f(orbm::fsub(orbm::fmul(c, t.z), orbm::fmul(s, t.w)));
     int cy2 = ky + orbm::lround_f(orbm::fadd(orbm::fmul(s, t.z), orbm::fmul(c, t.w)));
     // bound rule of :240-245 against the integral image dims (W+1, H+1)
-    bool skip = cx1 < 2 || cy1 < 2 || cx1 > W - 1 || cy1 > H - 1 || cx2 < 2 || cy2 < 2 || cx2 > W - 1 || cy2 > H - 1;
-    bool e1 = !skip && (cx1 > W - 3 || cy1 > H - 3), e2 = !skip && (cx2 > W - 3 || cy2 > H - 3);
+    const bool skip = cx1 < 2 || cy1 < 2 || cx1 > W - 1 || cy1 > H - 1 || cx2 < 2 || cy2 < 2 || cx2 > W - 1 || cy2 > H - 1;
+    const bool k1 = !skip && cx1 > W - 3 && cy1 > H - 3, k2 = !skip && cx2 > W - 3 && cy2 > H - 3;   // corner boxes
     int s1 = 0, s2 = 0;
     if (!skip) {
-      if (!e1) s1 = box[(size_t)cy1 * bpitch + cx1];
-      if (!e2) s2 = box[(size_t)cy2 * bpitch + cx2];
+      if (!k1) s1 = (cx1 > W - 3 || cy1 > H - 3) ? box_edge_lane(E, cx1, cy1) : (int)box[(size_t)cy1 * bpitch + cx1];
+      if (!k2) s2 = (cx2 > W - 3 || cy2 > H - 3) ? box_edge_lane(E, cx2, cy2) : (int)box[(size_t)cy2 * bpitch + cx2];
     }
-    unsigned pend = __ballot_sync(0xffffffffu, e1);
+    unsigned pend = __ballot_sync(0xffffffffu, k1);
     while (pend) {
       int src = __ffs(pend) - 1;
       pend &= pend - 1;
-      int v = box_edge(E, __shfl_sync(0xffffffffu, cx1, src), __shfl_sync(0xffffffffu, cy1, src), lane);
+      int v = box_corner(E, __shfl_sync(0xffffffffu, cx1, src), __shfl_sync(0xffffffffu, cy1, src), lane);
       if (lane == src) s1 = v;
     }
-    pend = __ballot_sync(0xffffffffu, e2);
+    pend = __ballot_sync(0xffffffffu, k2);
     while (pend) {
       int src = __ffs(pend) - 1;
       pend &= pend - 1;
-      int v = box_edge(E, __shfl_sync(0xffffffffu, cx2, src), __shfl_sync(0xffffffffu, cy2, src), lane);
+      int v = box_corner(E, __shfl_sync(0xffffffffu, cx2, src), __shfl_sync(0xffffffffu, cy2, src), lane);
       if (lane == src) s2 = v;
     }
     uint32_t word = __ballot_sync(0xffffffffu, !skip && s1 < s2);
@@ -760,7 +792,7 @@ __device__ __forceinline__ void brief_of(const uint8_t* __restrict__ img, int pi
   *out_words = mine;
 }
 
-__global__ void __launch_bounds__(K3_WARPS * 32) k_describe(const OrbPlan P, const Bufs B, const DescribeJob J) {
+__global__ void __launch_bounds__(K3_WARPS * 32, 4) k_describe(const OrbPlan P, const Bufs B, const DescribeJob J) {
   const int lane = threadIdx.x & 31;
   const int widx = blockIdx.x * K3_WARPS + (threadIdx.x >> 5);
   const int f = blockIdx.y;
@@ -795,7 +827,9 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k_describe(const OrbPlan P, con
   if (J.mode != 2 && lane == 0) B.out_angles[o] = angle;
   if (J.mode != 1) {
     uint32_t word;
-    brief_of(img, pitch, box, G.bpitch, G.w, G.h, (long long)B.level_sum[f * ORB_MAX_LEVELS + l], x, y, angle, B.pattern, lane, &word);
+    const int* ey = B.edge + (size_t)f * P.edge_frame_elems + G.edge_ofs;
+    const EdgeSrc E{img, pitch, G.w, G.h, (long long)B.level_sum[f * ORB_MAX_LEVELS + l], ey, ey + G.edge_w};
+    brief_of(img, pitch, box, G.bpitch, E, x, y, angle, B.pattern, lane, &word);
     if (lane < 8) ((uint32_t*)B.out_desc)[o * 8 + lane] = word;
   }
   if (J.mode == 0 && lane == 0) {
