@@ -43,8 +43,9 @@ struct orb_ctx {
   // arena
   uint8_t* d_frames = nullptr; size_t frames_slot_bytes = 0; int frames_pitch = 0;
   uint8_t* d_pyr = nullptr; uint16_t* d_box = nullptr; unsigned long long* d_cand = nullptr;
-  int* d_cand_count = nullptr; unsigned long long* d_level_sum = nullptr; int* d_edge = nullptr; size_t zero_bytes_per_frame = 0; uint32_t* d_kept_xy = nullptr; float* d_kept_r = nullptr; int* d_kept_count = nullptr;
+  int* d_cand_count = nullptr; int* d_edge = nullptr; size_t zero_bytes_per_frame = 0; uint32_t* d_kept_xy = nullptr; float* d_kept_r = nullptr; int* d_kept_count = nullptr;
   OrbTap *d_xtab = nullptr, *d_ytab = nullptr;
+  uint32_t *d_tile_a = nullptr, *d_tile_b = nullptr, *d_tile_b1 = nullptr; int tile_a_cap = 0, tile_b_cap = 0;
   float* d_harris_w = nullptr; float4* d_pattern = nullptr; int* d_flags = nullptr; int* h_flags = nullptr;
   orb_keypoint* d_kps = nullptr; float* d_angles = nullptr; orb_descriptor* d_desc = nullptr; int* d_nout = nullptr;
   orb_keypoint* d_side_xy = nullptr; int* d_side_level = nullptr; float* d_side_resp = nullptr;
@@ -165,6 +166,19 @@ void build_plan(const orb_params& p, int W, int H, int nlevels, int policy, int 
   P->pyr_frame_bytes = std::max<unsigned long long>(lv, 256); P->box_frame_elems = bx; P->cand_frame_elems = cd;
 }
 
+// flattened tile lists of the two tiled kernels: level | tile_x << 4 | tile_y << 18
+void make_tile_tables(const OrbPlan& P, std::vector<uint32_t>* ta, std::vector<uint32_t>* tb) {
+  ta->clear(); tb->clear();
+  for (int l = 0; l < P.nlevels; l++) {
+    const OrbLevel& G = P.lv[l];
+    if (l > 0)
+      for (int ty = 0; ty < G.a_tiles_y; ty++)
+        for (int tx = 0; tx < G.a_tiles_x; tx++) ta->push_back((uint32_t)l | ((uint32_t)tx << 4) | ((uint32_t)ty << 18));
+    for (int ty = 0; ty < G.tiles_y; ty++)
+      for (int tx = 0; tx < G.tiles_x; tx++) tb->push_back((uint32_t)l | ((uint32_t)tx << 4) | ((uint32_t)ty << 18));
+  }
+}
+
 int upload_tables(orb_ctx* ctx, const OrbPlan& P) {
   std::vector<OrbTap> xt, yt;
   for (int l = 0; l < P.nlevels; l++) {
@@ -174,6 +188,11 @@ int upload_tables(orb_ctx* ctx, const OrbPlan& P) {
     make_taps(P.H, G.h, yt.data() + G.ytab_ofs);
   }
   if ((int)xt.size() > ctx->xtab_cap || (int)yt.size() > ctx->ytab_cap) return fail(ctx, ORB_E_CAPACITY, "tap tables exceed arena");
+  std::vector<uint32_t> ta, tb;
+  make_tile_tables(P, &ta, &tb);
+  if ((int)ta.size() > ctx->tile_a_cap || (int)tb.size() > ctx->tile_b_cap) return fail(ctx, ORB_E_CAPACITY, "tile tables exceed arena");
+  if (!ta.empty()) CK(cudaMemcpyAsync(ctx->d_tile_a, ta.data(), ta.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_tile_b, tb.data(), tb.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_xtab, xt.data(), xt.size() * sizeof(OrbTap), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_ytab, yt.data(), yt.size() * sizeof(OrbTap), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));   // host vectors die here
@@ -196,8 +215,8 @@ int get_plan(orb_ctx* ctx, int w, int h) {
 void fill_bufs(orb_ctx* ctx, Bufs* B) {
   memset(B, 0, sizeof(*B));
   B->pyr = ctx->d_pyr; B->box = ctx->d_box; B->cand = ctx->d_cand; B->cand_count = ctx->d_cand_count;
-  B->level_sum = ctx->d_level_sum; B->edge = ctx->d_edge; B->kept_xy = ctx->d_kept_xy; B->kept_r = ctx->d_kept_r; B->kept_count = ctx->d_kept_count;
-  B->xtab = ctx->d_xtab; B->ytab = ctx->d_ytab; B->harris_w = ctx->d_harris_w; B->pattern = ctx->d_pattern;
+  B->edge = ctx->d_edge; B->kept_xy = ctx->d_kept_xy; B->kept_r = ctx->d_kept_r; B->kept_count = ctx->d_kept_count;
+  B->xtab = ctx->d_xtab; B->ytab = ctx->d_ytab; B->tile_a = ctx->d_tile_a; B->tile_b = ctx->d_tile_b; B->harris_w = ctx->d_harris_w; B->pattern = ctx->d_pattern;
   B->flags = ctx->d_flags;
 }
 
@@ -243,7 +262,7 @@ int launch_select(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, int nframes) {
   dim3 grid(P.nlevels, nframes);
   {
     StageTimer t(ctx, 2);
-    orbk::k_select<<<grid, orbk::K2_THREADS, (size_t)npow2 * 8, ctx->stream>>>(P, B);
+    orbk::k_select<<<grid, orbk::K2_THREADS, (size_t)(npow2 + orbk::K2_SMEM_KEYS) * 8, ctx->stream>>>(P, B, npow2);
   }
   CK(cudaGetLastError());
   ctx->launches += 1;
@@ -285,6 +304,13 @@ void stage_plan(orb_ctx* ctx, int w, int h, int policy, int quota, OrbPlan* P, B
   build_plan(ctx->p, w, h, 1, policy, quota, P);
   P->lv[0].cand_cap = ctx->max_plan.lv[0].cand_cap;
   fill_bufs(ctx, B);
+  {
+    std::vector<uint32_t> ta, tb;
+    make_tile_tables(*P, &ta, &tb);
+    cudaMemcpyAsync(ctx->d_tile_b1, tb.data(), tb.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);   // tb dies here
+    B->tile_b = ctx->d_tile_b1;
+  }
   B->frames = ctx->d_frames; B->frame_stride = ctx->frames_slot_bytes; B->pitch0 = ctx->frames_pitch;
   B->out_kps = ctx->d_kps; B->out_angles = ctx->d_angles; B->out_desc = ctx->d_desc; B->out_n = ctx->d_nout;
   B->out_cap = ctx->list_cap;
@@ -311,7 +337,7 @@ void orb_destroy(orb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->p.device);
   void* ptrs[] = {ctx->d_frames, ctx->d_pyr, ctx->d_box, ctx->d_cand, ctx->d_cand_count, ctx->d_kept_xy, ctx->d_kept_r,
-                  ctx->d_kept_count, ctx->d_xtab, ctx->d_ytab, ctx->d_harris_w, ctx->d_pattern, ctx->d_flags, ctx->d_kps,
+                  ctx->d_kept_count, ctx->d_xtab, ctx->d_ytab, ctx->d_tile_a, ctx->d_tile_b, ctx->d_tile_b1, ctx->d_harris_w, ctx->d_pattern, ctx->d_flags, ctx->d_kps,
                   ctx->d_angles, ctx->d_desc, ctx->d_nout, ctx->d_side_xy, ctx->d_side_level, ctx->d_side_resp,
                   ctx->d_list_kps, ctx->d_list_angles, ctx->d_list_out};
   for (void* q : ptrs) if (q) cudaFree(q);
@@ -384,19 +410,22 @@ int orb_create(const orb_params* p, orb_ctx** out) {
     CK(cudaMalloc(&ctx->d_pyr, (size_t)M.pyr_frame_bytes * C));
     CK(cudaMalloc(&ctx->d_box, (size_t)M.box_frame_elems * 2 * C));
     CK(cudaMalloc(&ctx->d_cand, (size_t)M.cand_frame_elems * 8 * C));
-    // per-chunk accumulators, zeroed by one memset per chunk: candidate counters | level totals | BRIEF border tables
+    // per-chunk accumulators, zeroed by one memset per chunk: candidate counters | BRIEF border tables
     {
       const int edge_max = std::max(M.edge_frame_elems, S.edge_frame_elems);
-      ctx->zero_bytes_per_frame = (sizeof(int) + sizeof(unsigned long long)) * ORB_MAX_LEVELS + sizeof(int) * (size_t)edge_max;
+      ctx->zero_bytes_per_frame = sizeof(int) * ORB_MAX_LEVELS + sizeof(int) * (size_t)edge_max;
       CK(cudaMalloc(&ctx->d_cand_count, ctx->zero_bytes_per_frame * C));
-      ctx->d_level_sum = (unsigned long long*)(ctx->d_cand_count + (size_t)ORB_MAX_LEVELS * C);
-      ctx->d_edge = (int*)(ctx->d_level_sum + (size_t)ORB_MAX_LEVELS * C);
+      ctx->d_edge = ctx->d_cand_count + (size_t)ORB_MAX_LEVELS * C;
     }
     CK(cudaMalloc(&ctx->d_kept_count, sizeof(int) * ORB_MAX_LEVELS * C));
     CK(cudaMalloc(&ctx->d_kept_xy, sizeof(uint32_t) * (size_t)kept_per_frame * C));
     CK(cudaMalloc(&ctx->d_kept_r, sizeof(float) * (size_t)kept_per_frame * C));
     ctx->xtab_cap = 0; ctx->ytab_cap = 0;
     for (int l = 0; l < M.nlevels; l++) { ctx->xtab_cap += M.lv[l].w; ctx->ytab_cap += M.lv[l].h; }
+    ctx->tile_a_cap = std::max(M.a_tiles_per_frame, 1); ctx->tile_b_cap = M.tiles_per_frame;
+    CK(cudaMalloc(&ctx->d_tile_a, 4 * (size_t)ctx->tile_a_cap));
+    CK(cudaMalloc(&ctx->d_tile_b, 4 * (size_t)ctx->tile_b_cap));
+    CK(cudaMalloc(&ctx->d_tile_b1, 4 * (size_t)S.tiles_per_frame));   // single-level stage plans
     CK(cudaMalloc(&ctx->d_xtab, sizeof(OrbTap) * ctx->xtab_cap));
     CK(cudaMalloc(&ctx->d_ytab, sizeof(OrbTap) * ctx->ytab_cap));
     CK(cudaMalloc(&ctx->d_harris_w, sizeof(float) * 49));
@@ -419,6 +448,7 @@ int orb_create(const orb_params* p, orb_ctx** out) {
     CK(cudaMalloc(&ctx->d_list_out, sizeof(float) * nrec));
     harris_weights(ctx->harris_w);
     CK(cudaMemcpy(ctx->d_harris_w, ctx->harris_w, sizeof(float) * 49, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyToSymbol(orbk::c_harris_w, ctx->harris_w, sizeof(float) * 49));   // identical for every context
     {
       float pat[1024];   // the 256 tests as floats (x1,y1,x2,y2): the reference converts them per use (src/orb_cpu.cpp:228)
       for (int i = 0; i < 1024; i++) pat[i] = (float)ORB_BRIEF_PATTERN_31[i];
@@ -426,7 +456,7 @@ int orb_create(const orb_params* p, orb_ctx** out) {
     }
     CK(cudaMemset(ctx->d_flags, 0, sizeof(int)));
     CK(cudaFuncSetAttribute(orbk::k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, orbk::B_SMEM));
-    CK(cudaFuncSetAttribute(orbk::k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, ORB_SORT_CAP * 8));
+    CK(cudaFuncSetAttribute(orbk::k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (ORB_SORT_CAP + orbk::K2_SMEM_KEYS) * 8));
     return ORB_OK;
   };
   rc = body();

@@ -32,13 +32,14 @@ struct Bufs {
   uint16_t* box;                 // [chunk][box_frame_elems]
   unsigned long long* cand;      // [chunk][cand_frame_elems]
   int* cand_count;               // [chunk][ORB_MAX_LEVELS]
-  unsigned long long* level_sum; // [chunk][ORB_MAX_LEVELS] sum of all pixels of the level (BRIEF corner boxes)
   int* edge;                     // [chunk][edge_frame_elems] strip sums for BRIEF boxes that leave the image
   uint32_t* kept_xy;             // [chunk][kept_per_frame]   (y << 16 | x), level space
   float* kept_r;                 // [chunk][kept_per_frame]
   int* kept_count;               // [chunk][ORB_MAX_LEVELS]
   const OrbTap* xtab;
   const OrbTap* ytab;
+  const uint32_t* tile_a;        // per tile of k_pyramid: level | tile_x << 4 | tile_y << 18
+  const uint32_t* tile_b;        // same for k_fast
   const float* harris_w;         // 49 window weights
   const float4* pattern;         // 256 BRIEF tests (x1,y1,x2,y2) as floats
   int* flags;                    // bit 0: candidate overflow
@@ -72,29 +73,45 @@ __device__ __forceinline__ float ord2f(uint32_t k) {
 // ---------------------------------------------------------------------------------------------
 // Harris response at a pixel, decision D5: integer 3x3 Sobel, float 7x7 window in
 // row-major order, separate multiply and add (no FMA), det - k * trace * trace.
-// PIX(y, x) must return the pixel of the reflect-101 extended level.
-template <typename PIX>
-__device__ __forceinline__ float harris_at(PIX pix, int y, int x, const float* __restrict__ wt, float k) {
+// REL(dy, dx) returns the pixel of the reflect-101 extended level at an offset from the keypoint.
+// The 9x9 neighbourhood is walked once, row by row: per window row the vertical [1 2 1] sums of the nine
+// columns give Ix = V[c+1] - V[c-1], the horizontal [1 2 1] sums of the rows above / below give Iy.
+__constant__ float c_harris_w[49];   // createGaussianKernel(7), ref src/GaussianBlur.cpp:7-37 (uploaded at orb_create)
+
+__device__ __forceinline__ float int2float_exact(int v) {   // |v| < 2^22: exact, two full-rate instructions
+  return __fsub_rn(__int_as_float(0x4B400000 + v), 12582912.0f);
+}
+
+template <typename REL>
+__device__ __forceinline__ float harris_at(REL pix, float k) {
   float A = 0.f, B = 0.f, C = 0.f;
-#pragma unroll 1
-  for (int dy = -3; dy <= 3; dy++) {
-    // sliding 3-column window of vertical sums along the row
-    int yy = y + dy;
-    int a0 = pix(yy - 1, x - 4), a1 = pix(yy, x - 4), a2 = pix(yy + 1, x - 4);
-    int b0 = pix(yy - 1, x - 3), b1 = pix(yy, x - 3), b2 = pix(yy + 1, x - 3);
+  int pm[9], pc[9], pp[9], hm[7], hc[7], hp[7];
 #pragma unroll
-    for (int dx = -3; dx <= 3; dx++) {
-      int xx = x + dx;
-      int c0 = pix(yy - 1, xx + 1), c1 = pix(yy, xx + 1), c2 = pix(yy + 1, xx + 1);
-      int ix = (c0 + 2 * c1 + c2) - (a0 + 2 * a1 + a2);
-      int iy = (a2 + 2 * b2 + c2) - (a0 + 2 * b0 + c0);
-      float g = __ldg(wt + (dy + 3) * 7 + (dx + 3));
-      A = orbm::fadd(A, orbm::fmul((float)(ix * ix), g));
-      B = orbm::fadd(B, orbm::fmul((float)(ix * iy), g));
-      C = orbm::fadd(C, orbm::fmul((float)(iy * iy), g));
-      a0 = b0; a1 = b1; a2 = b2;
-      b0 = c0; b1 = c1; b2 = c2;
+  for (int c = 0; c < 9; c++) { pm[c] = pix(-4, c - 4); pc[c] = pix(-3, c - 4); }
+#pragma unroll
+  for (int j = 0; j < 7; j++) { hm[j] = pm[j] + 2 * pm[j + 1] + pm[j + 2]; hc[j] = pc[j] + 2 * pc[j + 1] + pc[j + 2]; }
+#pragma unroll
+  for (int dy = -3; dy <= 3; dy++) {
+#pragma unroll
+    for (int c = 0; c < 9; c++) pp[c] = pix(dy + 1, c - 4);
+#pragma unroll
+    for (int j = 0; j < 7; j++) hp[j] = pp[j] + 2 * pp[j + 1] + pp[j + 2];
+    int V[9];
+#pragma unroll
+    for (int c = 0; c < 9; c++) V[c] = pm[c] + 2 * pc[c] + pp[c];
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+      const int ix = V[j + 2] - V[j];          // Sobel x at (dy, j-3)
+      const int iy = hp[j] - hm[j];            // Sobel y at (dy, j-3)
+      const float g = c_harris_w[(dy + 3) * 7 + j];
+      A = orbm::fadd(A, orbm::fmul(int2float_exact(ix * ix), g));
+      B = orbm::fadd(B, orbm::fmul(int2float_exact(ix * iy), g));
+      C = orbm::fadd(C, orbm::fmul(int2float_exact(iy * iy), g));
     }
+#pragma unroll
+    for (int c = 0; c < 9; c++) { pm[c] = pc[c]; pc[c] = pp[c]; }
+#pragma unroll
+    for (int j = 0; j < 7; j++) { hm[j] = hc[j]; hc[j] = hp[j]; }
   }
   float det = orbm::fsub(orbm::fmul(A, C), orbm::fmul(B, B));
   float tr = orbm::fadd(A, C);
@@ -155,11 +172,10 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
   __shared__ __align__(16) uint8_t s_res[A_RH * A_RP];
   __shared__ __align__(16) uint16_t s_h[A_RH * A_TW];
   const int tid = threadIdx.x, f = blockIdx.y;
-  int t = blockIdx.x, l = 1;
-  while (l + 1 < P.nlevels && t >= P.lv[l + 1].a_tile_ofs) l++;
+  const uint32_t tt = __ldg(B.tile_a + blockIdx.x);
+  const int l = tt & 15;
   const OrbLevel& G = P.lv[l];
-  t -= G.a_tile_ofs;
-  const int x0 = (t % G.a_tiles_x) * A_TW, y0 = (t / G.a_tiles_x) * A_TH;
+  const int x0 = ((tt >> 4) & 0x3fff) * A_TW, y0 = (tt >> 18) * A_TH;
   const int w = G.w, h = G.h;
   const bool blur = P.blur_levels != 0;
   const int halo = blur ? 2 : 0;
@@ -268,7 +284,7 @@ constexpr int B_SMEM = B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES + B_SURV * 2 +
 static_assert((B_TH + 4) * B_TW * 2 <= B_LIST_BYTES, "box rows alias the list");
 static_assert((B_TW + 2) * (B_TH + 2) <= B_LIST, "list capacity");
 
-__global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs B) {
+__global__ void __launch_bounds__(B_THREADS, 4) k_fast(const OrbPlan P, const Bufs B) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint8_t* s_pix = smem;
   uint16_t* s_score = (uint16_t*)(smem + B_PIX_BYTES);
@@ -277,11 +293,10 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
   int* s_ctr = (int*)(s_surv + B_SURV);   // [0] pretest list, [1] survivor list, [2] global base
 
   const int tid = threadIdx.x, lane = tid & 31, f = blockIdx.y;
-  int t = blockIdx.x, l = 0;
-  while (l + 1 < P.nlevels && t >= P.lv[l + 1].tile_ofs) l++;
+  const uint32_t tt = __ldg(B.tile_b + blockIdx.x);
+  const int l = tt & 15;
   const OrbLevel& G = P.lv[l];
-  t -= G.tile_ofs;
-  const int x0 = (t % G.tiles_x) * B_TW, y0 = (t / G.tiles_x) * B_TH;
+  const int x0 = ((tt >> 4) & 0x3fff) * B_TW, y0 = (tt >> 18) * B_TH;
   const int w = G.w, h = G.h;
   const uint8_t* __restrict__ img;
   int pitch;
@@ -291,24 +306,16 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
   // ---- phase 0/1: clear the score map, stage the tile (16-byte loads; rows reflect-101) -------
   for (int i = tid; i < B_SCORE_BYTES / 16; i += B_THREADS) ((uint4*)s_score)[i] = make_uint4(0, 0, 0, 0);
   if (tid < 3) s_ctr[tid] = 0;
-  unsigned tile_sum = 0;   // sum of the tile's own pixels -> level total (the reference's integral image corner value)
   for (int it = tid; it < B_PH * (B_SP / 16); it += B_THREADS) {
     const int py = it / (B_SP / 16), c = it - py * (B_SP / 16);
-    const int xs = x0 - 16 + 16 * c, y = y0 - 4 + py;
+    const int xs = x0 - 16 + 16 * c;
+    int y = y0 - 4 + py;                         // reflect-101 rows (one bounce is enough for a 4-pixel halo)
+    y = y < 0 ? -y : (y >= h ? 2 * h - 2 - y : y);
+    y = min(max(y, 0), h - 1);
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (xs >= 0 && xs < pitch) v = __ldg((const uint4*)(img + (size_t)reflect101(y, h) * pitch + xs));
+    if (xs >= 0 && xs < pitch) v = __ldg((const uint4*)(img + (size_t)y * pitch + xs));
     *(uint4*)(s_pix + py * B_SP + 16 * c) = v;
-    if (c >= 1 && c <= B_TW / 16 && py >= 4 && py < 4 + B_TH && y < h && xs < w) {
-      const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int nb = min(4, w - (xs + 4 * k));
-        if (nb > 0) tile_sum = __dp4a(nb == 4 ? wd[k] : (wd[k] & ((1u << (8 * nb)) - 1u)), 0x01010101u, tile_sum);
-      }
-    }
   }
-  tile_sum = (unsigned)warp_sum((int)tile_sum);
-  if (lane == 0 && tile_sum) atomicAdd(B.level_sum + f * ORB_MAX_LEVELS + l, (unsigned long long)tile_sum);
   __syncthreads();
   // columns -1 and w of the reflect-101 extension (Sobel taps of the Harris window reach them)
   if (tid < B_PH) {
@@ -408,12 +415,14 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
   unsigned long long* cand = B.cand + (size_t)f * P.cand_frame_elems + G.cand_ofs;
   int* gcount = B.cand_count + f * ORB_MAX_LEVELS + l;
   const int nmsr = P.nms_radius;
-  auto pixat = [&](int yy, int xx) { return (int)s_pix[yy * B_SP + xx]; };
   auto emit = [&](int idx, int slot) {
     const int sy = idx / B_SP, pcx = idx - sy * B_SP;
     const int lx = x0 + pcx - 16, ly = y0 - 1 + sy;
     uint32_t hi = 0;
-    if (P.select_policy == ORB_SELECT_HARRIS_TOP_N) hi = ~f2ord(harris_at(pixat, sy + 3, pcx, B.harris_w, P.harris_k));
+    if (P.select_policy == ORB_SELECT_HARRIS_TOP_N) {
+      const uint8_t* ctr = s_pix + (sy + 3) * B_SP + pcx;
+      hi = ~f2ord(harris_at([&](int dy, int dx) { return (int)ctr[dy * B_SP + dx]; }, P.harris_k));
+    }
     if (slot < G.cand_cap) cand[slot] = ((unsigned long long)hi << 32) | (unsigned)((ly << 16) | lx);
   };
   for (int j = tid; j < n1; j += B_THREADS) {
@@ -468,25 +477,39 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
   {
     int* ey = B.edge + (size_t)f * P.edge_frame_elems + G.edge_ofs;
     int* rs = ey + G.edge_w;
-    if (tid < B_TW) {
-      const int x = x0 + tid, rows = min(B_TH, h - 4 - y0);
-      if (rows > 0 && x >= 2 && x <= w - 3) {
-        const int j = tid & 7;   // u16 slot of pixel j inside its group of 8: lanes (o0,o2)(o1,o3)(o4,o6)(o5,o7)
-        const uint16_t* c = s_bh + 2 * B_TW + (tid & ~7) + ((j >> 2) * 2 + (j & 1)) * 2 + ((j >> 1) & 1);
-        int acc = 0;
-        for (int r = 0; r < rows; r++) acc += c[r * B_TW];
-        atomicAdd(ey + x, acc);
+    if (tid < 64) {            // warp 0-1: column strips, thread = (8-column group, quarter of the rows)
+      const int g = tid & 15, q = tid >> 4;
+      const int rows = min(16, h - 4 - y0 - 16 * q);            // rows of this quarter that lie above row h-4
+      if (rows > 0) {
+        const uint16_t* c = s_bh + (2 + 16 * q) * B_TW + 8 * g;   // horizontal 5-sums of row y0 + 16q
+        uint4 acc = make_uint4(0, 0, 0, 0);                       // 16-bit lanes: <= 16 * 1275
+        for (int r = 0; r < rows; r++) {
+          const uint4 v = *(const uint4*)(c + r * B_TW);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        // lanes (o0,o2)(o1,o3)(o4,o6)(o5,o7) -> pixel order
+        const int val[8] = {(int)(acc.x & 0xffff), (int)(acc.y & 0xffff), (int)(acc.x >> 16), (int)(acc.y >> 16),
+                            (int)(acc.z & 0xffff), (int)(acc.w & 0xffff), (int)(acc.z >> 16), (int)(acc.w >> 16)};
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int x = x0 + 8 * g + j;
+          if (x >= 2 && x <= w - 3) atomicAdd(ey + x, val[j]);
+        }
       }
-    } else if (tid < B_TW + B_TH) {
-      const int iy = tid - B_TW, y = y0 + iy;
+    } else if (tid < 64 + B_TH) {   // warp 2-3: row sums over columns < w-4 (and column 0 for the wrapped taps)
+      const int iy = tid - 64, y = y0 + iy;
       if (y < h) {
         const int ncol = min(B_TW, w - 4 - x0);
         const uint8_t* r = s_pix + (iy + 4) * B_SP + 16;
         unsigned acc = 0;
-        for (int c = 0; c < ncol; c += 4) {
-          uint32_t v = *(const uint32_t*)(r + c);
-          if (ncol - c < 4) v &= (1u << (8 * (ncol - c))) - 1u;
-          acc = __dp4a(v, 0x01010101u, acc);
+        for (int c = 0; c < ncol; c += 16) {
+          const uint4 v = *(const uint4*)(r + c);
+          const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int nb = ncol - c - 4 * k;
+            if (nb > 0) acc = __dp4a(nb >= 4 ? wd[k] : (wd[k] & ((1u << (8 * nb)) - 1u)), 0x01010101u, acc);
+          }
         }
         if (ncol > 0) atomicAdd(rs + y, (int)acc);
         if (x0 == 0 && y < h - 4) atomicAdd(ey, (int)r[0]);
@@ -511,13 +534,16 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
 // ---------------------------------------------------------------------------------------------
 // Selection: CTA per (frame, level).
 constexpr int K2_THREADS = 512;
+constexpr int K2_SMEM_KEYS = 6144;   // candidate keys of a level are staged in shared memory when they fit
 
-__global__ void __launch_bounds__(K2_THREADS) k_select(const OrbPlan P, const Bufs B) {
-  extern __shared__ __align__(16) unsigned long long s_sort[];   // [npow2]
+__global__ void __launch_bounds__(K2_THREADS) k_select(const OrbPlan P, const Bufs B, int npow2_max) {
+  extern __shared__ __align__(16) unsigned long long s_dyn[];   // [npow2_max] sort buffer, then [K2_SMEM_KEYS] keys
+  unsigned long long* s_sort = s_dyn;
+  unsigned long long* s_keys = s_dyn + npow2_max;
   __shared__ int s_hist[256];
   __shared__ unsigned long long s_prefix;
-  __shared__ int s_k, s_n;
-  const int tid = threadIdx.x, l = blockIdx.x, f = blockIdx.y;
+  __shared__ int s_k, s_n, s_done;
+  const int tid = threadIdx.x, lane = tid & 31, l = blockIdx.x, f = blockIdx.y;
   const OrbLevel& G = P.lv[l];
   int n = B.cand_count[f * ORB_MAX_LEVELS + l];
   if (n > G.cand_cap) {
@@ -525,19 +551,32 @@ __global__ void __launch_bounds__(K2_THREADS) k_select(const OrbPlan P, const Bu
     n = G.cand_cap;
   }
   const int m = min(G.quota, n);
-  const unsigned long long* __restrict__ keys = B.cand + (size_t)f * P.cand_frame_elems + G.cand_ofs;
+  const unsigned long long* __restrict__ gkeys = B.cand + (size_t)f * P.cand_frame_elems + G.cand_ofs;
+  const unsigned long long* keys = gkeys;
   unsigned long long T = ~0ull;
   if (n > m && m > 0) {
-    // m-th smallest key by MSB-first radix select, 8 bits per pass
-    if (tid == 0) { s_prefix = 0; s_k = m; }
+    if (n <= K2_SMEM_KEYS) {
+      for (int i = tid; i < n; i += K2_THREADS) s_keys[i] = gkeys[i];
+      keys = s_keys;
+    }
+    // m-th smallest key by MSB-first radix select, 8 bits per pass.  Lanes with equal digits are aggregated
+    // (match_any) before the shared atomic; the scan stops as soon as the whole bin is needed.
+    if (tid == 0) { s_prefix = 0; s_k = m; s_done = 0; }
+    __syncthreads();
     for (int pass = 7; pass >= 0; pass--) {
       for (int i = tid; i < 256; i += K2_THREADS) s_hist[i] = 0;
       __syncthreads();
       const unsigned long long prefix = s_prefix;
       const int shift = pass * 8;
-      for (int i = tid; i < n; i += K2_THREADS) {
-        unsigned long long k = keys[i];
-        if (pass == 7 || (k >> (shift + 8)) == prefix) atomicAdd(&s_hist[(int)(k >> shift) & 255], 1);
+      for (int i0 = 0; i0 < n; i0 += K2_THREADS) {
+        const int i = i0 + tid;
+        int digit = -1;
+        if (i < n) {
+          const unsigned long long k = keys[i];
+          if (pass == 7 || (k >> (shift + 8)) == prefix) digit = (int)(k >> shift) & 255;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        if (digit >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_hist[digit], __popc(peers));
       }
       __syncthreads();
       if (tid < 32) {
@@ -552,15 +591,22 @@ __global__ void __launch_bounds__(K2_THREADS) k_select(const OrbPlan P, const Bu
         }
         const int k = s_k;
         unsigned hit = __ballot_sync(0xffffffffu, incl >= k);
-        int lane = __ffs(hit) - 1;
-        if (tid == lane) {
+        int sel = __ffs(hit) - 1;
+        if (tid == sel) {
           int before = incl - sum, b = 0;
           for (; b < 8; b++) { if (before + local[b] >= k) break; before += local[b]; }
-          s_k = k - before;
-          s_prefix = (prefix << 8) | (unsigned)(tid * 8 + b);
+          const unsigned long long np = (prefix << 8) | (unsigned)(tid * 8 + b);
+          if (k - before == local[b]) {        // every key of this bin is kept: threshold = largest key of the bin
+            s_prefix = shift ? ((np << shift) | ((1ull << shift) - 1ull)) : np;
+            s_done = 1;
+          } else {
+            s_k = k - before;
+            s_prefix = np;
+          }
         }
       }
       __syncthreads();
+      if (s_done) break;
     }
     T = s_prefix;
   }
@@ -604,16 +650,9 @@ __global__ void __launch_bounds__(K2_THREADS) k_select(const OrbPlan P, const Bu
 // Orientation + rotated BRIEF: one warp per keypoint.
 constexpr int K3_WARPS = 8;
 
-// ---- BRIEF boxes that leave the image on the right / bottom ---------------------------------------
-// The reference's sum5x5 (src/orb_cpu.cpp:190-201) indexes its (H+1)x(W+1) integral image flat, so for centres
-// in the last two columns / rows the column overruns wrap into the next row and the row overruns fall off the
-// end (decision D7: those read 0).  What it then computes are *strip* sums of the image.  They are rebuilt here
-// from the 5x5 box-sum image (every 5th box tiles a strip) plus at most 20 remainder pixels, the whole warp
-// cooperating.  The lane_* helpers return per-lane partial sums; the caller reduces once.
 struct EdgeSrc {
   const uint8_t* __restrict__ img; int pitch;
   int W, H;
-  long long total;              // sum of all pixels of the level            (accumulated by k_fast)
   const int* __restrict__ ey;   // ey[cx]: rows [0,H-4) x cols [cx-2,cx+2]; ey[0]: column 0 over rows [0,H-4)
   const int* __restrict__ rs;   // rs[y]: row y over cols [0,W-4)
 };
@@ -645,41 +684,21 @@ __device__ __forceinline__ int box_edge_lane(const EdgeSrc& E, int cx, int cy) {
   return -s;
 }
 
-// column 0, rows [ya,yb)
-__device__ __forceinline__ int lane_col0(const EdgeSrc& E, int ya, int yb, int lane) {
-  int s = 0;
-  for (int y = ya + lane; y < yb; y += 32) s += E.img[(size_t)y * E.pitch];
-  return s;
-}
-// full rows [ya,yb) over all W columns (rows are 16-byte aligned: 4 pixels per load, masked tail)
-__device__ __forceinline__ int lane_rows_full(const EdgeSrc& E, int ya, int yb, int lane) {
-  unsigned s = 0;
-  const int nw = (E.W + 3) >> 2;
-  for (int y = ya; y < yb; y++) {
-    const uint32_t* row = (const uint32_t*)(E.img + (size_t)y * E.pitch);
-    for (int i = lane; i < nw; i += 32) {
-      uint32_t v = row[i];
-      const int nb = E.W - 4 * i;
-      if (nb < 4) v &= (1u << (8 * nb)) - 1u;
-      s = __dp4a(v, 0x01010101u, s);
-    }
-  }
-  return (int)s;
-}
-// rows [0,yb) x cols [xa, W)  (at most 4 columns)
-__device__ __forceinline__ int lane_cols_right(const EdgeSrc& E, int xa, int yb, int lane) {
-  int s = 0;
-  for (int y = lane; y < yb; y += 32)
-    for (int x = xa; x < E.W; x++) s += E.img[(size_t)y * E.pitch + x];
-  return s;
-}
 // bottom-right corner box (cx > W-3 and cy > H-3), whole warp cooperates:
-// rows [0,y0) x cols [0,x0) = level total - rows [y0,H) - (rows [0,y0) x cols [x0,W))
+//   +(rows [0,cy-2) x cols [0,cx-2)) - (column 0 over rows [0,cy-1) when cx == W-1)
 __device__ __noinline__ int box_corner(const EdgeSrc& E, int cx, int cy, int lane) {
-  const int x0 = cx - 2, y0 = cy - 2, col = cx + 3 - E.W - 1;
-  int s = -lane_rows_full(E, y0, E.H, lane) - lane_cols_right(E, x0, y0, lane);
-  if (col == 1) s -= lane_col0(E, 0, y0 + 1, lane);
-  return (int)(E.total + (long long)warp_sum(s));
+  const int W = E.W, H = E.H, y0 = cy - 2;
+  int s = 0;
+  for (int v = lane; v < y0; v += 32) {
+    s += E.rs[v];
+    if (cx == W - 1) s += E.img[(size_t)v * E.pitch + (W - 4)];
+  }
+  s = warp_sum(s);
+  if (cx == W - 1) {
+    s -= E.ey[0] + E.img[(size_t)(H - 4) * E.pitch];
+    if (y0 == H - 3) s -= E.img[(size_t)(H - 3) * E.pitch];
+  }
+  return s;
 }
 
 struct DescribeJob {             // where the keypoints of this launch come from
@@ -828,7 +847,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32, 4) k_describe(const OrbPlan P, 
   if (J.mode != 1) {
     uint32_t word;
     const int* ey = B.edge + (size_t)f * P.edge_frame_elems + G.edge_ofs;
-    const EdgeSrc E{img, pitch, G.w, G.h, (long long)B.level_sum[f * ORB_MAX_LEVELS + l], ey, ey + G.edge_w};
+    const EdgeSrc E{img, pitch, G.w, G.h, ey, ey + G.edge_w};
     brief_of(img, pitch, box, G.bpitch, E, x, y, angle, B.pattern, lane, &word);
     if (lane < 8) ((uint32_t*)B.out_desc)[o * 8 + lane] = word;
   }
@@ -847,8 +866,9 @@ __global__ void k_harris_list(const uint8_t* __restrict__ img, int pitch, int w,
                               const float* wt, float k, float* out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  auto pix = [&](int yy, int xx) { return (int)img[(size_t)reflect101(yy, h) * pitch + reflect101(xx, w)]; };
-  out[i] = harris_at(pix, kps[i].y, kps[i].x, wt, k);
+  const int ky = kps[i].y, kx = kps[i].x;
+  auto pix = [&](int dy, int dx) { return (int)img[(size_t)reflect101(ky + dy, h) * pitch + reflect101(kx + dx, w)]; };
+  out[i] = harris_at(pix, k);
 }
 
 // libm twins evaluated on arrays (tests/test_gpu_math.py): op 0 atan2f(a,b), 1 cosf(a), 2 sinf(a), 3 lround(a)
