@@ -264,11 +264,12 @@ def main():
     # dominant kernel = largest share of the step; its algorithmic bytes per frame ("Kernels"):
     #   k_pyramid : level 0 read once + levels >= 1 written once          = sum(P)
     #   k_fast    : every level read once (box sums / candidates are ours) = sum(P)
-    #   k_select  : 8 B per candidate read (count unknown here; use K)     ~ 8 K
+    #   k_harris  : 8 B key read + written per candidate (count unknown here; use 4 K)
+    #   k_select  : 8 B per candidate read                                 ~ 8 * 4 K
     #   k_describe: 44 B per output record written                         = 44 K
-    names = ["k_pyramid", "k_fast", "k_select", "k_describe"]
+    names = ["k_pyramid", "k_fast", "k_harris", "k_select", "k_describe"]
     kpf = n_kp / F
-    alg_bytes = [SUM_P, SUM_P, 8.0 * kpf, 44.0 * kpf]
+    alg_bytes = [SUM_P, SUM_P, 64.0 * kpf, 32.0 * kpf, 44.0 * kpf]
     dom = int(np.argmax(st_ms))
     k1_ms = st_ms[dom] / max(1, st_n[dom])                    # average duration of one launch of that kernel
     frames_per_launch = F * prof_steps / max(1, st_n[dom])
@@ -292,7 +293,7 @@ def main():
         "config": {"workload": workload_name(F), "frames_per_gpu_per_step": F, "levels": LEVELS, "nfeatures": NFEAT,
                    "keypoints_per_frame": kp_per_frame, "chunk_frames": args.chunk,
                    "cache_hygiene": "input batch %.0f MB > 126 MB L2; scratch arena reused per chunk" % (F * H * PITCH / 1e6),
-                   "stage_names": ["k_pyramid", "k_fast", "k_select", "k_describe"],
+                   "stage_names": names,
                    "stage_ms_per_step": [m / prof_steps for m in st_ms], "stage_share": stage_share,
                    "pass_b_min_bytes_per_frame": b_min, "pass_hbm_gbs_per_gpu": pass_gbs, "pass_hbm_frac": pass_gbs / peak,
                    "peak_source": peak_src},

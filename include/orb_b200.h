@@ -155,10 +155,10 @@ int  orb_debug_eval_math(orb_ctx* ctx, int op, const float* a, const float* b, i
 /* per-kernel timing (bench / roofline accounting): when enabled, every kernel launch of the detect calls is
  * bracketed by CUDA events on the context's stream.  orb_get_stage_ms waits for the stream and returns, for the
  * launches since the last call, the summed device time [ms] and launch count of
- * stage 0 = pyramid kernel (resize+blur), 1 = FAST+NMS+Harris+box-sum kernel, 2 = selection kernel,
- * 3 = orientation+BRIEF kernel. */
+ * stage 0 = pyramid kernel (resize+blur), 1 = FAST+NMS+box-sum kernel, 2 = Harris kernel, 3 = selection kernel,
+ * 4 = orientation+BRIEF kernel. */
 int  orb_set_profiling(orb_ctx* ctx, int enable);
-int  orb_get_stage_ms(orb_ctx* ctx, float ms[4], int launches[4]);
+int  orb_get_stage_ms(orb_ctx* ctx, float ms[5], int launches[5]);
 /* number of kernel launches issued by the last detect call (for bench accounting) */
 int  orb_last_launch_count(const orb_ctx* ctx);
 

@@ -300,7 +300,7 @@ def test_device_resident_batch_through_torch_pointers(V, O):
     for f in range(F):
         assert np.array_equal(k[f, :n[f], 0], k_ref[f, :n[f]]["x"]) and np.array_equal(k[f, :n[f], 1], k_ref[f, :n[f]]["y"])
         assert np.array_equal(dd[f, :n[f]], d_ref[f, :n[f]])
-    assert c.launch_count() == 2 * 4                                       # 4 kernels x 2 chunks
+    assert c.launch_count() == 2 * 5                                       # 5 kernels x 2 chunks
     c.close()
 
 
@@ -318,3 +318,41 @@ def test_reference_class_surface(V, O, kitti0):
     kk, aa, dd = orb.detectAndCompute(kitti0)
     r = O.detect_and_compute(kitti0, O.params(), cap=500)
     assert np.array_equal(kk, r["kps"]) and np.array_equal(dd, r["desc"])
+
+
+# ------------------------------------------------------------------------------------------------- BASELINE configs 4 / 5
+@pytest.mark.parametrize("W,H,L,N", [(1920, 1080, 8, 5000), (3840, 2160, 12, 10000)])
+def test_full_path_large_frames(V, O, W, H, L, N):
+    """BASELINE.json configs 4 and 5 (1080p / 8 levels / 5000 kp; 4K / 12 levels / 10000 kp): one synthetic frame each,
+    every output compared with the oracle (the oracle needs a few seconds per frame at these sizes)."""
+    img = V.synth_frames(1, W, H)[0]
+    c = V.Context(V.make_params(nfeatures=N, nlevels=L, max_width=W, max_height=H, keep_side_arrays=1))
+    p = O.params(nfeatures=N, nlevels=L)
+    n = _compare_full(c, O, img, p, c.max_kp)
+    assert n == sum(O.level_quota(N, 1.2, L, l) for l in range(L))           # every level fills its quota
+    for l in (1, L - 1):
+        assert np.array_equal(c.get_level(0, l, W, H), O.build_level(img, p, l))
+    c.close()
+
+
+def test_batch_properties_at_bench_size(V, O):
+    """Size-independent properties on a bench-sized batch (200 frames, 2 waves): identical frames give identical
+    records; per-frame results do not depend on the position in the batch or on the wave size; every frame of the
+    synthetic set fills its budget; one frame is spot-checked against the oracle."""
+    F, W, H, cap = 200, 1241, 376, 2000
+    pool = V.synth_frames(8, W, H)
+    frames = pool[np.arange(F) % 8]
+    c = V.Context(V.make_params(nfeatures=2000, nlevels=8, max_width=W, max_height=H, max_batch=F, max_keypoints=cap))
+    k, a, d, n = c.detect_and_compute_batch(frames, cap)
+    assert (n == 1996).all()
+    for f in range(8, F):
+        assert np.array_equal(k[f], k[f % 8]) and np.array_equal(d[f], d[f % 8]) and np.array_equal(a[f], a[f % 8])
+    c2 = V.Context(V.make_params(nfeatures=2000, nlevels=8, max_width=W, max_height=H, max_batch=F, max_keypoints=cap,
+                                 chunk_frames=7))
+    k2, a2, d2, n2 = c2.detect_and_compute_batch(frames[::-1].copy(), cap)
+    assert np.array_equal(k2[::-1], k) and np.array_equal(d2[::-1], d)
+    r = O.detect_and_compute(pool[5], O.params(nfeatures=2000, nlevels=8), cap=cap)
+    assert np.array_equal(k[5, :n[5]], r["kps"]) and np.array_equal(d[5, :n[5]], r["desc"])
+    assert np.array_equal(bits(a[5, :n[5]]), bits(r["angles"]))
+    c.close()
+    c2.close()

@@ -252,6 +252,16 @@ int launch_pyramid_fast(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, int nfram
   }
   CK(cudaGetLastError());
   ctx->launches += 1;
+  if (P.select_policy == ORB_SELECT_HARRIS_TOP_N) {
+    // grid sized for ~1.5 % of the pyramid pixels surviving NMS; denser frames take more grid-stride rounds
+    int total_px = 0;
+    for (int l = 0; l < P.nlevels; l++) total_px += P.lv[l].w * P.lv[l].h;
+    const int blocks = std::max(1, std::min(total_px / 128 / orbk::C_THREADS + 1, 4096));
+    StageTimer t(ctx, 2);
+    orbk::k_harris<<<dim3(blocks, nframes), orbk::C_THREADS, 0, ctx->stream>>>(P, B);
+    ctx->launches += 1;
+  }
+  CK(cudaGetLastError());
   return ORB_OK;
 }
 int launch_select(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, int nframes) {
@@ -261,7 +271,7 @@ int launch_select(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, int nframes) {
   while (npow2 < mq) npow2 <<= 1;
   dim3 grid(P.nlevels, nframes);
   {
-    StageTimer t(ctx, 2);
+    StageTimer t(ctx, 3);
     orbk::k_select<<<grid, orbk::K2_THREADS, (size_t)(npow2 + orbk::K2_SMEM_KEYS) * 8, ctx->stream>>>(P, B, npow2);
   }
   CK(cudaGetLastError());
@@ -272,7 +282,7 @@ int launch_describe(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, const Describ
   if (nwarps <= 0) return ORB_OK;
   dim3 grid((nwarps + orbk::K3_WARPS - 1) / orbk::K3_WARPS, nframes);
   {
-    StageTimer t(ctx, 3);
+    StageTimer t(ctx, 4);
     orbk::k_describe<<<grid, orbk::K3_WARPS * 32, 0, ctx->stream>>>(P, B, J);
   }
   CK(cudaGetLastError());
@@ -401,7 +411,9 @@ int orb_create(const orb_params* p, orb_ctx** out) {
     ctx->max_kp = p->max_keypoints > 0 ? p->max_keypoints : total_quota;
     // chunking: keep one chunk's scratch (levels + box sums) well inside the 126 MB L2
     size_t per_frame = (size_t)M.pyr_frame_bytes + (size_t)M.box_frame_elems * 2 + (size_t)p->max_width * p->max_height;
-    int chunk = p->chunk_frames > 0 ? p->chunk_frames : (int)std::max<size_t>(1, ((size_t)64 << 20) / per_frame);
+    // measured on B200: larger waves win (launch gaps and kernel tails outweigh L2 residency of the scratch), so the
+    // default is 128 frames per wave, bounded by 1 GB of scratch
+    int chunk = p->chunk_frames > 0 ? p->chunk_frames : (int)std::max<size_t>(1, std::min<size_t>(128, ((size_t)1 << 30) / per_frame));
     ctx->chunk = std::max(1, std::min(chunk, p->max_batch));
     const int C = ctx->chunk, Bn = p->max_batch;
     ctx->frames_pitch = align_up(p->max_width, 16);
@@ -511,11 +523,11 @@ int orb_set_profiling(orb_ctx* ctx, int enable) {
   return ORB_OK;
 }
 
-int orb_get_stage_ms(orb_ctx* ctx, float ms[4], int launches[4]) {
+int orb_get_stage_ms(orb_ctx* ctx, float ms[5], int launches[5]) {
   if (!ctx || !ms || !launches) return ORB_E_INVALID;
   CK(cudaSetDevice(ctx->p.device));
   CK(cudaStreamSynchronize(ctx->stream));
-  for (int i = 0; i < 4; i++) { ms[i] = 0.f; launches[i] = 0; }
+  for (int i = 0; i < 5; i++) { ms[i] = 0.f; launches[i] = 0; }
   for (size_t i = 0; i < ctx->spans_used; i++) {
     float t = 0.f;
     CK(cudaEventElapsedTime(&t, ctx->spans[i].a, ctx->spans[i].b));

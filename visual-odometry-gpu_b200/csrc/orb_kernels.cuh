@@ -166,9 +166,10 @@ constexpr int A_RW = A_TW + 4, A_RH = A_TH + 4;   // resized region incl. blur h
 constexpr int A_RP = 136;                          // shared pitch of resized rows (bytes)
 
 __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bufs B) {
-  __shared__ __align__(16) uint32_t s_xs[A_RW];    // column taps, struct-of-arrays so that a thread's 4 taps are one
-  __shared__ __align__(16) uint32_t s_xa[A_RW];    // conflict-free 16-byte load: s0 | s1 << 16 and a0 | a1 << 16
-  __shared__ __align__(16) OrbTap s_yt[A_RH];
+  __shared__ uint32_t s_xs[A_RW];    // column taps: s0 | s1 << 16
+  __shared__ uint32_t s_xa[A_RW];    //              a0 | a1 << 16
+  __shared__ uint2 s_yo[A_RH];       // row taps: byte offsets of the two source rows inside the frame
+  __shared__ uint32_t s_yb[A_RH];    //           b0 | b1 << 16
   __shared__ __align__(16) uint8_t s_res[A_RH * A_RP];
   __shared__ __align__(16) uint16_t s_h[A_RH * A_TW];
   const int tid = threadIdx.x, f = blockIdx.y;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
   const int halo = blur ? 2 : 0;
   const int rw = A_TW + 2 * halo, rh = A_TH + 2 * halo;
   const uint8_t* __restrict__ src = B.frames + (size_t)f * B.frame_stride;
-  const int sp = B.pitch0;
+  const uint32_t sp = (uint32_t)B.pitch0;
 
   for (int i = tid; i < rw + rh; i += A_THREADS) {
     if (i < rw) {
@@ -189,31 +190,38 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
       s_xs[i] = (uint32_t)tx.s0 | ((uint32_t)tx.s1 << 16);
       s_xa[i] = (uint32_t)(uint16_t)tx.a0 | ((uint32_t)(uint16_t)tx.a1 << 16);
     } else {
-      s_yt[i - rw] = B.ytab[G.ytab_ofs + reflect101(y0 - halo + i - rw, h)];
+      const OrbTap ty = B.ytab[G.ytab_ofs + reflect101(y0 - halo + i - rw, h)];
+      s_yo[i - rw] = make_uint2(ty.s0 * sp, ty.s1 * sp);
+      s_yb[i - rw] = (uint32_t)(uint16_t)ty.a0 | ((uint32_t)(uint16_t)ty.a1 << 16);
     }
   }
   __syncthreads();
 
-  // resize: 4 output pixels per item (cv::resize INTER_LINEAR restated: 11-bit taps, >>4, >>16, +2 >>2)
-  const int nwords = rw >> 2;
-  for (int it = tid; it < rh * nwords; it += A_THREADS) {
-    const int ry = it / nwords, gx = it - ry * nwords;
-    if (y0 - halo + ry >= h + halo || x0 - halo + 4 * gx >= w + halo) continue;
-    const OrbTap ty = s_yt[ry];
-    const uint8_t* r0 = src + (size_t)ty.s0 * sp;
-    const uint8_t* r1 = src + (size_t)ty.s1 * sp;
-    const uint4 xs4 = *(const uint4*)(s_xs + 4 * gx), xa4 = *(const uint4*)(s_xa + 4 * gx);
-    const uint32_t xs[4] = {xs4.x, xs4.y, xs4.z, xs4.w}, xa[4] = {xa4.x, xa4.y, xa4.z, xa4.w};
-    uint32_t word = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int s0 = xs[j] & 0xffff, s1 = xs[j] >> 16, a0 = xa[j] & 0xffff, a1 = xa[j] >> 16;
-      int h0 = __ldg(r0 + s0) * a0 + __ldg(r0 + s1) * a1;
-      int h1 = __ldg(r1 + s0) * a0 + __ldg(r1 + s1) * a1;
-      int v = (((ty.a0 * (h0 >> 4)) >> 16) + ((ty.a1 * (h1 >> 4)) >> 16) + 2) >> 2;
-      word |= (uint32_t)min(v, 255) << (8 * j);
+  // resize (cv::resize INTER_LINEAR restated: 11-bit taps, >>4, >>16, +2 >>2): a thread owns one column of the region
+  // (its taps stay in registers) and walks down half of the rows; row taps are broadcast from shared memory.
+  auto resize_column = [&](int col, int r0, int r1) {
+    if (x0 - halo + col >= w + halo) return;
+    const uint32_t xs = s_xs[col], xa = s_xa[col];
+    const uint32_t s0 = xs & 0xffff, s1 = xs >> 16;
+    const int a0 = xa & 0xffff, a1 = xa >> 16;
+    r1 = min(r1, h + halo - (y0 - halo));
+#pragma unroll 3
+    for (int ry = r0; ry < r1; ry++) {
+      const uint2 ro = s_yo[ry];
+      const uint32_t yb = s_yb[ry];
+      const int h0 = __ldg(src + (ro.x + s0)) * a0 + __ldg(src + (ro.x + s1)) * a1;
+      const int h1 = __ldg(src + (ro.y + s0)) * a0 + __ldg(src + (ro.y + s1)) * a1;
+      const int v = ((((int)(yb & 0xffff) * (h0 >> 4)) >> 16) + (((int)(yb >> 16) * (h1 >> 4)) >> 16) + 2) >> 2;
+      s_res[ry * A_RP + col] = (uint8_t)min(v, 255);
     }
-    *(uint32_t*)(s_res + ry * A_RP + 4 * gx) = word;
+  };
+  {
+    const int half = tid >> 7, rows_half = (rh + 1) >> 1;
+    resize_column(tid & 127, half * rows_half, min(rh, (half + 1) * rows_half));
+    if (rw > A_TW) {                                   // the 4 extra halo columns: 4 x rh pixels, one per thread
+      const int extra = tid;                           // column 128 + extra % 4, row extra / 4
+      if (extra < 4 * rh) resize_column(A_TW + (extra & 3), extra >> 2, (extra >> 2) + 1);
+    }
   }
   __syncthreads();
 
@@ -284,7 +292,7 @@ constexpr int B_SMEM = B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES + B_SURV * 2 +
 static_assert((B_TH + 4) * B_TW * 2 <= B_LIST_BYTES, "box rows alias the list");
 static_assert((B_TW + 2) * (B_TH + 2) <= B_LIST, "list capacity");
 
-__global__ void __launch_bounds__(B_THREADS, 4) k_fast(const OrbPlan P, const Bufs B) {
+__global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs B) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint8_t* s_pix = smem;
   uint16_t* s_score = (uint16_t*)(smem + B_PIX_BYTES);
@@ -415,15 +423,10 @@ __global__ void __launch_bounds__(B_THREADS, 4) k_fast(const OrbPlan P, const Bu
   unsigned long long* cand = B.cand + (size_t)f * P.cand_frame_elems + G.cand_ofs;
   int* gcount = B.cand_count + f * ORB_MAX_LEVELS + l;
   const int nmsr = P.nms_radius;
-  auto emit = [&](int idx, int slot) {
+  auto emit = [&](int idx, int slot) {   // key = raster position; k_harris adds the response in the high word
     const int sy = idx / B_SP, pcx = idx - sy * B_SP;
     const int lx = x0 + pcx - 16, ly = y0 - 1 + sy;
-    uint32_t hi = 0;
-    if (P.select_policy == ORB_SELECT_HARRIS_TOP_N) {
-      const uint8_t* ctr = s_pix + (sy + 3) * B_SP + pcx;
-      hi = ~f2ord(harris_at([&](int dy, int dx) { return (int)ctr[dy * B_SP + dx]; }, P.harris_k));
-    }
-    if (slot < G.cand_cap) cand[slot] = ((unsigned long long)hi << 32) | (unsigned)((ly << 16) | lx);
+    if (slot < G.cand_cap) cand[slot] = (unsigned long long)(unsigned)((ly << 16) | lx);
   };
   for (int j = tid; j < n1; j += B_THREADS) {
     const int idx = s_list[j];
@@ -528,6 +531,42 @@ __global__ void __launch_bounds__(B_THREADS, 4) k_fast(const OrbPlan P, const Bu
     uint4 o;   // lanes (o0,o2)(o1,o3) -> natural order
     o.x = prmt(a, b, 0x5410); o.y = prmt(a, b, 0x7632); o.z = prmt(cc, d, 0x5410); o.w = prmt(cc, d, 0x7632);
     *(uint4*)(box + (size_t)(y0 + iy) * G.bpitch + x0 + 8 * g) = o;
+  }
+}
+
+// =============================================================================================
+// Kernel C: Harris response of every NMS survivor (decision D5), one thread per candidate, grid-stride over the
+// candidates of a frame.  Replaces HarrisScore() (ref src/cuda/HarrisScore.cu:42-89, call site src/orb.cpp:65): the
+// reference blurs three full-frame product images to read them at <= 2N points; here the 9x9 neighbourhood of each
+// candidate is read from the level (L2-resident, just written) and the response goes into the high word of its key.
+constexpr int C_THREADS = 128;
+
+__global__ void __launch_bounds__(C_THREADS, 8) k_harris(const OrbPlan P, const Bufs B) {
+  const int f = blockIdx.y;
+  const int* cc = B.cand_count + f * ORB_MAX_LEVELS;
+  int total = 0;
+  for (int q = 0; q < P.nlevels; q++) total += min(cc[q], P.lv[q].cand_cap);
+  for (int i = blockIdx.x * C_THREADS + threadIdx.x; i < total; i += gridDim.x * C_THREADS) {
+    int l = 0, j = i;
+    while (j >= min(cc[l], P.lv[l].cand_cap)) { j -= min(cc[l], P.lv[l].cand_cap); l++; }
+    const OrbLevel& G = P.lv[l];
+    unsigned long long* slot = B.cand + (size_t)f * P.cand_frame_elems + G.cand_ofs + j;
+    const uint32_t xy = (uint32_t)*slot;
+    const int x = xy & 0xffff, y = xy >> 16, w = G.w, h = G.h;
+    const uint8_t* img;
+    int pitch;
+    if (l == 0) { img = B.frames + (size_t)f * B.frame_stride; pitch = B.pitch0; }
+    else { img = B.pyr + (size_t)f * P.pyr_frame_bytes + G.lvl_ofs; pitch = G.pitch; }
+    // candidates sit >= 3 pixels inside the level, the Sobel taps reach 4: only the outermost row / column of the
+    // 9x9 neighbourhood can leave the level and is reflected (BORDER_REFLECT_101, ref src/Sobel.cpp:29)
+    const int dxl = x >= 4 ? -4 : 4 - 2 * x, dxr = x + 4 < w ? 4 : 2 * (w - 1 - x) - 4;   // offsets of columns x-4, x+4
+    const int dyt = y >= 4 ? -4 : 4 - 2 * y, dyb = y + 4 < h ? 4 : 2 * (h - 1 - y) - 4;
+    const uint8_t* ctr = img + (size_t)y * pitch + x;
+    const float r = harris_at([&](int dy, int dx) {
+      const int oy = dy == -4 ? dyt : (dy == 4 ? dyb : dy), ox = dx == -4 ? dxl : (dx == 4 ? dxr : dx);
+      return (int)ctr[oy * pitch + ox];
+    }, P.harris_k);
+    *slot = ((unsigned long long)(~f2ord(r)) << 32) | xy;
   }
 }
 

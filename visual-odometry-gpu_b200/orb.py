@@ -88,7 +88,7 @@ def load_library():
     L.orb_last_launch_count.argtypes = [vp]
     L.orb_debug_eval_math.argtypes = [vp, i, vp, vp, i, vp]
     L.orb_set_profiling.argtypes = [vp, i]
-    L.orb_get_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 4), C.POINTER(C.c_int * 4)]
+    L.orb_get_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 5), C.POINTER(C.c_int * 5)]
     _lib = L
     return L
 
@@ -161,8 +161,8 @@ class Context:
         self._ck(self.lib.orb_set_profiling(self.h, int(on)))
 
     def stage_ms(self):
-        """(ms[4], launches[4]) per kernel (pyramid, FAST, select, describe) since the last call; needs set_profiling(True)."""
-        ms, n = (C.c_float * 4)(), (C.c_int * 4)()
+        """(ms[5], launches[5]) per kernel (pyramid, FAST, Harris, select, describe) since the last call; needs set_profiling(True)."""
+        ms, n = (C.c_float * 5)(), (C.c_int * 5)()
         self._ck(self.lib.orb_get_stage_ms(self.h, C.byref(ms), C.byref(n)))
         return list(ms), list(n)
 
