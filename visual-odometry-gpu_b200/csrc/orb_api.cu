@@ -418,7 +418,7 @@ int orb_create(const orb_params* p, orb_ctx** out) {
     const int C = ctx->chunk, Bn = p->max_batch;
     ctx->frames_pitch = align_up(p->max_width, 16);
     ctx->frames_slot_bytes = (size_t)ctx->frames_pitch * p->max_height;
-    CK(cudaMalloc(&ctx->d_frames, ctx->frames_slot_bytes * Bn));
+    CK(cudaMalloc(&ctx->d_frames, ctx->frames_slot_bytes * Bn + 16));   // k_pyramid may read one byte past the last row
     CK(cudaMalloc(&ctx->d_pyr, (size_t)M.pyr_frame_bytes * C));
     CK(cudaMalloc(&ctx->d_box, (size_t)M.box_frame_elems * 2 * C));
     CK(cudaMalloc(&ctx->d_cand, (size_t)M.cand_frame_elems * 8 * C));
@@ -559,7 +559,8 @@ int orb_detect_and_compute_batch(orb_ctx* ctx, const uint8_t* frames, int frames
   // and frame stride.  Host frames (and device frames that are not) go through the staging area, chunk by chunk on a
   // copy stream so that the transfer of chunk i+1 overlaps the kernels of chunk i; host outputs leave on a third
   // stream as soon as their chunk is described.
-  const bool direct = frames_on_device && ((uintptr_t)frames % 16 == 0) && pitch % 16 == 0 && frame_stride % 16 == 0;
+  // (and pitch > w: k_pyramid reads the byte after a row's last pixel, which must belong to the caller's buffer)
+  const bool direct = frames_on_device && ((uintptr_t)frames % 16 == 0) && pitch % 16 == 0 && frame_stride % 16 == 0 && pitch > (size_t)w;
   const uint8_t* src = direct ? frames : ctx->d_frames;
   const size_t stride = direct ? frame_stride : ctx->frames_slot_bytes;
   const int sp = direct ? (int)pitch : ctx->frames_pitch;

@@ -202,15 +202,19 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
   auto resize_column = [&](int col, int r0, int r1) {
     if (x0 - halo + col >= w + halo) return;
     const uint32_t xs = s_xs[col], xa = s_xa[col];
-    const uint32_t s0 = xs & 0xffff, s1 = xs >> 16;
     const int a0 = xa & 0xffff, a1 = xa >> 16;
+    // the second horizontal tap is the next byte (s1 == s0 + 1) except at the clamped right border, where a1 == 0
+    // and the byte after the row is only read, never used (the host guarantees it is addressable)
+    const uint8_t* p0 = src + (xs & 0xffff);
     r1 = min(r1, h + halo - (y0 - halo));
 #pragma unroll 3
     for (int ry = r0; ry < r1; ry++) {
       const uint2 ro = s_yo[ry];
       const uint32_t yb = s_yb[ry];
-      const int h0 = __ldg(src + (ro.x + s0)) * a0 + __ldg(src + (ro.x + s1)) * a1;
-      const int h1 = __ldg(src + (ro.y + s0)) * a0 + __ldg(src + (ro.y + s1)) * a1;
+      const uint8_t* q0 = p0 + ro.x;
+      const uint8_t* q1 = p0 + ro.y;
+      const int h0 = __ldg(q0) * a0 + __ldg(q0 + 1) * a1;
+      const int h1 = __ldg(q1) * a0 + __ldg(q1 + 1) * a1;
       const int v = ((((int)(yb & 0xffff) * (h0 >> 4)) >> 16) + (((int)(yb >> 16) * (h1 >> 4)) >> 16) + 2) >> 2;
       s_res[ry * A_RP + col] = (uint8_t)min(v, 255);
     }
@@ -283,14 +287,14 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
 constexpr int B_TW = 128, B_TH = 64, B_THREADS = 256;
 constexpr int B_SP = 160;              // pixel tile pitch (bytes); pixel x sits at column x - x0 + 16
 constexpr int B_PH = B_TH + 8;         // rows y0-4 .. y0+B_TH+3
-constexpr int B_SCP = 144;             // score pitch (u16); pixel x sits at column x - x0 + 8
+constexpr int B_SCP = 136;             // score pitch (u16); pixel x sits at column x - x0 + 4
 constexpr int B_SH = B_TH + 2;         // rows y0-1 .. y0+B_TH
-constexpr int B_LIST = 8704;           // >= (B_TW+2)*(B_TH+2) pretest positions; also holds the box rows
+constexpr int B_LIST = 4096;           // pretest passers kept in the list; denser tiles take the dense fallback
+constexpr int B_BOXH = B_TH / 2;       // box sums are produced in two halves of 32 rows (+4 halo rows)
 constexpr int B_SURV = 1024;
-constexpr int B_PIX_BYTES = B_PH * B_SP, B_SCORE_BYTES = B_SH * B_SCP * 2, B_LIST_BYTES = B_LIST * 2;
-constexpr int B_SMEM = B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES + B_SURV * 2 + 16;
-static_assert((B_TH + 4) * B_TW * 2 <= B_LIST_BYTES, "box rows alias the list");
-static_assert((B_TW + 2) * (B_TH + 2) <= B_LIST, "list capacity");
+constexpr int B_PIX_BYTES = B_PH * B_SP, B_SCORE_BYTES = B_SH * B_SCP * 2;
+constexpr int B_LIST_BYTES = (B_BOXH + 4) * B_TW * 2 > B_LIST * 2 ? (B_BOXH + 4) * B_TW * 2 : B_LIST * 2;
+constexpr int B_SMEM = B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES + B_SURV * 2 + 16;   // 40.7 KB -> 5 CTAs / SM
 
 __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs B) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -402,7 +406,8 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
         while (flags) {
           const int b = __ffs(flags) - 1;
           flags &= flags - 1;
-          s_list[off++] = (uint16_t)(rowbase + (b & 15));
+          if (off < B_LIST) s_list[off] = (uint16_t)(rowbase + (b & 15));
+          off++;
         }
       }
     }
@@ -410,12 +415,30 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
   __syncthreads();
 
   // ---- phase 3: ring test + SAD score for the passers, one pixel per thread --------------------
+  // (a tile with more than B_LIST passers -- synthetic worst cases only -- is rescanned densely instead)
   const int n1 = s_ctr[0];
-  for (int j = tid; j < n1; j += B_THREADS) {
-    const int idx = s_list[j];
-    const int sy = idx / B_SP, pcx = idx - sy * B_SP;
-    const int sc = fast_ring_score<B_SP>(s_pix + (sy + 3) * B_SP + pcx, thr, fn);
-    if (sc) s_score[sy * B_SCP + pcx - 8] = (uint16_t)sc;
+  const bool dense = n1 > B_LIST;
+  if (!dense) {
+    for (int j = tid; j < n1; j += B_THREADS) {
+      const int idx = s_list[j];
+      const int sy = idx / B_SP, pcx = idx - sy * B_SP;
+      const int sc = fast_ring_score<B_SP>(s_pix + (sy + 3) * B_SP + pcx, thr, fn);
+      if (sc) s_score[sy * B_SCP + pcx - 12] = (uint16_t)sc;
+    }
+  } else {
+    for (int i = tid; i < B_SH * (B_TW + 2); i += B_THREADS) {
+      const int sy = i / (B_TW + 2), pcx = 15 + (i - sy * (B_TW + 2));
+      const int x = x0 + pcx - 16, y = y0 - 1 + sy;
+      if (x < 3 || x >= w - 3 || y < 3 || y >= h - 3) continue;
+      const uint8_t* c = s_pix + (sy + 3) * B_SP + pcx;
+      const int Ip = c[0], hi = Ip + thr, lo = Ip - thr;
+      const int v0 = c[-3 * B_SP], v4 = c[3], v8 = c[3 * B_SP], v12 = c[-3];
+      const int br = (v0 >= hi) + (v4 >= hi) + (v8 >= hi) + (v12 >= hi);
+      const int dk = (v0 < hi && v0 <= lo) + (v4 < hi && v4 <= lo) + (v8 < hi && v8 <= lo) + (v12 < hi && v12 <= lo);
+      if (max(br, dk) < 3) continue;                       // ref src/orb_cpu.cpp:39-58
+      const int sc = fast_ring_score<B_SP>(c, thr, fn);
+      if (sc) s_score[sy * B_SCP + pcx - 12] = (uint16_t)sc;
+    }
   }
   __syncthreads();
 
@@ -428,21 +451,25 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
     const int lx = x0 + pcx - 16, ly = y0 - 1 + sy;
     if (slot < G.cand_cap) cand[slot] = (unsigned long long)(unsigned)((ly << 16) | lx);
   };
-  for (int j = tid; j < n1; j += B_THREADS) {
-    const int idx = s_list[j];
+  auto nms_one = [&](int idx) {
     const int sy = idx / B_SP, pcx = idx - sy * B_SP;
-    if (sy < 1 || sy > B_TH || pcx < 16 || pcx >= 16 + B_TW) continue;   // halo positions belong to neighbours
-    const uint16_t* s = s_score + sy * B_SCP + pcx - 8;
+    if (sy < 1 || sy > B_TH || pcx < 16 || pcx >= 16 + B_TW) return;   // halo positions belong to neighbours
+    const uint16_t* s = s_score + sy * B_SCP + pcx - 12;
     const int v = s[0];
-    if (v == 0) continue;
-    if (nmsr) {
+    if (v == 0) return;
+    if (nmsr) {   // ties keep both (ref src/orb_cpu.cpp:126)
       int mx = max(max(max(s[-B_SCP - 1], s[-B_SCP]), max(s[-B_SCP + 1], s[-1])),
                    max(max(s[1], s[B_SCP - 1]), max(s[B_SCP], s[B_SCP + 1])));
-      if (v < mx) continue;
+      if (v < mx) return;
     }
     const int slot = atomicAdd(&s_ctr[1], 1);
     if (slot < B_SURV) s_surv[slot] = (uint16_t)idx;
-    else emit(idx, atomicAdd(gcount, 1));   // list full: finish this survivor inline
+    else emit(idx, atomicAdd(gcount, 1));   // survivor list full: finish this one inline
+  };
+  if (!dense) {
+    for (int j = tid; j < n1; j += B_THREADS) nms_one(s_list[j]);
+  } else {
+    for (int i = tid; i < B_TH * B_TW; i += B_THREADS) nms_one((1 + i / B_TW) * B_SP + 16 + (i % B_TW));
   }
   __syncthreads();
   const int nsurv = min(s_ctr[1], B_SURV);
@@ -454,43 +481,67 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
   }
   __syncthreads();
 
-  // ---- phase 5: 5x5 box sums (replaces the int32 integral image of ref src/orb_cpu.cpp:207-208) ----
-  uint16_t* s_bh = s_list;
-  const uint32_t M = 0x00ff00ffu;
-  for (int it = tid; it < (B_TH + 4) * (B_TW / 8); it += B_THREADS) {
-    const int r = it / (B_TW / 8), g = it - r * (B_TW / 8);
-    const uint8_t* rc = s_pix + (r + 2) * B_SP + 16 + 8 * g;
-    const uint32_t m = *(const uint32_t*)(rc - 4), p = *(const uint32_t*)(rc + 8);
-    const uint2 cc = *(const uint2*)rc;
-    const uint32_t w0 = prmt(m, cc.x, 0x5432), w1 = prmt(cc.x, cc.y, 0x5432), w2 = prmt(cc.y, p, 0x5432);
-    const uint32_t q0 = w0 & M, q1 = (w0 >> 8) & M, q2 = cc.x & M, q3 = (cc.x >> 8) & M, q4 = w1 & M, q5 = (w1 >> 8) & M,
-                   q6 = cc.y & M, q7 = (cc.y >> 8) & M, q8 = w2 & M, q9 = (w2 >> 8) & M;
-    uint4 o;
-    o.x = q0 + q1 + q2 + q3 + q4;
-    o.y = q1 + q2 + q3 + q4 + q5;
-    o.z = q4 + q5 + q6 + q7 + q8;
-    o.w = q5 + q6 + q7 + q8 + q9;
-    *(uint4*)(s_bh + r * B_TW + 8 * g) = o;
-  }
-  __syncthreads();
-  // ---- phase 6: strip sums for BRIEF boxes that leave the image on the right / bottom (decision D7) ------
+  // ---- phase 5/6: 5x5 box sums (replace the int32 integral image of ref src/orb_cpu.cpp:207-208) and the strip
+  // sums for BRIEF boxes that leave the image on the right / bottom (decision D7):
   //   ey[cx] = sum of rows [0,h-4) x cols [cx-2,cx+2]   (ey[0] instead holds column 0 over rows [0,h-4))
   //   rs[y]  = sum of row y over cols [0,w-4)
   // each tile adds its share; k_describe turns them into the values of the reference's wrapped integral taps.
-  {
-    int* ey = B.edge + (size_t)f * P.edge_frame_elems + G.edge_ofs;
-    int* rs = ey + G.edge_w;
-    if (tid < 64) {            // warp 0-1: column strips, thread = (8-column group, quarter of the rows)
+  // The tile is processed in two halves of 32 rows so that the row buffer stays small.
+  uint16_t* s_bh = s_list;
+  const uint32_t M = 0x00ff00ffu;
+  uint16_t* box = B.box + (size_t)f * P.box_frame_elems + G.box_ofs;
+  int* ey = B.edge + (size_t)f * P.edge_frame_elems + G.edge_ofs;
+  int* rs = ey + G.edge_w;
+  if (tid >= B_THREADS - B_TH) {   // last two warps: row sums over columns < w-4 (and column 0 for the wrapped taps)
+    const int iy = tid - (B_THREADS - B_TH), y = y0 + iy;
+    if (y < h) {
+      const int ncol = min(B_TW, w - 4 - x0);
+      const uint8_t* r = s_pix + (iy + 4) * B_SP + 16;
+      unsigned acc = 0;
+      for (int c = 0; c < ncol; c += 16) {
+        const uint4 v = *(const uint4*)(r + c);
+        const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int nb = ncol - c - 4 * k;
+          if (nb > 0) acc = __dp4a(nb >= 4 ? wd[k] : (wd[k] & ((1u << (8 * nb)) - 1u)), 0x01010101u, acc);
+        }
+      }
+      if (ncol > 0) atomicAdd(rs + y, (int)acc);
+      if (x0 == 0 && y < h - 4) atomicAdd(ey, (int)r[0]);
+    }
+  }
+#pragma unroll 1
+  for (int half = 0; half < 2; half++) {
+    const int yb = y0 + half * B_BOXH;               // first output row of this half
+    if (yb >= h) break;                              // uniform
+    // horizontal 5-sums of rows yb-2 .. yb+33, 8 pixels per item, lanes (o0,o2)(o1,o3)(o4,o6)(o5,o7)
+    for (int it = tid; it < (B_BOXH + 4) * (B_TW / 8); it += B_THREADS) {
+      const int r = it / (B_TW / 8), g = it - r * (B_TW / 8);
+      const uint8_t* rc = s_pix + (half * B_BOXH + r + 2) * B_SP + 16 + 8 * g;
+      const uint32_t m = *(const uint32_t*)(rc - 4), p = *(const uint32_t*)(rc + 8);
+      const uint2 cc = *(const uint2*)rc;
+      const uint32_t w0 = prmt(m, cc.x, 0x5432), w1 = prmt(cc.x, cc.y, 0x5432), w2 = prmt(cc.y, p, 0x5432);
+      const uint32_t q0 = w0 & M, q1 = (w0 >> 8) & M, q2 = cc.x & M, q3 = (cc.x >> 8) & M, q4 = w1 & M, q5 = (w1 >> 8) & M,
+                     q6 = cc.y & M, q7 = (cc.y >> 8) & M, q8 = w2 & M, q9 = (w2 >> 8) & M;
+      uint4 o;
+      o.x = q0 + q1 + q2 + q3 + q4;
+      o.y = q1 + q2 + q3 + q4 + q5;
+      o.z = q4 + q5 + q6 + q7 + q8;
+      o.w = q5 + q6 + q7 + q8 + q9;
+      *(uint4*)(s_bh + r * B_TW + 8 * g) = o;
+    }
+    __syncthreads();
+    if (tid < 32) {            // warp 0: column strips, thread = (8-column group, 16 rows)
       const int g = tid & 15, q = tid >> 4;
-      const int rows = min(16, h - 4 - y0 - 16 * q);            // rows of this quarter that lie above row h-4
+      const int rows = min(16, h - 4 - yb - 16 * q);            // rows of this slice that lie above row h-4
       if (rows > 0) {
-        const uint16_t* c = s_bh + (2 + 16 * q) * B_TW + 8 * g;   // horizontal 5-sums of row y0 + 16q
+        const uint16_t* c = s_bh + (2 + 16 * q) * B_TW + 8 * g;   // horizontal 5-sums of row yb + 16q
         uint4 acc = make_uint4(0, 0, 0, 0);                       // 16-bit lanes: <= 16 * 1275
         for (int r = 0; r < rows; r++) {
           const uint4 v = *(const uint4*)(c + r * B_TW);
           acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
-        // lanes (o0,o2)(o1,o3)(o4,o6)(o5,o7) -> pixel order
         const int val[8] = {(int)(acc.x & 0xffff), (int)(acc.y & 0xffff), (int)(acc.x >> 16), (int)(acc.y >> 16),
                             (int)(acc.z & 0xffff), (int)(acc.w & 0xffff), (int)(acc.z >> 16), (int)(acc.w >> 16)};
 #pragma unroll
@@ -499,38 +550,20 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
           if (x >= 2 && x <= w - 3) atomicAdd(ey + x, val[j]);
         }
       }
-    } else if (tid < 64 + B_TH) {   // warp 2-3: row sums over columns < w-4 (and column 0 for the wrapped taps)
-      const int iy = tid - 64, y = y0 + iy;
-      if (y < h) {
-        const int ncol = min(B_TW, w - 4 - x0);
-        const uint8_t* r = s_pix + (iy + 4) * B_SP + 16;
-        unsigned acc = 0;
-        for (int c = 0; c < ncol; c += 16) {
-          const uint4 v = *(const uint4*)(r + c);
-          const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const int nb = ncol - c - 4 * k;
-            if (nb > 0) acc = __dp4a(nb >= 4 ? wd[k] : (wd[k] & ((1u << (8 * nb)) - 1u)), 0x01010101u, acc);
-          }
-        }
-        if (ncol > 0) atomicAdd(rs + y, (int)acc);
-        if (x0 == 0 && y < h - 4) atomicAdd(ey, (int)r[0]);
-      }
     }
-  }
-  uint16_t* box = B.box + (size_t)f * P.box_frame_elems + G.box_ofs;
-  for (int it = tid; it < B_TH * (B_TW / 8); it += B_THREADS) {
-    const int iy = it / (B_TW / 8), g = it - iy * (B_TW / 8);
-    if (y0 + iy >= h || x0 + 8 * g >= G.bpitch) continue;
-    const uint16_t* c = s_bh + iy * B_TW + 8 * g;
-    const uint4 r0 = *(const uint4*)c, r1 = *(const uint4*)(c + B_TW), r2 = *(const uint4*)(c + 2 * B_TW),
-                r3 = *(const uint4*)(c + 3 * B_TW), r4 = *(const uint4*)(c + 4 * B_TW);
-    const uint32_t a = r0.x + r1.x + r2.x + r3.x + r4.x, b = r0.y + r1.y + r2.y + r3.y + r4.y;
-    const uint32_t cc = r0.z + r1.z + r2.z + r3.z + r4.z, d = r0.w + r1.w + r2.w + r3.w + r4.w;
-    uint4 o;   // lanes (o0,o2)(o1,o3) -> natural order
-    o.x = prmt(a, b, 0x5410); o.y = prmt(a, b, 0x7632); o.z = prmt(cc, d, 0x5410); o.w = prmt(cc, d, 0x7632);
-    *(uint4*)(box + (size_t)(y0 + iy) * G.bpitch + x0 + 8 * g) = o;
+    for (int it = tid; it < B_BOXH * (B_TW / 8); it += B_THREADS) {
+      const int iy = it / (B_TW / 8), g = it - iy * (B_TW / 8);
+      if (yb + iy >= h || x0 + 8 * g >= G.bpitch) continue;
+      const uint16_t* c = s_bh + iy * B_TW + 8 * g;
+      const uint4 r0 = *(const uint4*)c, r1 = *(const uint4*)(c + B_TW), r2 = *(const uint4*)(c + 2 * B_TW),
+                  r3 = *(const uint4*)(c + 3 * B_TW), r4 = *(const uint4*)(c + 4 * B_TW);
+      const uint32_t a = r0.x + r1.x + r2.x + r3.x + r4.x, b = r0.y + r1.y + r2.y + r3.y + r4.y;
+      const uint32_t cc = r0.z + r1.z + r2.z + r3.z + r4.z, d = r0.w + r1.w + r2.w + r3.w + r4.w;
+      uint4 o;   // lanes (o0,o2)(o1,o3) -> natural order
+      o.x = prmt(a, b, 0x5410); o.y = prmt(a, b, 0x7632); o.z = prmt(cc, d, 0x5410); o.w = prmt(cc, d, 0x7632);
+      *(uint4*)(box + (size_t)(yb + iy) * G.bpitch + x0 + 8 * g) = o;
+    }
+    __syncthreads();
   }
 }
 
