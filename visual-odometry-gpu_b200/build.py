@@ -38,6 +38,7 @@ def needs_build():
 def build(force=False, verbose=False, extra=()):
     if not force and not needs_build():
         return LIB
+    extra = list(extra) + os.environ.get("ORB_NVCC_EXTRA", "").split()
     cmd = [nvcc_path()] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     env = dict(os.environ)

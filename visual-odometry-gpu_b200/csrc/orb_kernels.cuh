@@ -290,11 +290,10 @@ constexpr int B_PH = B_TH + 8;         // rows y0-4 .. y0+B_TH+3
 constexpr int B_SCP = 136;             // score pitch (u16); pixel x sits at column x - x0 + 4
 constexpr int B_SH = B_TH + 2;         // rows y0-1 .. y0+B_TH
 constexpr int B_LIST = 4096;           // pretest passers kept in the list; denser tiles take the dense fallback
-constexpr int B_BOXH = B_TH / 2;       // box sums are produced in two halves of 32 rows (+4 halo rows)
 constexpr int B_SURV = 1024;
 constexpr int B_PIX_BYTES = B_PH * B_SP, B_SCORE_BYTES = B_SH * B_SCP * 2;
-constexpr int B_LIST_BYTES = (B_BOXH + 4) * B_TW * 2 > B_LIST * 2 ? (B_BOXH + 4) * B_TW * 2 : B_LIST * 2;
-constexpr int B_SMEM = B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES + B_SURV * 2 + 16;   // 40.7 KB -> 5 CTAs / SM
+constexpr int B_LIST_BYTES = B_LIST * 2;
+constexpr int B_SMEM = B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES + B_SURV * 2 + 16;   // 39.6 KB -> 5 CTAs / SM
 
 __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs B) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -486,13 +485,55 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
   //   ey[cx] = sum of rows [0,h-4) x cols [cx-2,cx+2]   (ey[0] instead holds column 0 over rows [0,h-4))
   //   rs[y]  = sum of row y over cols [0,w-4)
   // each tile adds its share; k_describe turns them into the values of the reference's wrapped integral taps.
-  // The tile is processed in two halves of 32 rows so that the row buffer stays small.
-  uint16_t* s_bh = s_list;
-  const uint32_t M = 0x00ff00ffu;
-  uint16_t* box = B.box + (size_t)f * P.box_frame_elems + G.box_ofs;
+  // Threads 0..127 own an 8-pixel column group and 8 output rows each: horizontal 5-sums of 12 input rows stay in
+  // registers (16-bit lanes (o0,o2)(o1,o3)(o4,o6)(o5,o7)), five consecutive ones add up to a box row.  Threads
+  // 192..255 produce the row sums meanwhile.
+  int* s_ey = (int*)s_list;                       // [B_TW] column-strip sums of this tile (the list is dead by now)
+  if (tid < B_TW) s_ey[tid] = 0;
+  __syncthreads();
   int* ey = B.edge + (size_t)f * P.edge_frame_elems + G.edge_ofs;
   int* rs = ey + G.edge_w;
-  if (tid >= B_THREADS - B_TH) {   // last two warps: row sums over columns < w-4 (and column 0 for the wrapped taps)
+  if (tid < B_TW) {
+    const uint32_t M = 0x00ff00ffu;
+    const int g = tid & 15, seg = tid >> 4;
+    const int yb = y0 + 8 * seg;                                    // first output row of this thread
+    if (yb < h && x0 + 8 * g < G.bpitch) {
+      uint16_t* box = B.box + (size_t)f * P.box_frame_elems + G.box_ofs + (size_t)yb * G.bpitch + x0 + 8 * g;
+      const uint8_t* rc = s_pix + (8 * seg + 2) * B_SP + 16 + 8 * g;   // input row yb - 2
+      const int nstrip = min(8, h - 4 - yb);                         // owned rows that lie above row h-4
+      uint4 hs[5];
+      uint4 strip = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int r = 0; r < 12; r++) {
+        const uint32_t m = *(const uint32_t*)(rc - 4), p = *(const uint32_t*)(rc + 8);
+        const uint2 cc = *(const uint2*)rc;
+        rc += B_SP;
+        const uint32_t w0 = prmt(m, cc.x, 0x5432), w1 = prmt(cc.x, cc.y, 0x5432), w2 = prmt(cc.y, p, 0x5432);
+        const uint32_t q0 = w0 & M, q1 = (w0 >> 8) & M, q2 = cc.x & M, q3 = (cc.x >> 8) & M, q4 = w1 & M, q5 = (w1 >> 8) & M,
+                       q6 = cc.y & M, q7 = (cc.y >> 8) & M, q8 = w2 & M, q9 = (w2 >> 8) & M;
+        uint4 o;
+        o.x = q0 + q1 + q2 + q3 + q4;
+        o.y = q1 + q2 + q3 + q4 + q5;
+        o.z = q4 + q5 + q6 + q7 + q8;
+        o.w = q5 + q6 + q7 + q8 + q9;
+        hs[r % 5] = o;
+        if (r >= 2 && r - 2 < nstrip) { strip.x += o.x; strip.y += o.y; strip.z += o.z; strip.w += o.w; }
+        if (r >= 4 && yb + r - 4 < h) {                              // box row yb + r - 4 = sum of the last five
+          const uint32_t a = hs[0].x + hs[1].x + hs[2].x + hs[3].x + hs[4].x, b = hs[0].y + hs[1].y + hs[2].y + hs[3].y + hs[4].y;
+          const uint32_t c = hs[0].z + hs[1].z + hs[2].z + hs[3].z + hs[4].z, d = hs[0].w + hs[1].w + hs[2].w + hs[3].w + hs[4].w;
+          uint4 v;   // lanes (o0,o2)(o1,o3) -> natural order
+          v.x = prmt(a, b, 0x5410); v.y = prmt(a, b, 0x7632); v.z = prmt(c, d, 0x5410); v.w = prmt(c, d, 0x7632);
+          *(uint4*)(box + (size_t)(r - 4) * G.bpitch) = v;
+        }
+      }
+      if (nstrip > 0) {
+        const int val[8] = {(int)(strip.x & 0xffff), (int)(strip.y & 0xffff), (int)(strip.x >> 16), (int)(strip.y >> 16),
+                            (int)(strip.z & 0xffff), (int)(strip.w & 0xffff), (int)(strip.z >> 16), (int)(strip.w >> 16)};
+#pragma unroll
+        for (int j = 0; j < 8; j++) atomicAdd(&s_ey[8 * g + j], val[j]);
+      }
+    }
+  } else if (tid >= B_THREADS - B_TH) {   // last two warps: row sums over columns < w-4 (and column 0 for the wrapped taps)
     const int iy = tid - (B_THREADS - B_TH), y = y0 + iy;
     if (y < h) {
       const int ncol = min(B_TW, w - 4 - x0);
@@ -511,59 +552,10 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
       if (x0 == 0 && y < h - 4) atomicAdd(ey, (int)r[0]);
     }
   }
-#pragma unroll 1
-  for (int half = 0; half < 2; half++) {
-    const int yb = y0 + half * B_BOXH;               // first output row of this half
-    if (yb >= h) break;                              // uniform
-    // horizontal 5-sums of rows yb-2 .. yb+33, 8 pixels per item, lanes (o0,o2)(o1,o3)(o4,o6)(o5,o7)
-    for (int it = tid; it < (B_BOXH + 4) * (B_TW / 8); it += B_THREADS) {
-      const int r = it / (B_TW / 8), g = it - r * (B_TW / 8);
-      const uint8_t* rc = s_pix + (half * B_BOXH + r + 2) * B_SP + 16 + 8 * g;
-      const uint32_t m = *(const uint32_t*)(rc - 4), p = *(const uint32_t*)(rc + 8);
-      const uint2 cc = *(const uint2*)rc;
-      const uint32_t w0 = prmt(m, cc.x, 0x5432), w1 = prmt(cc.x, cc.y, 0x5432), w2 = prmt(cc.y, p, 0x5432);
-      const uint32_t q0 = w0 & M, q1 = (w0 >> 8) & M, q2 = cc.x & M, q3 = (cc.x >> 8) & M, q4 = w1 & M, q5 = (w1 >> 8) & M,
-                     q6 = cc.y & M, q7 = (cc.y >> 8) & M, q8 = w2 & M, q9 = (w2 >> 8) & M;
-      uint4 o;
-      o.x = q0 + q1 + q2 + q3 + q4;
-      o.y = q1 + q2 + q3 + q4 + q5;
-      o.z = q4 + q5 + q6 + q7 + q8;
-      o.w = q5 + q6 + q7 + q8 + q9;
-      *(uint4*)(s_bh + r * B_TW + 8 * g) = o;
-    }
-    __syncthreads();
-    if (tid < 32) {            // warp 0: column strips, thread = (8-column group, 16 rows)
-      const int g = tid & 15, q = tid >> 4;
-      const int rows = min(16, h - 4 - yb - 16 * q);            // rows of this slice that lie above row h-4
-      if (rows > 0) {
-        const uint16_t* c = s_bh + (2 + 16 * q) * B_TW + 8 * g;   // horizontal 5-sums of row yb + 16q
-        uint4 acc = make_uint4(0, 0, 0, 0);                       // 16-bit lanes: <= 16 * 1275
-        for (int r = 0; r < rows; r++) {
-          const uint4 v = *(const uint4*)(c + r * B_TW);
-          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
-        const int val[8] = {(int)(acc.x & 0xffff), (int)(acc.y & 0xffff), (int)(acc.x >> 16), (int)(acc.y >> 16),
-                            (int)(acc.z & 0xffff), (int)(acc.w & 0xffff), (int)(acc.z >> 16), (int)(acc.w >> 16)};
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const int x = x0 + 8 * g + j;
-          if (x >= 2 && x <= w - 3) atomicAdd(ey + x, val[j]);
-        }
-      }
-    }
-    for (int it = tid; it < B_BOXH * (B_TW / 8); it += B_THREADS) {
-      const int iy = it / (B_TW / 8), g = it - iy * (B_TW / 8);
-      if (yb + iy >= h || x0 + 8 * g >= G.bpitch) continue;
-      const uint16_t* c = s_bh + iy * B_TW + 8 * g;
-      const uint4 r0 = *(const uint4*)c, r1 = *(const uint4*)(c + B_TW), r2 = *(const uint4*)(c + 2 * B_TW),
-                  r3 = *(const uint4*)(c + 3 * B_TW), r4 = *(const uint4*)(c + 4 * B_TW);
-      const uint32_t a = r0.x + r1.x + r2.x + r3.x + r4.x, b = r0.y + r1.y + r2.y + r3.y + r4.y;
-      const uint32_t cc = r0.z + r1.z + r2.z + r3.z + r4.z, d = r0.w + r1.w + r2.w + r3.w + r4.w;
-      uint4 o;   // lanes (o0,o2)(o1,o3) -> natural order
-      o.x = prmt(a, b, 0x5410); o.y = prmt(a, b, 0x7632); o.z = prmt(cc, d, 0x5410); o.w = prmt(cc, d, 0x7632);
-      *(uint4*)(box + (size_t)(yb + iy) * G.bpitch + x0 + 8 * g) = o;
-    }
-    __syncthreads();
+  __syncthreads();
+  if (tid < B_TW) {
+    const int x = x0 + tid, v = s_ey[tid];
+    if (v && x >= 2 && x <= w - 3) atomicAdd(ey + x, v);
   }
 }
 
@@ -720,7 +712,13 @@ __global__ void __launch_bounds__(K2_THREADS) k_select(const OrbPlan P, const Bu
 
 // ---------------------------------------------------------------------------------------------
 // Orientation + rotated BRIEF: one warp per keypoint.
-constexpr int K3_WARPS = 8;
+#ifndef ORB_K3_WARPS
+#define ORB_K3_WARPS 2
+#endif
+#ifndef ORB_K3_MINB
+#define ORB_K3_MINB 12
+#endif
+constexpr int K3_WARPS = ORB_K3_WARPS;
 
 struct EdgeSrc {
   const uint8_t* __restrict__ img; int pitch;
@@ -883,20 +881,31 @@ __device__ __forceinline__ void brief_of(const uint8_t* __restrict__ img, int pi
   *out_words = mine;
 }
 
-__global__ void __launch_bounds__(K3_WARPS * 32, 4) k_describe(const OrbPlan P, const Bufs B, const DescribeJob J) {
+__global__ void __launch_bounds__(K3_WARPS * 32, ORB_K3_MINB) k_describe(const OrbPlan P, const Bufs B, const DescribeJob J) {
   const int lane = threadIdx.x & 31;
   const int widx = blockIdx.x * K3_WARPS + (threadIdx.x >> 5);
   const int f = blockIdx.y;
   int l = 0, i = widx;
   int x, y;
   float resp = 0.f;
+  __shared__ int s_pref[ORB_MAX_LEVELS + 1];   // exclusive prefix of the frame's kept counts (levels are concatenated)
   if (J.mode == 0) {
-    const int* kc = B.kept_count + f * ORB_MAX_LEVELS;
-    int total = 0;
-    for (int q = 0; q < P.nlevels; q++) total += kc[q];
+    if (threadIdx.x < 32) {
+      const int c = lane < P.nlevels ? B.kept_count[f * ORB_MAX_LEVELS + lane] : 0;
+      int incl = c;
+#pragma unroll
+      for (int d = 1; d < 16; d <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      if (lane <= ORB_MAX_LEVELS) s_pref[lane] = incl - c;   // lane == nlevels .. 16 hold the total
+    }
+    __syncthreads();
+    const int total = s_pref[P.nlevels];
     if (widx == 0 && lane == 0) B.out_n[f] = min(total, B.out_cap);
     if (widx >= total || widx >= B.out_cap) return;
-    while (i >= kc[l]) { i -= kc[l]; l++; }
+    while (l + 1 < P.nlevels && widx >= s_pref[l + 1]) l++;
+    i = widx - s_pref[l];
     uint32_t xy = B.kept_xy[(size_t)f * P.kept_per_frame + P.lv[l].kept_ofs + i];
     resp = B.kept_r[(size_t)f * P.kept_per_frame + P.lv[l].kept_ofs + i];
     x = xy & 0xffff; y = xy >> 16;
