@@ -159,9 +159,9 @@ __device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<
 
 // =============================================================================================
 // Kernel A: pyramid level l >= 1 = GaussianBlur5x5( resize_linear(level 0) )  (ref src/orb_cpu.cpp:283-290).
-// One CTA per 128x32 output tile.  Bilinear taps come from host tables (no floating point on the device);
+// One CTA per 128x64 output tile.  Bilinear taps come from host tables (no floating point on the device);
 // the blur runs in 16-bit lanes, two pixels per register, and each level is written exactly once.
-constexpr int A_TW = 128, A_TH = 32, A_THREADS = 256;
+constexpr int A_TW = 128, A_TH = 64, A_THREADS = 256;
 constexpr int A_RW = A_TW + 4, A_RH = A_TH + 4;   // resized region incl. blur halo 2
 constexpr int A_RP = 136;                          // shared pitch of resized rows (bytes)
 
@@ -222,10 +222,9 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
   {
     const int half = tid >> 7, rows_half = (rh + 1) >> 1;
     resize_column(tid & 127, half * rows_half, min(rh, (half + 1) * rows_half));
-    if (rw > A_TW) {                                   // the 4 extra halo columns: 4 x rh pixels, one per thread
-      const int extra = tid;                           // column 128 + extra % 4, row extra / 4
-      if (extra < 4 * rh) resize_column(A_TW + (extra & 3), extra >> 2, (extra >> 2) + 1);
-    }
+    if (rw > A_TW)                                     // the 4 extra halo columns: 4 x rh pixels, one per thread
+      for (int extra = tid; extra < 4 * rh; extra += A_THREADS)   // column 128 + extra % 4, row extra / 4
+        resize_column(A_TW + (extra & 3), extra >> 2, (extra >> 2) + 1);
   }
   __syncthreads();
 
