@@ -59,7 +59,7 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """SM clock + throttle reasons during the timed regions (pynvml, 20 ms period)."""
+    """SM clock + throttle reasons during the timed regions (pynvml, 5 ms period)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -94,7 +94,7 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(k)
                 except Exception:
                     pass
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def stop(self):
         self._stop_evt.set()
@@ -297,9 +297,9 @@ def main():
                    "stage_ms_per_step": [m / prof_steps for m in st_ms], "stage_share": stage_share,
                    "pass_b_min_bytes_per_frame": b_min, "pass_hbm_gbs_per_gpu": pass_gbs, "pass_hbm_frac": pass_gbs / peak,
                    "peak_source": peak_src},
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(F * H * PITCH),
-                "d2h_bytes_per_step": int(F * cap * 44 + F * 4)},
-        "gpu_launches": int(launches_per_step * args.steps),
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(F * H * PITCH) * world,
+                "d2h_bytes_per_step": int(F * cap * 44 + F * 4) * world},
+        "gpu_launches": int(launches_per_step * args.steps) * world,
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic,
                      "algorithmic_bytes_per_launch": alg_bytes[dom] * frames_per_launch, "avg_launch_ms": k1_ms},
