@@ -846,33 +846,45 @@ __device__ __forceinline__ void brief_of(const uint8_t* __restrict__ img, int pi
     *out_words = mine;
     return;
   }
+  // keypoint near a border: only the sides it is close to need the bound rule of :240-245 (against the integral image
+  // dims W+1, H+1), and only right / bottom proximity can produce boxes that leave the image (decision D7)
+  const bool nearL = kx - 19 < 2, nearT = ky - 19 < 2, nearR = kx + 19 > W - 3, nearB = ky + 19 > H - 3;
   for (int wd = 0; wd < 8; wd++) {
     const float4 t = __ldg(pattern + wd * 32 + lane);
-    int cx1 = kx + orbm::lround_f(orbm::fsub(orbm::fmul(c, t.x), orbm::fmul(s, t.y)));
-    int cy1 = ky + orbm::lround_f(orbm::fadd(orbm::fmul(s, t.x), orbm::fmul(c, t.y)));
-    int cx2 = kx + orbm::lround_f(orbm::fsub(orbm::fmul(c, t.z), orbm::fmul(s, t.w)));
-    int cy2 = ky + orbm::lround_f(orbm::fadd(orbm::fmul(s, t.z), orbm::fmul(c, t.w)));
-    // bound rule of :240-245 against the integral image dims (W+1, H+1)
-    const bool skip = cx1 < 2 || cy1 < 2 || cx1 > W - 1 || cy1 > H - 1 || cx2 < 2 || cy2 < 2 || cx2 > W - 1 || cy2 > H - 1;
-    const bool k1 = !skip && cx1 > W - 3 && cy1 > H - 3, k2 = !skip && cx2 > W - 3 && cy2 > H - 3;   // corner boxes
+    const int cx1 = kx + orbm::lround_f(orbm::fsub(orbm::fmul(c, t.x), orbm::fmul(s, t.y)));
+    const int cy1 = ky + orbm::lround_f(orbm::fadd(orbm::fmul(s, t.x), orbm::fmul(c, t.y)));
+    const int cx2 = kx + orbm::lround_f(orbm::fsub(orbm::fmul(c, t.z), orbm::fmul(s, t.w)));
+    const int cy2 = ky + orbm::lround_f(orbm::fadd(orbm::fmul(s, t.z), orbm::fmul(c, t.w)));
+    bool skip = false;
+    if (nearL) skip |= cx1 < 2 || cx2 < 2;
+    if (nearT) skip |= cy1 < 2 || cy2 < 2;
+    if (nearR) skip |= cx1 > W - 1 || cx2 > W - 1;
+    if (nearB) skip |= cy1 > H - 1 || cy2 > H - 1;
     int s1 = 0, s2 = 0;
-    if (!skip) {
-      if (!k1) s1 = (cx1 > W - 3 || cy1 > H - 3) ? box_edge_lane(E, cx1, cy1) : (int)box[(size_t)cy1 * bpitch + cx1];
-      if (!k2) s2 = (cx2 > W - 3 || cy2 > H - 3) ? box_edge_lane(E, cx2, cy2) : (int)box[(size_t)cy2 * bpitch + cx2];
-    }
-    unsigned pend = __ballot_sync(0xffffffffu, k1);
-    while (pend) {
-      int src = __ffs(pend) - 1;
-      pend &= pend - 1;
-      int v = box_corner(E, __shfl_sync(0xffffffffu, cx1, src), __shfl_sync(0xffffffffu, cy1, src), lane);
-      if (lane == src) s1 = v;
-    }
-    pend = __ballot_sync(0xffffffffu, k2);
-    while (pend) {
-      int src = __ffs(pend) - 1;
-      pend &= pend - 1;
-      int v = box_corner(E, __shfl_sync(0xffffffffu, cx2, src), __shfl_sync(0xffffffffu, cy2, src), lane);
-      if (lane == src) s2 = v;
+    if (!(nearR || nearB)) {
+      if (!skip) { s1 = box[(size_t)cy1 * bpitch + cx1]; s2 = box[(size_t)cy2 * bpitch + cx2]; }
+    } else {
+      const bool k1 = !skip && cx1 > W - 3 && cy1 > H - 3, k2 = !skip && cx2 > W - 3 && cy2 > H - 3;   // corner boxes
+      if (!skip) {
+        if (!k1) s1 = (cx1 > W - 3 || cy1 > H - 3) ? box_edge_lane(E, cx1, cy1) : (int)box[(size_t)cy1 * bpitch + cx1];
+        if (!k2) s2 = (cx2 > W - 3 || cy2 > H - 3) ? box_edge_lane(E, cx2, cy2) : (int)box[(size_t)cy2 * bpitch + cx2];
+      }
+      if (nearR && nearB) {
+        unsigned pend = __ballot_sync(0xffffffffu, k1);
+        while (pend) {
+          int src = __ffs(pend) - 1;
+          pend &= pend - 1;
+          int v = box_corner(E, __shfl_sync(0xffffffffu, cx1, src), __shfl_sync(0xffffffffu, cy1, src), lane);
+          if (lane == src) s1 = v;
+        }
+        pend = __ballot_sync(0xffffffffu, k2);
+        while (pend) {
+          int src = __ffs(pend) - 1;
+          pend &= pend - 1;
+          int v = box_corner(E, __shfl_sync(0xffffffffu, cx2, src), __shfl_sync(0xffffffffu, cy2, src), lane);
+          if (lane == src) s2 = v;
+        }
+      }
     }
     uint32_t word = __ballot_sync(0xffffffffu, !skip && s1 < s2);
     if (lane == wd) mine = word;
