@@ -711,11 +711,19 @@ __global__ void __launch_bounds__(K2_THREADS) k_select(const OrbPlan P, const Bu
 
 // ---------------------------------------------------------------------------------------------
 // Orientation + rotated BRIEF: one warp per keypoint.
+#ifndef ORB_BRIEF_UNROLL
+#define ORB_BRIEF_UNROLL 8
+#endif
+constexpr int BRIEF_UNROLL = ORB_BRIEF_UNROLL;
+#ifndef ORB_ORIENT_UNROLL
+#define ORB_ORIENT_UNROLL 31
+#endif
+constexpr int ORIENT_UNROLL = ORB_ORIENT_UNROLL;
 #ifndef ORB_K3_WARPS
 #define ORB_K3_WARPS 2
 #endif
 #ifndef ORB_K3_MINB
-#define ORB_K3_MINB 12
+#define ORB_K3_MINB 16
 #endif
 constexpr int K3_WARPS = ORB_K3_WARPS;
 
@@ -734,7 +742,7 @@ struct EdgeSrc {
 //   right cols only  : -(rows [cy-2,cy+2] x cols [0,cx-2)) + wrapped column-0 taps (when cx == W-1)
 //   corner           : +(rows [0,cy-2) x cols [0,cx-2)) - column-0 prefix
 // The first two come from the strip tables k_fast accumulates (+ at most 15 pixels), one lane per box.
-__device__ __forceinline__ int box_edge_lane(const EdgeSrc& E, int cx, int cy) {
+__device__ __noinline__ int box_edge_lane(const EdgeSrc& E, int cx, int cy) {
   const int W = E.W, H = E.H, p = E.pitch;
   if (cx <= W - 3) {
     int s = E.ey[cx];
@@ -791,7 +799,7 @@ __device__ __forceinline__ void patch_moments(const uint8_t* __restrict__ img, i
     const uint8_t* p = img + (size_t)(y - pr) * pitch + x + c;
     int colsum = 0;
     if (PR > 0) {
-#pragma unroll
+#pragma unroll (ORIENT_UNROLL)
       for (int r = -PR; r <= PR; r++) {
         const int I = p[(size_t)(r + PR) * pitch];
         colsum += I;
@@ -832,7 +840,7 @@ __device__ __forceinline__ void brief_of(const uint8_t* __restrict__ img, int pi
   const bool interior = kx - 19 >= 2 && kx + 19 <= W - 3 && ky - 19 >= 2 && ky + 19 <= H - 3;
   if (interior) {
     const uint16_t* bc = box + (size_t)ky * bpitch + kx;
-#pragma unroll
+#pragma unroll (BRIEF_UNROLL)
     for (int wd = 0; wd < 8; wd++) {
       const float4 t = __ldg(pattern + wd * 32 + lane);
       const int dx1 = orbm::lround_f(orbm::fsub(orbm::fmul(c, t.x), orbm::fmul(s, t.y)));   // :228-232
