@@ -168,8 +168,7 @@ constexpr int A_RP = 136;                          // shared pitch of resized ro
 __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bufs B) {
   __shared__ uint32_t s_xs[A_RW];    // column taps: s0 | s1 << 16
   __shared__ uint32_t s_xa[A_RW];    //              a0 | a1 << 16
-  __shared__ uint2 s_yo[A_RH];       // row taps: byte offsets of the two source rows inside the frame
-  __shared__ uint32_t s_yb[A_RH];    //           b0 | b1 << 16
+  __shared__ __align__(16) uint4 s_yt[A_RH];   // row taps: byte offsets of the two source rows inside the frame, b0, b1
   __shared__ __align__(16) uint8_t s_res[A_RH * A_RP];
   __shared__ __align__(16) uint16_t s_h[A_RH * A_TW];
   const int tid = threadIdx.x, f = blockIdx.y;
@@ -191,8 +190,7 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
       s_xa[i] = (uint32_t)(uint16_t)tx.a0 | ((uint32_t)(uint16_t)tx.a1 << 16);
     } else {
       const OrbTap ty = B.ytab[G.ytab_ofs + reflect101(y0 - halo + i - rw, h)];
-      s_yo[i - rw] = make_uint2(ty.s0 * sp, ty.s1 * sp);
-      s_yb[i - rw] = (uint32_t)(uint16_t)ty.a0 | ((uint32_t)(uint16_t)ty.a1 << 16);
+      s_yt[i - rw] = make_uint4(ty.s0 * sp, ty.s1 * sp, (uint32_t)ty.a0, (uint32_t)ty.a1);
     }
   }
   __syncthreads();
@@ -206,16 +204,16 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
     // the second horizontal tap is the next byte (s1 == s0 + 1) except at the clamped right border, where a1 == 0
     // and the byte after the row is only read, never used (the host guarantees it is addressable)
     const uint8_t* p0 = src + (xs & 0xffff);
+    asm volatile("" : "+l"(p0));      // keep the column base in a register pair: two adds per row address, not three
     r1 = min(r1, h + halo - (y0 - halo));
 #pragma unroll 3
     for (int ry = r0; ry < r1; ry++) {
-      const uint2 ro = s_yo[ry];
-      const uint32_t yb = s_yb[ry];
-      const uint8_t* q0 = p0 + ro.x;
-      const uint8_t* q1 = p0 + ro.y;
+      const uint4 ty = s_yt[ry];
+      const uint8_t* q0 = p0 + ty.x;
+      const uint8_t* q1 = p0 + ty.y;
       const int h0 = __ldg(q0) * a0 + __ldg(q0 + 1) * a1;
       const int h1 = __ldg(q1) * a0 + __ldg(q1 + 1) * a1;
-      const int v = ((((int)(yb & 0xffff) * (h0 >> 4)) >> 16) + (((int)(yb >> 16) * (h1 >> 4)) >> 16) + 2) >> 2;
+      const int v = ((((int)ty.z * (h0 >> 4)) >> 16) + (((int)ty.w * (h1 >> 4)) >> 16) + 2) >> 2;
       s_res[ry * A_RP + col] = (uint8_t)min(v, 255);
     }
   };
