@@ -290,7 +290,7 @@ constexpr int B_LIST = 4096;           // pretest passers kept in the list; dens
 constexpr int B_SURV = 1024;
 constexpr int B_PIX_BYTES = B_PH * B_SP, B_SCORE_BYTES = B_SH * B_SCP * 2;
 constexpr int B_LIST_BYTES = B_LIST * 2;
-constexpr int B_SMEM = B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES + B_SURV * 2 + 16;   // 39.6 KB -> 5 CTAs / SM
+constexpr int B_SMEM = B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES + B_SURV * 2 + 16 + B_TW * 4;   // 40.1 KB -> 5 CTAs / SM
 
 __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs B) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
   uint16_t* s_list = (uint16_t*)(smem + B_PIX_BYTES + B_SCORE_BYTES);
   uint16_t* s_surv = (uint16_t*)(smem + B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES);
   int* s_ctr = (int*)(s_surv + B_SURV);   // [0] pretest list, [1] survivor list, [2] global base
+  int* s_ey = s_ctr + 4;                  // [B_TW] column-strip sums of this tile (phase 5/6)
 
   const int tid = threadIdx.x, lane = tid & 31, f = blockIdx.y;
   const uint32_t tt = __ldg(B.tile_b + blockIdx.x);
@@ -314,6 +315,7 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
   // ---- phase 0/1: clear the score map, stage the tile (16-byte loads; rows reflect-101) -------
   for (int i = tid; i < B_SCORE_BYTES / 16; i += B_THREADS) ((uint4*)s_score)[i] = make_uint4(0, 0, 0, 0);
   if (tid < 3) s_ctr[tid] = 0;
+  if (tid < B_TW) s_ey[tid] = 0;
   for (int it = tid; it < B_PH * (B_SP / 16); it += B_THREADS) {
     const int py = it / (B_SP / 16), c = it - py * (B_SP / 16);
     const int xs = x0 - 16 + 16 * c;
@@ -323,14 +325,6 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
     uint4 v = make_uint4(0, 0, 0, 0);
     if (xs >= 0 && xs < pitch) v = __ldg((const uint4*)(img + (size_t)y * pitch + xs));
     *(uint4*)(s_pix + py * B_SP + 16 * c) = v;
-  }
-  __syncthreads();
-  // columns -1 and w of the reflect-101 extension (Sobel taps of the Harris window reach them)
-  if (tid < B_PH) {
-    uint8_t* r = s_pix + tid * B_SP;
-    if (x0 == 0) r[15] = r[17];
-    const int cw = w - x0 + 16;
-    if (cw < B_SP && cw >= 2) r[cw] = r[cw - 2];
   }
   __syncthreads();
 
@@ -475,7 +469,6 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
     const int base = s_ctr[2];
     for (int j = tid; j < nsurv; j += B_THREADS) emit(s_surv[j], base + j);
   }
-  __syncthreads();
 
   // ---- phase 5/6: 5x5 box sums (replace the int32 integral image of ref src/orb_cpu.cpp:207-208) and the strip
   // sums for BRIEF boxes that leave the image on the right / bottom (decision D7):
@@ -485,9 +478,6 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
   // Threads 0..127 own an 8-pixel column group and 8 output rows each: horizontal 5-sums of 12 input rows stay in
   // registers (16-bit lanes (o0,o2)(o1,o3)(o4,o6)(o5,o7)), five consecutive ones add up to a box row.  Threads
   // 192..255 produce the row sums meanwhile.
-  int* s_ey = (int*)s_list;                       // [B_TW] column-strip sums of this tile (the list is dead by now)
-  if (tid < B_TW) s_ey[tid] = 0;
-  __syncthreads();
   int* ey = B.edge + (size_t)f * P.edge_frame_elems + G.edge_ofs;
   int* rs = ey + G.edge_w;
   if (tid < B_TW) {
