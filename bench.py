@@ -154,7 +154,18 @@ def main():
     ap.add_argument("--frames", type=int, default=1000, help="frames per GPU per step")
     ap.add_argument("--chunk", type=int, default=0, help="frames per kernel wave (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--shape", default=None, help="WxH of the synthetic frames (default 1241x376 = the headline workload)")
+    ap.add_argument("--levels", type=int, default=None)
+    ap.add_argument("--nfeatures", type=int, default=None)
     args = ap.parse_args()
+    global W, H, LEVELS, NFEAT, PITCH, SUM_P, P0
+    if args.shape:
+        W, H = (int(v) for v in args.shape.lower().split("x"))
+    LEVELS = args.levels or LEVELS
+    NFEAT = args.nfeatures or NFEAT
+    PITCH = (W + 15) // 16 * 16 + (16 if W % 16 == 0 else 0)      # 16-byte rows, one spare byte after the last pixel
+    SUM_P = sum(w * h for w, h in level_sizes())
+    P0 = W * H
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))

@@ -135,6 +135,21 @@ int  orb_orientations(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pit
 int  orb_brief(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch,
                const orb_keypoint* kps, const float* angles, int n, orb_descriptor* desc);
 
+/* ---- descriptor matching (the step right after the descriptors) ----------
+ * replaces: flann->knnMatch(des1, des2, matches, 2) of the VO loops (reference src/feature_matching.cpp:168,
+ * src/feature_tracking.cpp:205) by an exact brute-force Hamming 2-nearest-neighbour search on the device (the reference's
+ * FLANN-LSH index is approximate and randomised; ties here go to the lower train index).  Descriptors stay on the device
+ * when they were produced with outputs_on_device = 1. */
+typedef struct { int32_t idx1, dist1, idx2, dist2; } orb_match;   /* absent neighbour: idx -1, dist INT32_MAX */
+int  orb_match_knn2(orb_ctx* ctx, const orb_descriptor* query, int nq, const orb_descriptor* train, int nt,
+                    int on_device, orb_match* out /* [nq], same memory space as the inputs */);
+/* all consecutive frame pairs of a batch: pair p = frame p (query, n[p] descriptors) against frame p+1 (train);
+ * desc is [n_frames][cap], out is [n_frames-1][cap] (entries >= n[p] untouched) */
+int  orb_match_knn2_batch(orb_ctx* ctx, const orb_descriptor* desc, const int* n, int n_frames, int cap, int on_device,
+                          orb_match* out);
+/* the reference's ratio test, src/feature_matching.cpp:174-182: keep[i] = has two neighbours && dist1 < ratio * dist2 */
+void orb_ratio_test(const orb_match* m, int n, float ratio, uint8_t* keep);
+
 /* ---- side arrays of the LAST orb_detect_and_compute[_batch] call (testing / diagnostics) ----
  * level-space coordinates, level id and Harris response of output record i of `frame`
  * (the reference drops them, src/orb.cpp:94-102).  Any pointer may be NULL. */

@@ -388,6 +388,22 @@ int orc_detect_and_compute(const uint8_t* img, int W, int H, size_t pitch, const
   return total;
 }
 
+void orc_match_knn2(const orc_descriptor* query, int nq, const orc_descriptor* train, int nt, int32_t* out4, float ratio,
+                    uint8_t* keep) {
+  for (int i = 0; i < nq; i++) {
+    int d1 = 0x7fffffff, d2 = 0x7fffffff, i1 = -1, i2 = -1;
+    for (int j = 0; j < nt; j++) {
+      int d = 0;
+      for (int k = 0; k < 32; k++) d += __builtin_popcount((unsigned)(query[i].data[k] ^ train[j].data[k]));   // as src/compare.cpp:95-97
+      if (d < d1) { d2 = d1; i2 = i1; d1 = d; i1 = j; }
+      else if (d < d2) { d2 = d; i2 = j; }
+    }
+    out4[4 * i] = i1; out4[4 * i + 1] = d1; out4[4 * i + 2] = i2; out4[4 * i + 3] = d2;
+    // if (m.distance < 0.8 * n.distance): float distances, double product (src/feature_matching.cpp:178)
+    if (keep) keep[i] = i2 >= 0 && (double)(float)d1 < (double)ratio * (double)(float)d2;
+  }
+}
+
 int orc_detect_and_compute_batch(const uint8_t* frames, int n_frames, size_t frame_stride, int W, int H, size_t pitch,
                                  const orc_params* p, int cap, orc_keypoint* kps, float* angles, orc_descriptor* desc,
                                  int* n_out, int n_threads) {

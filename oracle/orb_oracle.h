@@ -75,6 +75,12 @@ int  orc_detect_and_compute_batch(const uint8_t* frames, int n_frames, size_t fr
                                   const orc_params* p, int cap, orc_keypoint* kps, float* angles, orc_descriptor* desc,
                                   int* n_out, int n_threads);
 
+/* exact brute-force Hamming 2-NN (the deterministic counterpart of flann->knnMatch(des1, des2, matches, 2),
+ * reference src/feature_matching.cpp:168): out[i] = {idx1, dist1, idx2, dist2}, ties to the lower train index,
+ * absent neighbour = {-1, INT32_MAX}; keep[i] = ratio test of src/feature_matching.cpp:178 (may be NULL) */
+void orc_match_knn2(const orc_descriptor* query, int nq, const orc_descriptor* train, int nt, int32_t* out4, float ratio,
+                    uint8_t* keep);
+
 /* helpers for property tests */
 long orc_lround_f(float v);                       /* std::lround(float)                   */
 float orc_atan2f(float y, float x);

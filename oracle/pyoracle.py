@@ -86,6 +86,7 @@ def lib():
         L.orc_orientations.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orc_brief.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.orc_brief_flags.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_match_knn2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p]
         _lib = L
     return _lib
 
@@ -230,6 +231,16 @@ def brief_flags(w, h, kps, angles):
     out = np.zeros(len(kps), np.uint8)
     lib().orc_brief_flags(w, h, _ptr(kps), _ptr(angles), len(kps), _ptr(out))
     return out
+
+
+def match_knn2(query, train, ratio=0.8):
+    """Exact Hamming 2-NN per query: (int32[nq,4] = idx1, dist1, idx2, dist2; bool[nq] ratio test)."""
+    q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+    t = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+    out = np.zeros((len(q), 4), np.int32)
+    keep = np.zeros(len(q), np.uint8)
+    lib().orc_match_knn2(_ptr(q), len(q), _ptr(t), len(t), _ptr(out), ratio, _ptr(keep))
+    return out, keep.astype(bool)
 
 
 # ---------------------------------------------------------------- whole path

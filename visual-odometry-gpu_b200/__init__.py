@@ -6,11 +6,11 @@ The directory name carries a hyphen (it is the reference's name); import it with
 repository root.  The product is csrc/ (CUDA kernels + C ABI, built to liborb_b200.so) and the thin host
 mirror in orb.py; the CPU parity checker is never imported from here.
 """
-from .orb import (KP, ORB, ORBCPU, Context, OrbError, OrientedFAST, Params, RotatedBRIEF, SELECT_HARRIS_TOP_N,
+from .orb import (KP, MATCH, ORB, ORBCPU, Context, OrbError, OrientedFAST, Params, RotatedBRIEF, SELECT_HARRIS_TOP_N,
                   SELECT_RASTER_FIRST_N, EXPORTS, default_params, lib_path, load_library, make_params)
 from .sharding import shard_range
 from .synth import synth_frames
 
-__all__ = ["KP", "ORB", "ORBCPU", "Context", "OrbError", "OrientedFAST", "Params", "RotatedBRIEF",
+__all__ = ["KP", "MATCH", "ORB", "ORBCPU", "Context", "OrbError", "OrientedFAST", "Params", "RotatedBRIEF",
            "SELECT_HARRIS_TOP_N", "SELECT_RASTER_FIRST_N", "EXPORTS", "default_params", "lib_path", "load_library",
            "make_params", "shard_range", "synth_frames"]

@@ -794,6 +794,70 @@ int orb_brief(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch, cons
   return describe_list(ctx, img, w, h, pitch, kps, angles, n, nullptr, desc);
 }
 
+// ---- descriptor matching -------------------------------------------------------------------------
+static int match_launch(orb_ctx* ctx, const orb_descriptor* dq, const orb_descriptor* dt, const int* dn, int nq, int nt, int npairs,
+                        long long sq, long long st, long long so, orb_match* dout) {
+  if (npairs <= 0 || nq <= 0) return ORB_OK;
+  dim3 grid((nq + orbk::M_THREADS - 1) / orbk::M_THREADS, npairs);
+  orbk::k_match<<<grid, orbk::M_THREADS, 0, ctx->stream>>>(dq, dt, dn, nq, nt, sq, st, so, dout);
+  CK(cudaGetLastError());
+  ctx->launches += 1;
+  return ORB_OK;
+}
+
+int orb_match_knn2(orb_ctx* ctx, const orb_descriptor* query, int nq, const orb_descriptor* train, int nt, int on_device,
+                   orb_match* out) {
+  if (!ctx) return ORB_E_INVALID;
+  if (nq < 0 || nt < 0 || (nq > 0 && (!query || !out)) || (nt > 0 && !train)) return fail(ctx, ORB_E_INVALID, "bad match arguments");
+  if (nq == 0) return ORB_OK;
+  CK(cudaSetDevice(ctx->p.device));
+  if (on_device) return match_launch(ctx, query, train, nullptr, nq, nt, 1, 0, 0, 0, out);
+  orb_descriptor *dq = nullptr, *dt = nullptr; orb_match* dm = nullptr;
+  CK(cudaMalloc(&dq, sizeof(orb_descriptor) * (size_t)nq));
+  CK(cudaMalloc(&dt, sizeof(orb_descriptor) * (size_t)std::max(nt, 1)));
+  CK(cudaMalloc(&dm, sizeof(orb_match) * (size_t)nq));
+  CK(cudaMemcpyAsync(dq, query, sizeof(orb_descriptor) * (size_t)nq, cudaMemcpyHostToDevice, ctx->stream));
+  if (nt) CK(cudaMemcpyAsync(dt, train, sizeof(orb_descriptor) * (size_t)nt, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = match_launch(ctx, dq, dt, nullptr, nq, nt, 1, 0, 0, 0, dm);
+  if (!rc) {
+    CK(cudaMemcpyAsync(out, dm, sizeof(orb_match) * (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  cudaFree(dq); cudaFree(dt); cudaFree(dm);
+  return rc;
+}
+
+int orb_match_knn2_batch(orb_ctx* ctx, const orb_descriptor* desc, const int* n, int n_frames, int cap, int on_device,
+                         orb_match* out) {
+  if (!ctx) return ORB_E_INVALID;
+  if (!desc || !n || !out || n_frames < 1 || cap < 1) return fail(ctx, ORB_E_INVALID, "bad match arguments");
+  if (n_frames < 2) return ORB_OK;
+  CK(cudaSetDevice(ctx->p.device));
+  const long long s = cap;
+  if (on_device) return match_launch(ctx, desc, desc + cap, n, cap, cap, n_frames - 1, s, s, s, out);
+  orb_descriptor* dd = nullptr; int* dn = nullptr; orb_match* dm = nullptr;
+  const size_t nd = (size_t)n_frames * cap, nm = (size_t)(n_frames - 1) * cap;
+  CK(cudaMalloc(&dd, sizeof(orb_descriptor) * nd));
+  CK(cudaMalloc(&dn, sizeof(int) * n_frames));
+  CK(cudaMalloc(&dm, sizeof(orb_match) * nm));
+  CK(cudaMemcpyAsync(dd, desc, sizeof(orb_descriptor) * nd, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(dn, n, sizeof(int) * n_frames, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(dm, out, sizeof(orb_match) * nm, cudaMemcpyHostToDevice, ctx->stream));   // entries >= n[p] stay as they were
+  int rc = match_launch(ctx, dd, dd + cap, dn, cap, cap, n_frames - 1, s, s, s, dm);
+  if (!rc) {
+    CK(cudaMemcpyAsync(out, dm, sizeof(orb_match) * nm, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  cudaFree(dd); cudaFree(dn); cudaFree(dm);
+  return rc;
+}
+
+void orb_ratio_test(const orb_match* m, int n, float ratio, uint8_t* keep) {
+  // if (m.distance < 0.8 * n.distance), reference src/feature_matching.cpp:178 (float distances, double product)
+  for (int i = 0; i < n; i++)
+    keep[i] = m[i].idx2 >= 0 && (double)(float)m[i].dist1 < (double)ratio * (double)(float)m[i].dist2;
+}
+
 int orb_debug_eval_math(orb_ctx* ctx, int op, const float* a, const float* b, int n, float* out) {
   if (!ctx || !a || !out || n < 0 || op < 0 || op > 3 || (op == 0 && !b)) return ORB_E_INVALID;
   CK(cudaSetDevice(ctx->p.device));

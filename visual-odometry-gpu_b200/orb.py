@@ -20,6 +20,7 @@ import numpy as np
 from . import build as _build
 
 KP = np.dtype([("x", "<i4"), ("y", "<i4")])
+MATCH = np.dtype([("idx1", "<i4"), ("dist1", "<i4"), ("idx2", "<i4"), ("dist2", "<i4")])   # == orb_match
 
 SELECT_RASTER_FIRST_N = 0
 SELECT_HARRIS_TOP_N = 1
@@ -44,7 +45,7 @@ EXPORTS = [
     "orb_abi_version", "orb_default_params", "orb_create", "orb_destroy", "orb_last_error", "orb_set_stream", "orb_use_own_stream",
     "orb_synchronize", "orb_detect_and_compute", "orb_detect_and_compute_batch", "orb_get_level", "orb_level_size",
     "orb_level_quota", "orb_fast_detect", "orb_harris", "orb_orientations", "orb_brief", "orb_get_side_arrays",
-    "orb_get_candidates", "orb_get_harris_weights", "orb_last_launch_count", "orb_set_profiling", "orb_get_stage_ms", "orb_debug_eval_math", "bit_pattern_31_",
+    "orb_get_candidates", "orb_get_harris_weights", "orb_last_launch_count", "orb_set_profiling", "orb_get_stage_ms", "orb_match_knn2", "orb_match_knn2_batch", "orb_ratio_test", "orb_debug_eval_math", "bit_pattern_31_",
 ]
 
 _lib = None
@@ -87,6 +88,10 @@ def load_library():
     L.orb_get_harris_weights.argtypes = [vp, vp]
     L.orb_last_launch_count.argtypes = [vp]
     L.orb_debug_eval_math.argtypes = [vp, i, vp, vp, i, vp]
+    L.orb_match_knn2.argtypes = [vp, vp, i, vp, i, i, vp]
+    L.orb_match_knn2_batch.argtypes = [vp, vp, vp, i, i, i, vp]
+    L.orb_ratio_test.argtypes = [vp, i, C.c_float, vp]
+    L.orb_ratio_test.restype = None
     L.orb_set_profiling.argtypes = [vp, i]
     L.orb_get_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 5), C.POINTER(C.c_int * 5)]
     _lib = L
@@ -265,6 +270,34 @@ class Context:
         self._ck(self.lib.orb_brief(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), _p(angles),
                                     len(kps), _p(out)))
         return out
+
+    # ---- descriptor matching (replaces flann->knnMatch(des1, des2, matches, 2) + ratio test of the reference VO loops)
+    def match_knn2(self, query, train):
+        q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+        out = np.zeros(len(q), MATCH)
+        self._ck(self.lib.orb_match_knn2(self.h, _p(q), len(q), _p(t), len(t), 0, _p(out)))
+        return out
+
+    def match_knn2_batch(self, desc, n):
+        desc = np.ascontiguousarray(desc, np.uint8)
+        F, cap = desc.shape[0], desc.shape[1]
+        n = np.ascontiguousarray(n, np.int32)
+        out = np.zeros((max(F - 1, 0), cap), MATCH)
+        out["idx1"] = out["idx2"] = -1
+        self._ck(self.lib.orb_match_knn2_batch(self.h, _p(desc), _p(n), F, cap, 0, _p(out)))
+        return out
+
+    def match_knn2_batch_ptr(self, desc_ptr, n_ptr, n_frames, cap, out_ptr):
+        """device-resident form: descriptors / counts as produced by detect_and_compute_batch_ptr(..., outputs_on_device=1)"""
+        self._ck(self.lib.orb_match_knn2_batch(self.h, C.c_void_p(desc_ptr), C.c_void_p(n_ptr), n_frames, cap, 1,
+                                               C.c_void_p(out_ptr)))
+
+    def ratio_test(self, matches, ratio=0.8):
+        m = np.ascontiguousarray(matches, MATCH).ravel()
+        keep = np.zeros(len(m), np.uint8)
+        self.lib.orb_ratio_test(_p(m), len(m), ratio, _p(keep))
+        return keep.astype(bool).reshape(np.shape(matches))
 
     def eval_math(self, op, a, b=None):
         a = np.ascontiguousarray(a, np.float32)
