@@ -163,7 +163,7 @@ def main():
         W, H = (int(v) for v in args.shape.lower().split("x"))
     LEVELS = args.levels or LEVELS
     NFEAT = args.nfeatures or NFEAT
-    PITCH = (W + 15) // 16 * 16 + (16 if W % 16 == 0 else 0)      # 16-byte rows, one spare byte after the last pixel
+    PITCH = (W + 1 + 15) // 16 * 16                                # 16-byte rows, one spare byte after the last pixel
     SUM_P = sum(w * h for w, h in level_sizes())
     P0 = W * H
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -263,6 +263,15 @@ def main():
     st_ms, st_n = ctx.stage_ms()
     ctx.set_profiling(False)
 
+    # SURVEY 8(f) rank 2 (not part of the headline metric): exact Hamming 2-NN between consecutive frames of the batch,
+    # descriptors still resident on the device
+    d_m = torch.zeros(F - 1, cap, 4, dtype=torch.int32, device=dev) if F > 1 else None
+    ms_match = None
+    if d_m is not None:
+        def step_match():
+            ctx.match_knn2_batch_ptr(d_d.data_ptr(), d_n.data_ptr(), F, cap, d_m.data_ptr())
+        ms_match = timed(step_match, 2, 1) / 2
+
     ms_e2e = timed(step_e2e, max(1, args.steps // 2), 2)
     e2e_steps = max(1, args.steps // 2)
     sampler.stop()
@@ -306,6 +315,7 @@ def main():
                    "cache_hygiene": "input batch %.0f MB > 126 MB L2; scratch arena reused per chunk" % (F * H * PITCH / 1e6),
                    "stage_names": names,
                    "stage_ms_per_step": [m / prof_steps for m in st_ms], "stage_share": stage_share,
+                   "match_knn2_ms_per_step": ms_match, "match_pairs_per_step": F - 1,
                    "pass_b_min_bytes_per_frame": b_min, "pass_hbm_gbs_per_gpu": pass_gbs, "pass_hbm_frac": pass_gbs / peak,
                    "peak_source": peak_src},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(F * H * PITCH) * world,

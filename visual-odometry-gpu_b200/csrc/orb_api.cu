@@ -416,7 +416,8 @@ int orb_create(const orb_params* p, orb_ctx** out) {
     int chunk = p->chunk_frames > 0 ? p->chunk_frames : (int)std::max<size_t>(1, std::min<size_t>(128, ((size_t)1 << 30) / per_frame));
     ctx->chunk = std::max(1, std::min(chunk, p->max_batch));
     const int C = ctx->chunk, Bn = p->max_batch;
-    ctx->frames_pitch = align_up(p->max_width, 16);
+    // staged rows are 16-byte multiples with at least one spare byte after the last pixel (k_pyramid's second tap)
+    ctx->frames_pitch = align_up(p->max_width + 1, 16);
     ctx->frames_slot_bytes = (size_t)ctx->frames_pitch * p->max_height;
     CK(cudaMalloc(&ctx->d_frames, ctx->frames_slot_bytes * Bn + 16));   // k_pyramid may read one byte past the last row
     CK(cudaMalloc(&ctx->d_pyr, (size_t)M.pyr_frame_bytes * C));
