@@ -573,7 +573,19 @@ int orb_detect_and_compute_batch(orb_ctx* ctx, const uint8_t* frames, int frames
   int total_quota = 0;
   for (int l = 0; l < P.nlevels; l++) total_quota += P.lv[l].quota;
   const int nwarps = std::min(total_quota, cap);
-  const int nchunks = (n_frames + ctx->chunk - 1) / ctx->chunk;
+  // wave boundaries: full waves of `chunk` frames; when frames are staged from the host the first waves are short
+  // (chunk/8, chunk/4, chunk/2) so that the kernels start while most of the batch is still in flight over PCIe
+  std::vector<int> wave_begin;
+  {
+    int c0 = 0, ramp = (!direct && n_frames > 2 * ctx->chunk) ? std::max(1, ctx->chunk / 8) : ctx->chunk;
+    while (c0 < n_frames) {
+      wave_begin.push_back(c0);
+      c0 += std::min(ramp, ctx->chunk);
+      if (ramp < ctx->chunk) ramp *= 2;
+    }
+    wave_begin.push_back(n_frames);
+  }
+  const int nchunks = (int)wave_begin.size() - 1;
   const bool piped = !direct || !outputs_on_device;
   if (piped) {
     while ((int)ctx->ev_in.size() < nchunks) {
@@ -590,7 +602,7 @@ int orb_detect_and_compute_batch(orb_ctx* ctx, const uint8_t* frames, int frames
   if (!direct) {
     const cudaMemcpyKind kind = frames_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     for (int ci = 0; ci < nchunks; ci++) {
-      const int c0 = ci * ctx->chunk, nc = std::min(ctx->chunk, n_frames - c0);
+      const int c0 = wave_begin[ci], nc = wave_begin[ci + 1] - c0;
       uint8_t* dst = ctx->d_frames + (size_t)c0 * ctx->frames_slot_bytes;
       const uint8_t* from = frames + (size_t)c0 * frame_stride;
       if (pitch == (size_t)ctx->frames_pitch && frame_stride == ctx->frames_slot_bytes) {
@@ -607,7 +619,7 @@ int orb_detect_and_compute_batch(orb_ctx* ctx, const uint8_t* frames, int frames
   }
 
   for (int ci = 0; ci < nchunks; ci++) {
-    const int c0 = ci * ctx->chunk, nc = std::min(ctx->chunk, n_frames - c0);
+    const int c0 = wave_begin[ci], nc = wave_begin[ci + 1] - c0;
     if (!direct) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[ci], 0));
     Bufs B;
     fill_bufs(ctx, &B);
