@@ -58,3 +58,43 @@ def test_facade_matches_oracle(tmp_path, V, O, kitti0):
     assert np.array_equal(k, kr)
     ar = O.orientations(kitti0, kr, 31)
     assert np.array_equal(a.view(np.uint32), ar.view(np.uint32)) and np.array_equal(d, O.brief(kitti0, kr, ar))
+
+
+def _build_feature2d(tmp_path, V):
+    exe = str(tmp_path / "feature2d_test")
+    libdir = os.path.dirname(V.lib_path())
+    cmd = ["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "tests", "cpp", "mock_opencv"), "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "cpp", "feature2d_test.cpp"), "-o", exe, "-L" + libdir, "-lorb_b200", "-Wl,-rpath," + libdir]
+    env = {k: v for k, v in os.environ.items() if k not in ("CXX", "CC")}
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    assert r.returncode == 0, r.stdout
+    return exe
+
+
+def test_feature2d_adapter_compiles_against_mock_opencv(tmp_path, V):
+    """SURVEY 8(f) rank 1: the cv::Feature2D adapter (include/orb_feature2d.hpp) against the mock OpenCV headers."""
+    V.load_library()
+    _build_feature2d(tmp_path, V)
+
+
+@pytest.mark.gpu
+def test_feature2d_adapter_matches_oracle(tmp_path, V, O, kitti0):
+    V.load_library()
+    exe = _build_feature2d(tmp_path, V)
+    raw = tmp_path / "k0.raw"
+    kitti0.tofile(raw)
+    out = str(tmp_path / "f2d")
+    r = subprocess.run([exe, str(raw), "1241", "376", out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "FEATURE2D_OK" in r.stdout, r.stdout
+    kp = np.fromfile(out + ".kp", dtype=np.float32).reshape(-1, 6)
+    desc = np.fromfile(out + ".desc", dtype=np.uint8).reshape(-1, 32)
+    ref = O.detect_and_compute(kitti0, O.params(nfeatures=3000), cap=3000)          # ORB::create(3000): 1.2 / 8 / thr 20 / patch 31
+    assert len(kp) == ref["n"] and np.array_equal(desc, ref["desc"])
+    assert np.array_equal(kp[:, 0], ref["kps"]["x"].astype(np.float32)) and np.array_equal(kp[:, 1], ref["kps"]["y"].astype(np.float32))
+    assert np.array_equal(kp[:, 5].astype(np.int32), ref["level_id"])
+    assert np.array_equal(kp[:, 4].view(np.uint32), ref["response"].view(np.uint32))
+    deg = ref["angles"] * np.float32(180.0 / np.pi)
+    deg = np.where(deg < 0, deg + np.float32(360), deg)
+    assert np.allclose(kp[:, 3], deg, atol=1e-4) and (kp[:, 3] >= 0).all() and (kp[:, 3] < 360).all()
+    size = np.float32(31) * np.float32(1.2) ** ref["level_id"].astype(np.float32)
+    assert np.allclose(kp[:, 2], size, rtol=1e-6)
