@@ -35,7 +35,7 @@ struct orb_ctx {
   orb_params p;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   char err[512];
-  int chunk = 1, max_kp = 0;
+  int chunk = 1, chunk_staged = 1, max_kp = 0;   // frames per wave: arena capacity / wave size when host copies are involved
   // plan of the last shape + arena limits (plan of the max shape)
   OrbPlan plan, max_plan;
   bool plan_valid = false;
@@ -43,7 +43,7 @@ struct orb_ctx {
   // arena
   uint8_t* d_frames = nullptr; size_t frames_slot_bytes = 0; int frames_pitch = 0;
   uint8_t* d_pyr = nullptr; uint16_t* d_box = nullptr; unsigned long long* d_cand = nullptr;
-  int* d_cand_count = nullptr; int* d_edge = nullptr; size_t zero_bytes_per_frame = 0; uint32_t* d_kept_xy = nullptr; float* d_kept_r = nullptr; int* d_kept_count = nullptr;
+  int* d_cand_count = nullptr; size_t zero_bytes_per_frame = 0; uint32_t* d_kept_xy = nullptr; float* d_kept_r = nullptr; int* d_kept_count = nullptr;
   OrbTap *d_xtab = nullptr, *d_ytab = nullptr;
   uint32_t *d_tile_a = nullptr, *d_tile_b = nullptr, *d_tile_b1 = nullptr; int tile_a_cap = 0, tile_b_cap = 0;
   float* d_harris_w = nullptr; float4* d_pattern = nullptr; int* d_flags = nullptr; int* h_flags = nullptr;
@@ -215,7 +215,7 @@ int get_plan(orb_ctx* ctx, int w, int h) {
 void fill_bufs(orb_ctx* ctx, Bufs* B) {
   memset(B, 0, sizeof(*B));
   B->pyr = ctx->d_pyr; B->box = ctx->d_box; B->cand = ctx->d_cand; B->cand_count = ctx->d_cand_count;
-  B->edge = ctx->d_edge; B->kept_xy = ctx->d_kept_xy; B->kept_r = ctx->d_kept_r; B->kept_count = ctx->d_kept_count;
+  B->zero_stride = (int)(ctx->zero_bytes_per_frame / sizeof(int)); B->kept_xy = ctx->d_kept_xy; B->kept_r = ctx->d_kept_r; B->kept_count = ctx->d_kept_count;
   B->xtab = ctx->d_xtab; B->ytab = ctx->d_ytab; B->tile_a = ctx->d_tile_a; B->tile_b = ctx->d_tile_b; B->harris_w = ctx->d_harris_w; B->pattern = ctx->d_pattern;
   B->flags = ctx->d_flags;
 }
@@ -238,8 +238,8 @@ struct StageTimer {
 };
 
 int launch_pyramid_fast(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, int nframes) {
-  // candidate counters and level totals of the whole chunk arena (one small memset)
-  CK(cudaMemsetAsync(ctx->d_cand_count, 0, ctx->zero_bytes_per_frame * ctx->chunk, ctx->stream));
+  // candidate counters and BRIEF border tables of the wave's frames (one small memset)
+  CK(cudaMemsetAsync(ctx->d_cand_count, 0, ctx->zero_bytes_per_frame * nframes, ctx->stream));
   if (P.a_tiles_per_frame > 0) {
     StageTimer t(ctx, 0);
     orbk::k_pyramid<<<dim3(P.a_tiles_per_frame, nframes), orbk::A_THREADS, 0, ctx->stream>>>(P, B);
@@ -411,10 +411,13 @@ int orb_create(const orb_params* p, orb_ctx** out) {
     ctx->max_kp = p->max_keypoints > 0 ? p->max_keypoints : total_quota;
     // chunking: keep one chunk's scratch (levels + box sums) well inside the 126 MB L2
     size_t per_frame = (size_t)M.pyr_frame_bytes + (size_t)M.box_frame_elems * 2 + (size_t)p->max_width * p->max_height;
-    // measured on B200: larger waves win (launch gaps and kernel tails outweigh L2 residency of the scratch), so the
-    // default is 128 frames per wave, bounded by 1 GB of scratch
-    int chunk = p->chunk_frames > 0 ? p->chunk_frames : (int)std::max<size_t>(1, std::min<size_t>(128, ((size_t)1 << 30) / per_frame));
+    // measured on B200: larger waves win (launch gaps and kernel tails outweigh L2 residency of the scratch): 512 frames
+    // per wave when frames and results stay on the device, 128 when they are staged from / to the host so that the
+    // copies of one wave hide behind the kernels of another (bounded by 3 GB of scratch)
+    int chunk = p->chunk_frames > 0 ? p->chunk_frames : (int)std::max<size_t>(1, std::min<size_t>(512, ((size_t)3 << 30) / per_frame));
+    ctx->chunk_staged = p->chunk_frames > 0 ? p->chunk_frames : 128;
     ctx->chunk = std::max(1, std::min(chunk, p->max_batch));
+    ctx->chunk_staged = std::max(1, std::min(ctx->chunk_staged, ctx->chunk));
     const int C = ctx->chunk, Bn = p->max_batch;
     // staged rows are 16-byte multiples with at least one spare byte after the last pixel (k_pyramid's second tap)
     ctx->frames_pitch = align_up(p->max_width + 1, 16);
@@ -428,7 +431,6 @@ int orb_create(const orb_params* p, orb_ctx** out) {
       const int edge_max = std::max(M.edge_frame_elems, S.edge_frame_elems);
       ctx->zero_bytes_per_frame = sizeof(int) * ORB_MAX_LEVELS + sizeof(int) * (size_t)edge_max;
       CK(cudaMalloc(&ctx->d_cand_count, ctx->zero_bytes_per_frame * C));
-      ctx->d_edge = ctx->d_cand_count + (size_t)ORB_MAX_LEVELS * C;
     }
     CK(cudaMalloc(&ctx->d_kept_count, sizeof(int) * ORB_MAX_LEVELS * C));
     CK(cudaMalloc(&ctx->d_kept_xy, sizeof(uint32_t) * (size_t)kept_per_frame * C));
@@ -577,11 +579,12 @@ int orb_detect_and_compute_batch(orb_ctx* ctx, const uint8_t* frames, int frames
   // (chunk/8, chunk/4, chunk/2) so that the kernels start while most of the batch is still in flight over PCIe
   std::vector<int> wave_begin;
   {
-    int c0 = 0, ramp = (!direct && n_frames > 2 * ctx->chunk) ? std::max(1, ctx->chunk / 8) : ctx->chunk;
+    const int wave = (direct && outputs_on_device) ? ctx->chunk : ctx->chunk_staged;
+    int c0 = 0, ramp = (!direct && n_frames > wave) ? std::max(1, wave / 8) : wave;
     while (c0 < n_frames) {
       wave_begin.push_back(c0);
-      c0 += std::min(ramp, ctx->chunk);
-      if (ramp < ctx->chunk) ramp *= 2;
+      c0 += std::min(ramp, wave);
+      if (ramp < wave) ramp *= 2;
     }
     wave_begin.push_back(n_frames);
   }
@@ -712,7 +715,7 @@ int orb_get_candidates(orb_ctx* ctx, int frame, int level, int cap, orb_keypoint
   const int slot = frame - ctx->last_chunk_start;
   const OrbLevel& G = ctx->plan.lv[level];
   int n = 0;
-  CK(cudaMemcpy(&n, ctx->d_cand_count + slot * ORB_MAX_LEVELS + level, sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&n, ctx->d_cand_count + (size_t)slot * (ctx->zero_bytes_per_frame / sizeof(int)) + level, sizeof(int), cudaMemcpyDeviceToHost));
   *n_out = n;
   int m = std::min(std::min(n, cap), G.cand_cap);
   if (m > 0 && (xy || response)) {

@@ -31,8 +31,8 @@ struct Bufs {
   uint8_t* pyr;                  // [chunk][pyr_frame_bytes]
   uint16_t* box;                 // [chunk][box_frame_elems]
   unsigned long long* cand;      // [chunk][cand_frame_elems]
-  int* cand_count;               // [chunk][ORB_MAX_LEVELS]
-  int* edge;                     // [chunk][edge_frame_elems] strip sums for BRIEF boxes that leave the image
+  int* cand_count;               // per frame (stride zero_stride ints): [ORB_MAX_LEVELS] candidate counters, then the
+  int zero_stride;               //   BRIEF border tables of every level (zeroed together before each wave)
   uint32_t* kept_xy;             // [chunk][kept_per_frame]   (y << 16 | x), level space
   float* kept_r;                 // [chunk][kept_per_frame]
   int* kept_count;               // [chunk][ORB_MAX_LEVELS]
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
 
   // ---- phase 4: NMS over the corners of the tile interior ---------------------------------------
   unsigned long long* cand = B.cand + (size_t)f * P.cand_frame_elems + G.cand_ofs;
-  int* gcount = B.cand_count + f * ORB_MAX_LEVELS + l;
+  int* gcount = B.cand_count + (size_t)f * B.zero_stride + l;
   const int nmsr = P.nms_radius;
   auto emit = [&](int idx, int slot) {   // key = raster position; k_harris adds the response in the high word
     const int sy = idx / B_SP, pcx = idx - sy * B_SP;
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
   // Threads 0..127 own an 8-pixel column group and 8 output rows each: horizontal 5-sums of 12 input rows stay in
   // registers (16-bit lanes (o0,o2)(o1,o3)(o4,o6)(o5,o7)), five consecutive ones add up to a box row.  Threads
   // 192..255 produce the row sums meanwhile.
-  int* ey = B.edge + (size_t)f * P.edge_frame_elems + G.edge_ofs;
+  int* ey = B.cand_count + (size_t)f * B.zero_stride + ORB_MAX_LEVELS + G.edge_ofs;
   int* rs = ey + G.edge_w;
   if (tid < B_TW) {
     const uint32_t M = 0x00ff00ffu;
@@ -555,7 +555,7 @@ constexpr int C_THREADS = 128;
 
 __global__ void __launch_bounds__(C_THREADS, 8) k_harris(const OrbPlan P, const Bufs B) {
   const int f = blockIdx.y;
-  const int* cc = B.cand_count + f * ORB_MAX_LEVELS;
+  const int* cc = B.cand_count + (size_t)f * B.zero_stride;
   int total = 0;
   for (int q = 0; q < P.nlevels; q++) total += min(cc[q], P.lv[q].cand_cap);
   for (int i = blockIdx.x * C_THREADS + threadIdx.x; i < total; i += gridDim.x * C_THREADS) {
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(K2_THREADS) k_select(const OrbPlan P, const Bu
   __shared__ int s_k, s_n, s_done;
   const int tid = threadIdx.x, lane = tid & 31, l = blockIdx.x, f = blockIdx.y;
   const OrbLevel& G = P.lv[l];
-  int n = B.cand_count[f * ORB_MAX_LEVELS + l];
+  int n = B.cand_count[(size_t)f * B.zero_stride + l];
   if (n > G.cand_cap) {
     if (tid == 0) atomicOr(B.flags, 1);
     n = G.cand_cap;
@@ -934,7 +934,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32, ORB_K3_MINB) k_describe(const O
   if (J.mode != 2 && lane == 0) B.out_angles[o] = angle;
   if (J.mode != 1) {
     uint32_t word;
-    const int* ey = B.edge + (size_t)f * P.edge_frame_elems + G.edge_ofs;
+    const int* ey = B.cand_count + (size_t)f * B.zero_stride + ORB_MAX_LEVELS + G.edge_ofs;
     const EdgeSrc E{img, pitch, G.w, G.h, ey, ey + G.edge_w};
     brief_of(img, pitch, box, G.bpitch, E, x, y, angle, B.pattern, lane, &word);
     if (lane < 8) ((uint32_t*)B.out_desc)[o * 8 + lane] = word;
