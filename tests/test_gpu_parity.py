@@ -356,3 +356,30 @@ def test_batch_properties_at_bench_size(V, O):
     assert np.array_equal(bits(a[5, :n[5]]), bits(r["angles"]))
     c.close()
     c2.close()
+
+
+@pytest.mark.parametrize("f,L", [(1.5, 4), (2.0, 3), (1.1, 6)])
+def test_full_path_other_scale_factors(V, O, kitti0, f, L):
+    """Pyramid geometry, taps and quotas for scale factors other than 1.2 (the integer-2x resize path included)."""
+    img = kitti0[:300, :500]
+    c = V.Context(V.make_params(nfeatures=700, scaleFactor=f, nlevels=L, max_width=500, max_height=300, keep_side_arrays=1))
+    p = O.params(nfeatures=700, scale_factor=f, nlevels=L)
+    _compare_full(c, O, img, p, c.max_kp)
+    for l in range(L):
+        assert np.array_equal(c.get_level(0, l, 500, 300), O.build_level(img, p, l))
+    c.close()
+
+
+def test_shape_changes_on_one_context(V, O, kitti0):
+    """A context re-plans (level geometry, tap and tile tables) whenever the frame shape changes."""
+    c = V.Context(V.make_params(nfeatures=800, nlevels=6, max_width=1241, max_height=376, max_batch=3, keep_side_arrays=1))
+    p = O.params(nfeatures=800, nlevels=6)
+    for shape in ((376, 1241), (200, 640), (376, 1241), (123, 517)):
+        img = kitti0[:shape[0], :shape[1]]
+        _compare_full(c, O, img, p, c.max_kp)
+    frames = np.stack([kitti0[:200, :640], kitti0[100:300, 300:940], kitti0[50:250, 10:650]])
+    k, a, d, n = c.detect_and_compute_batch(frames)
+    for i in range(3):
+        r = O.detect_and_compute(frames[i], p, cap=c.max_kp)
+        assert n[i] == r["n"] and np.array_equal(d[i, :n[i]], r["desc"]) and np.array_equal(k[i, :n[i]], r["kps"])
+    c.close()
