@@ -216,7 +216,7 @@ void fill_bufs(orb_ctx* ctx, Bufs* B) {
   memset(B, 0, sizeof(*B));
   B->pyr = ctx->d_pyr; B->box = ctx->d_box; B->cand = ctx->d_cand; B->cand_count = ctx->d_cand_count;
   B->zero_stride = (int)(ctx->zero_bytes_per_frame / sizeof(int)); B->kept_xy = ctx->d_kept_xy; B->kept_r = ctx->d_kept_r; B->kept_count = ctx->d_kept_count;
-  B->xtab = ctx->d_xtab; B->ytab = ctx->d_ytab; B->tile_a = ctx->d_tile_a; B->tile_b = ctx->d_tile_b; B->harris_w = ctx->d_harris_w; B->pattern = ctx->d_pattern;
+  B->xtab = ctx->d_xtab; B->ytab = ctx->d_ytab; B->tile_a = ctx->d_tile_a; B->tile_b = ctx->d_tile_b; B->pattern = ctx->d_pattern;
   B->flags = ctx->d_flags;
 }
 
@@ -768,7 +768,7 @@ int orb_harris(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch, con
     int m = std::min(ctx->list_cap, n - o);
     CK(cudaMemcpyAsync(ctx->d_list_kps, kps + o, sizeof(orb_keypoint) * m, cudaMemcpyHostToDevice, ctx->stream));
     orbk::k_harris_list<<<(m + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_frames, ctx->frames_pitch, w, h, ctx->d_list_kps, m,
-                                                                 ctx->d_harris_w, ctx->p.harris_k, ctx->d_list_out);
+                                                                 ctx->p.harris_k, ctx->d_list_out);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(response + o, ctx->d_list_out, sizeof(float) * m, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -1,18 +1,20 @@
-// orb_kernels.cuh -- sm_100a kernels of the ORB hot path (u8 end to end, no tensor cores: nothing
-// here is a dense contraction).  Four launches per chunk of frames:
-//   k_pyramid      : per (frame, level >= 1, 128x32 tile): bilinear resize from level 0 + 5x5 Gaussian in shared
-//                    memory, level pixels written once.  Replaces ref ORB::buildPyramid (src/orb.cpp:111-120 /
-//                    src/orb_cpu.cpp:278-290).
-//   k_fast         : per (frame, level, 128x64 tile): FAST-n segment test + SAD score + 3x3 NMS, Harris response
-//                    of the survivors, 5x5 box-sum image for BRIEF.  Replaces d_Fast (src/cuda/Fast.cu:30-209),
-//                    d_NMS (src/cuda/NMS.cu:21-128), HarrisScore (src/cuda/HarrisScore.cu:23-89) and cv::integral
-//                    (src/cuda/Brief.cu:101-105).
-//   k_select       : per (frame, level): exact top-quota selection under the total order
-//                    (response desc, y asc, x asc) by 64-bit radix select, then raster sort
-//                    (ref std::nth_element at src/orb.cpp:73-86; raster cap at src/orb_cpu.cpp:110).
-//   k_describe     : one warp per kept keypoint: intensity-centroid orientation (ref d_Orientations,
-//                    src/cuda/Orientations.cu:22-63 == src/orb_cpu.cpp:139-183) and rotated BRIEF with
-//                    ballot-packed words (ref d_Brief, src/cuda/Brief.cu:40-95 == src/orb_cpu.cpp:203-258).
+// orb_kernels.cuh -- sm_100a kernels of the ORB hot path (u8 end to end; no tensor cores: nothing in the extractor is
+// a dense contraction).  Per wave of frames one small memset and five launches:
+//   k_pyramid  : per (frame, level >= 1, 128x64 tile): bilinear resize from level 0 + 5x5 Gaussian in shared memory,
+//                level pixels written once.  Replaces ORB::buildPyramid (ref src/orb.cpp:111-120 / src/orb_cpu.cpp:278-290).
+//   k_fast     : per (frame, level, 128x64 tile): FAST-n segment test + SAD score + 3x3 NMS -> candidate positions;
+//                5x5 box-sum image and border strip tables for BRIEF.  Replaces d_Fast (ref src/cuda/Fast.cu:30-209),
+//                d_NMS (src/cuda/NMS.cu:21-128) and the host cv::integral (src/cuda/Brief.cu:101-105).
+//   k_harris   : one thread per candidate: Harris response into the candidate key.  Replaces HarrisScore
+//                (ref src/cuda/HarrisScore.cu:23-89 + src/Sobel.cpp + src/GaussianBlur.cpp).
+//   k_select   : per (frame, level): exact top-quota selection under the total order (response desc, y asc, x asc) by
+//                64-bit radix select, then raster sort (ref std::nth_element at src/orb.cpp:73-86; raster cap at
+//                src/orb_cpu.cpp:110).
+//   k_describe : one warp per kept keypoint: intensity-centroid orientation (ref d_Orientations,
+//                src/cuda/Orientations.cu:22-63 == src/orb_cpu.cpp:139-183) and rotated BRIEF with ballot-packed words
+//                (ref d_Brief, src/cuda/Brief.cu:40-95 == src/orb_cpu.cpp:203-258).
+// plus k_match (exact Hamming 2-NN, the step after the descriptors: ref flann->knnMatch, src/feature_matching.cpp:168)
+// and two helpers for the single-image stage entry points (k_harris_list, k_eval_math).
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -40,7 +42,6 @@ struct Bufs {
   const OrbTap* ytab;
   const uint32_t* tile_a;        // per tile of k_pyramid: level | tile_x << 4 | tile_y << 18
   const uint32_t* tile_b;        // same for k_fast
-  const float* harris_w;         // 49 window weights
   const float4* pattern;         // 256 BRIEF tests (x1,y1,x2,y2) as floats
   int* flags;                    // bit 0: candidate overflow
   orb_keypoint* out_kps;         // [chunk][out_cap]
@@ -951,7 +952,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32, ORB_K3_MINB) k_describe(const O
 
 // Harris response for an explicit keypoint list on a level-0 image (stage entry point orb_harris)
 __global__ void k_harris_list(const uint8_t* __restrict__ img, int pitch, int w, int h, const orb_keypoint* kps, int n,
-                              const float* wt, float k, float* out) {
+                              float k, float* out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int ky = kps[i].y, kx = kps[i].x;
