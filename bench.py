@@ -106,6 +106,22 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU (no-op when unavailable)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64 + 1)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def oracle_params(O):
     return O.params(nfeatures=NFEAT, scale_factor=SCALE, nlevels=LEVELS, fast_threshold=THR, orient_patch=PATCH,
                     select_policy=1, blur_levels=1, harris_k=0.04)
@@ -182,6 +198,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the ORB path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    bind_to_gpu_numa_node(local_rank)            # pinned staging buffers get first-touched next to this GPU's PCIe root
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)

@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
         const int val[8] = {(int)(strip.x & 0xffff), (int)(strip.y & 0xffff), (int)(strip.x >> 16), (int)(strip.y >> 16),
                             (int)(strip.z & 0xffff), (int)(strip.w & 0xffff), (int)(strip.z >> 16), (int)(strip.w >> 16)};
 #pragma unroll
-        for (int j = 0; j < 8; j++) atomicAdd(&s_ey[8 * g + j], val[j]);
+        for (int j = 0; j < 8; j++) atomicAdd(&s_ey[16 * j + g], val[j]);   // column 8g+j lives at [16j+g]: lanes hit distinct banks
       }
     }
   } else if (tid >= B_THREADS - B_TH) {   // last two warps: row sums over columns < w-4 (and column 0 for the wrapped taps)
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs 
   }
   __syncthreads();
   if (tid < B_TW) {
-    const int x = x0 + tid, v = s_ey[tid];
+    const int x = x0 + tid, v = s_ey[16 * (tid & 7) + (tid >> 3)];
     if (v && x >= 2 && x <= w - 3) atomicAdd(ey + x, v);
   }
 }
