@@ -319,7 +319,10 @@ def main():
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "latest_ncu.json")))
-        traffic = prof.get(names[int(np.argmax(st_ms))], {}).get("dram_bytes_per_launch")
+        # DRAM bytes of one captured launch, rescaled from the capture's frames per launch to this run's
+        per_launch = prof.get(names[int(np.argmax(st_ms))], {}).get("dram_bytes_per_launch")
+        if per_launch is not None:
+            traffic = per_launch / float(prof.get("_frames_per_launch", 128)) * frames_per_launch
     except Exception:
         pass
 

@@ -57,8 +57,8 @@ def main():
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     summary = {"tag": tag, "source": os.path.basename(rep), "kernels": {}}
     md = ["# ncu summary `%s`" % tag, "",
-          "`ncu --set full --clock-control none --import-source on` on `python bench.py --steps 2 --warmup 3 --frames 112 --no-cpu`"
-          " (1 B200, chunk of 15 frames per launch). Times are per launch in microseconds, bytes per launch.", ""]
+          "`ncu --set full --clock-control none --import-source on` on `python bench.py --steps 2 --warmup 3 --frames 128 --no-cpu`"
+          " (1 B200, one wave of 128 frames per launch). Times are per launch in microseconds, bytes per launch.", ""]
     if os.path.exists(rep):
         ks = read_rep(rep)
         md.append("| kernel | captures | time us | DRAM read | DRAM write | regs | warps active % | SM thr % | L1/TEX % | L2 % | DRAM % | issue active % | warp inst | L1 hit % | L2 hit % | smem conflicts |")
@@ -103,7 +103,7 @@ def main():
     json.dump(summary, open(os.path.join(ROOT, "profiles", "%s_ncu_summary.json" % tag), "w"), indent=1)
     latest = {k: {"dram_bytes_per_launch": v["dram_bytes_per_launch"], "time_us": v.get("time")} for k, v in summary["kernels"].items()}
     latest["_tag"] = tag
-    latest["_frames_per_launch"] = 15
+    latest["_frames_per_launch"] = int(sys.argv[sys.argv.index("--frames-per-launch") + 1]) if "--frames-per-launch" in sys.argv else 128
     json.dump(latest, open(os.path.join(ROOT, "profiles", "latest_ncu.json"), "w"), indent=1)
     print("\n".join(md))
 
