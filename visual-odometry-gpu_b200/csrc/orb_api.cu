@@ -280,7 +280,7 @@ int launch_select(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, int nframes) {
 }
 int launch_describe(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, const DescribeJob& J, int nwarps, int nframes) {
   if (nwarps <= 0) return ORB_OK;
-  dim3 grid((nwarps + orbk::K3_WARPS - 1) / orbk::K3_WARPS, nframes);
+  dim3 grid((nwarps + orbk::K3_KPS - 1) / orbk::K3_KPS, nframes);
   {
     StageTimer t(ctx, 4);
     orbk::k_describe<<<grid, orbk::K3_WARPS * 32, 0, ctx->stream>>>(P, B, J);

@@ -10,8 +10,8 @@
 //   k_select   : per (frame, level): exact top-quota selection under the total order (response desc, y asc, x asc) by
 //                64-bit radix select, then raster sort (ref std::nth_element at src/orb.cpp:73-86; raster cap at
 //                src/orb_cpu.cpp:110).
-//   k_describe : one warp per kept keypoint: intensity-centroid orientation (ref d_Orientations,
-//                src/cuda/Orientations.cu:22-63 == src/orb_cpu.cpp:139-183) and rotated BRIEF with ballot-packed words
+//   k_describe : CTA per 32 kept keypoints (warp per keypoint; lane per keypoint for the libm part):
+//                intensity-centroid orientation (ref d_Orientations, src/cuda/Orientations.cu:22-63 == src/orb_cpu.cpp:139-183) and rotated BRIEF with ballot-packed words
 //                (ref d_Brief, src/cuda/Brief.cu:40-95 == src/orb_cpu.cpp:203-258).
 // plus k_match (exact Hamming 2-NN, the step after the descriptors: ref flann->knnMatch, src/feature_matching.cpp:168)
 // and two helpers for the single-image stage entry points (k_harris_list, k_eval_math).
@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(K2_THREADS) k_select(const OrbPlan P, const Bu
 }
 
 // ---------------------------------------------------------------------------------------------
-// Orientation + rotated BRIEF: one warp per keypoint.
+// Orientation + rotated BRIEF.
 #ifndef ORB_BRIEF_UNROLL
 #define ORB_BRIEF_UNROLL 8
 #endif
@@ -709,10 +709,10 @@ constexpr int BRIEF_UNROLL = ORB_BRIEF_UNROLL;
 #endif
 constexpr int ORIENT_UNROLL = ORB_ORIENT_UNROLL;
 #ifndef ORB_K3_WARPS
-#define ORB_K3_WARPS 2
+#define ORB_K3_WARPS 4
 #endif
 #ifndef ORB_K3_MINB
-#define ORB_K3_MINB 16
+#define ORB_K3_MINB 8
 #endif
 constexpr int K3_WARPS = ORB_K3_WARPS;
 
@@ -808,21 +808,21 @@ __device__ __forceinline__ void patch_moments(const uint8_t* __restrict__ img, i
   *m01_out = warp_sum(m01);
 }
 
-__device__ __forceinline__ float orientation_of(const uint8_t* __restrict__ img, int pitch, int w, int h, int x, int y,
-                                                int pr, int lane) {
-  if (x - pr < 0 || x + pr >= w || y - pr < 0 || y + pr >= h) return 0.0f;   // ref src/orb_cpu.cpp:152-156
-  int m10, m01;
-  if (pr == 15) patch_moments<15>(img, pitch, x, y, pr, lane, &m10, &m01);      // patch 31 (include/orb.hpp:12)
-  else if (pr == 4) patch_moments<4>(img, pitch, x, y, pr, lane, &m10, &m01);   // patch 9 (include/orb_cpu.hpp:6)
-  else patch_moments<0>(img, pitch, x, y, pr, lane, &m10, &m01);
-  return orbm::atan2f_glibc((float)m01, (float)m10);                            // :178
+// moments of the orientation patch; returns false (moments untouched) when the patch leaves the level, in which case the
+// reference sets the angle to 0 (src/orb_cpu.cpp:152-156)
+__device__ __forceinline__ bool moments_of(const uint8_t* __restrict__ img, int pitch, int w, int h, int x, int y,
+                                           int pr, int lane, int* m10, int* m01) {
+  if (x - pr < 0 || x + pr >= w || y - pr < 0 || y + pr >= h) return false;
+  if (pr == 15) patch_moments<15>(img, pitch, x, y, pr, lane, m10, m01);      // patch 31 (include/orb.hpp:12)
+  else if (pr == 4) patch_moments<4>(img, pitch, x, y, pr, lane, m10, m01);   // patch 9 (include/orb_cpu.hpp:6)
+  else patch_moments<0>(img, pitch, x, y, pr, lane, m10, m01);
+  return true;
 }
 
 __device__ __forceinline__ void brief_of(const uint8_t* __restrict__ img, int pitch, const uint16_t* __restrict__ box,
-                                         int bpitch, const EdgeSrc& E, int kx, int ky, float angle,
+                                         int bpitch, const EdgeSrc& E, int kx, int ky, float c, float s,
                                          const float4* __restrict__ pattern, int lane, uint32_t* out_words) {
-  const int W = E.W, H = E.H;
-  const float c = orbm::cosf_glibc(angle), s = orbm::sinf_glibc(angle);   // ref src/orb_cpu.cpp:217-218
+  const int W = E.W, H = E.H;   // c, s = cos / sin of the keypoint angle (ref src/orb_cpu.cpp:217-218)
   uint32_t mine = 0;
   // rotated offsets stay within +-19 (pattern radius 18.4): if every box is interior the bound rule of
   // src/orb_cpu.cpp:240-245 can never fire and the sums are plain box-sum lookups
@@ -889,14 +889,20 @@ __device__ __forceinline__ void brief_of(const uint8_t* __restrict__ img, int pi
   *out_words = mine;
 }
 
+// A CTA of K3_WARPS warps owns K3_KPS = 32 consecutive keypoints of one frame and works in three phases so that the scalar
+// libm work (atan2f, cosf, sinf: ~250 instructions that a warp would execute for a single keypoint) runs once per lane
+// for 32 keypoints:  (1) warp per keypoint: integer patch moments -> shared;  (2) warp 0, lane = keypoint: angle, cos,
+// sin, level-0 coordinates, record headers;  (3) warp per keypoint: rotated BRIEF with the shared cos / sin.
+constexpr int K3_KPS = 32;
+
 __global__ void __launch_bounds__(K3_WARPS * 32, ORB_K3_MINB) k_describe(const OrbPlan P, const Bufs B, const DescribeJob J) {
-  const int lane = threadIdx.x & 31;
-  const int widx = blockIdx.x * K3_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int f = blockIdx.y;
-  int l = 0, i = widx;
-  int x, y;
-  float resp = 0.f;
-  __shared__ int s_pref[ORB_MAX_LEVELS + 1];   // exclusive prefix of the frame's kept counts (levels are concatenated)
+  const int k0 = blockIdx.x * K3_KPS;            // first keypoint (output slot) of this CTA
+  __shared__ int s_pref[ORB_MAX_LEVELS + 1];     // exclusive prefix of the frame's kept counts (levels are concatenated)
+  __shared__ int s_x[K3_KPS], s_y[K3_KPS], s_l[K3_KPS], s_m10[K3_KPS], s_m01[K3_KPS];
+  __shared__ float s_c[K3_KPS], s_s[K3_KPS];
+  int total;
   if (J.mode == 0) {
     if (threadIdx.x < 32) {
       const int c = lane < P.nlevels ? B.kept_count[f * ORB_MAX_LEVELS + lane] : 0;
@@ -909,44 +915,81 @@ __global__ void __launch_bounds__(K3_WARPS * 32, ORB_K3_MINB) k_describe(const O
       if (lane <= ORB_MAX_LEVELS) s_pref[lane] = incl - c;   // lane == nlevels .. 16 hold the total
     }
     __syncthreads();
-    const int total = s_pref[P.nlevels];
-    if (widx == 0 && lane == 0) B.out_n[f] = min(total, B.out_cap);
-    if (widx >= total || widx >= B.out_cap) return;
-    while (l + 1 < P.nlevels && widx >= s_pref[l + 1]) l++;
-    i = widx - s_pref[l];
-    uint32_t xy = B.kept_xy[(size_t)f * P.kept_per_frame + P.lv[l].kept_ofs + i];
-    resp = B.kept_r[(size_t)f * P.kept_per_frame + P.lv[l].kept_ofs + i];
-    x = xy & 0xffff; y = xy >> 16;
+    total = min(s_pref[P.nlevels], B.out_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) B.out_n[f] = total;
   } else {
-    if (widx >= J.list_n) return;
-    x = J.list_kps[widx].x; y = J.list_kps[widx].y;
+    total = J.list_n;
   }
-  const OrbLevel& G = P.lv[l];
-  const uint8_t* img;
-  int pitch;
-  if (l == 0) { img = B.frames + (size_t)f * B.frame_stride; pitch = B.pitch0; }
-  else { img = B.pyr + (size_t)f * P.pyr_frame_bytes + G.lvl_ofs; pitch = G.pitch; }
-  const uint16_t* box = B.box + (size_t)f * P.box_frame_elems + G.box_ofs;
-  const size_t o = (size_t)f * B.out_cap + widx;
+  if (k0 >= total) return;
 
-  float angle;
-  if (J.mode == 2) angle = J.list_angles[widx];
-  else angle = orientation_of(img, pitch, G.w, G.h, x, y, P.patch_radius, lane);
-  if (J.mode != 2 && lane == 0) B.out_angles[o] = angle;
-  if (J.mode != 1) {
-    uint32_t word;
+  // ---- phase 1: keypoint lookup + patch moments, one warp per keypoint ----------------------------
+  for (int q = warp; q < K3_KPS; q += K3_WARPS) {
+    const int widx = k0 + q;
+    if (widx >= total) break;
+    int l = 0, x, y;
+    if (J.mode == 0) {
+      while (l + 1 < P.nlevels && widx >= s_pref[l + 1]) l++;
+      const uint32_t xy = B.kept_xy[(size_t)f * P.kept_per_frame + P.lv[l].kept_ofs + (widx - s_pref[l])];
+      x = xy & 0xffff; y = xy >> 16;
+    } else {
+      x = J.list_kps[widx].x; y = J.list_kps[widx].y;
+    }
+    int m10 = 0, m01 = 0;
+    bool inside = false;
+    if (J.mode != 2) {
+      const OrbLevel& G = P.lv[l];
+      const uint8_t* img;
+      int pitch;
+      if (l == 0) { img = B.frames + (size_t)f * B.frame_stride; pitch = B.pitch0; }
+      else { img = B.pyr + (size_t)f * P.pyr_frame_bytes + G.lvl_ofs; pitch = G.pitch; }
+      inside = moments_of(img, pitch, G.w, G.h, x, y, P.patch_radius, lane, &m10, &m01);
+    }
+    if (lane == 0) { s_x[q] = x; s_y[q] = y; s_l[q] = inside ? l : (l | 0x100); s_m10[q] = m10; s_m01[q] = m01; }
+  }
+  __syncthreads();
+
+  // ---- phase 2: lane = keypoint: angle (glibc-exact atan2f), cos / sin, record headers -----------
+  if (warp == 0 && k0 + lane < total) {
+    const int widx = k0 + lane, x = s_x[lane], y = s_y[lane], l = s_l[lane] & 0xff;
+    const size_t o = (size_t)f * B.out_cap + widx;
+    float angle;
+    if (J.mode == 2) angle = J.list_angles[widx];
+    else angle = (s_l[lane] & 0x100) ? 0.0f : orbm::atan2f_glibc((float)s_m01[lane], (float)s_m10[lane]);   // ref src/orb_cpu.cpp:178
+    if (J.mode != 1) { s_c[lane] = orbm::cosf_glibc(angle); s_s[lane] = orbm::sinf_glibc(angle); }      // :217-218
+    if (J.mode != 2) B.out_angles[o] = angle;
+    if (J.mode == 0) {
+      // kp.x *= scale (int * float, truncated): ref src/orb.cpp:94-98
+      const float sc = P.lv[l].scale;
+      orb_keypoint kp;
+      kp.x = __float2int_rz(orbm::fmul((float)x, sc));
+      kp.y = __float2int_rz(orbm::fmul((float)y, sc));
+      B.out_kps[o] = kp;
+      if (B.side_xy) {
+        B.side_xy[o] = orb_keypoint{x, y};
+        B.side_level[o] = l;
+        B.side_resp[o] = B.kept_r[(size_t)f * P.kept_per_frame + P.lv[l].kept_ofs + (widx - s_pref[l])];
+      }
+    }
+  }
+  if (J.mode == 1) return;
+  __syncthreads();
+
+  // ---- phase 3: rotated BRIEF, one warp per keypoint ----------------------------------------------
+  for (int q = warp; q < K3_KPS; q += K3_WARPS) {
+    const int widx = k0 + q;
+    if (widx >= total) break;
+    const int l = s_l[q] & 0xff;
+    const OrbLevel& G = P.lv[l];
+    const uint8_t* img;
+    int pitch;
+    if (l == 0) { img = B.frames + (size_t)f * B.frame_stride; pitch = B.pitch0; }
+    else { img = B.pyr + (size_t)f * P.pyr_frame_bytes + G.lvl_ofs; pitch = G.pitch; }
+    const uint16_t* box = B.box + (size_t)f * P.box_frame_elems + G.box_ofs;
     const int* ey = B.cand_count + (size_t)f * B.zero_stride + ORB_MAX_LEVELS + G.edge_ofs;
     const EdgeSrc E{img, pitch, G.w, G.h, ey, ey + G.edge_w};
-    brief_of(img, pitch, box, G.bpitch, E, x, y, angle, B.pattern, lane, &word);
-    if (lane < 8) ((uint32_t*)B.out_desc)[o * 8 + lane] = word;
-  }
-  if (J.mode == 0 && lane == 0) {
-    // kp.x *= scale (int * float, truncated): ref src/orb.cpp:94-98
-    orb_keypoint kp;
-    kp.x = __float2int_rz(orbm::fmul((float)x, G.scale));
-    kp.y = __float2int_rz(orbm::fmul((float)y, G.scale));
-    B.out_kps[o] = kp;
-    if (B.side_xy) { B.side_xy[o] = orb_keypoint{x, y}; B.side_level[o] = l; B.side_resp[o] = resp; }
+    uint32_t word;
+    brief_of(img, pitch, box, G.bpitch, E, s_x[q], s_y[q], s_c[q], s_s[q], B.pattern, lane, &word);
+    if (lane < 8) ((uint32_t*)B.out_desc)[((size_t)f * B.out_cap + widx) * 8 + lane] = word;
   }
 }
 
