@@ -140,6 +140,49 @@ def cpu_leg(frames_np, threads, steps, warmup):
     return frames_np.shape[0] / dt, dt
 
 
+def ingest_leg(V, ctx, pool_frames, idx, cap, outs, n_kp_expected):
+    """SURVEY 8(f)-3 (not part of the headline metric): the same batch read from 8-bit gray PNG files (page cache) through
+    orb_detect_and_compute_files, host threads decoding into the pinned staging area while the GPU works.  Wall clock,
+    because host threads are part of the path.  Beside it: single-thread decode rates of this library and of cv2."""
+    import shutil
+    import tempfile
+    import time
+    d = tempfile.mkdtemp(prefix="orb_ingest_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        files = []
+        for i in range(len(pool_frames)):
+            files.append(os.path.join(d, "%06d.png" % i))
+            V.synth.write_png_gray8(files[-1], pool_frames[i])
+        paths = [files[i] for i in idx]
+        png_bytes = float(np.mean([os.path.getsize(f) for f in files]))
+        out = tuple(t.numpy() for t in outs)
+        threads = os.cpu_count() or 1
+        ctx.detect_and_compute_files(paths, cap=cap, threads=threads, out=out)       # warm-up (pinned area, page cache)
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            ctx.detect_and_compute_files(paths, cap=cap, threads=threads, out=out)
+        dt = (time.perf_counter() - t0) / reps
+        assert int(out[3].sum()) == n_kp_expected, "file path and batch path disagree"
+        res = {"frames_per_s": len(paths) / dt, "frames": len(paths), "host_threads": threads, "png_bytes_per_frame": png_bytes,
+               "decode": "host"}
+        t0 = time.perf_counter()
+        for f in files[:16]:
+            V.imread_gray8(f)
+        res["imread_1thread_frames_per_s"] = 16 / (time.perf_counter() - t0)
+        try:
+            import cv2
+            t0 = time.perf_counter()
+            for f in files[:16]:
+                cv2.imread(f, cv2.IMREAD_GRAYSCALE)
+            res["cv2_imread_1thread_frames_per_s"] = 16 / (time.perf_counter() - t0)
+        except ImportError:
+            pass
+        return res
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU algorithm for this path on the host cores (oracle port; the
     reference's own orb_cpu.cpp is single-level and needs OpenCV)."""
@@ -170,6 +213,7 @@ def main():
     ap.add_argument("--frames", type=int, default=1000, help="frames per GPU per step")
     ap.add_argument("--chunk", type=int, default=0, help="frames per kernel wave (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ingest", action="store_true", help="skip the PNG-file ingest leg (SURVEY 8(f)-3)")
     ap.add_argument("--shape", default=None, help="WxH of the synthetic frames (default 1241x376 = the headline workload)")
     ap.add_argument("--levels", type=int, default=None)
     ap.add_argument("--nfeatures", type=int, default=None)
@@ -294,6 +338,10 @@ def main():
     sampler.stop()
     assert int(h_n.sum().item()) == n_kp, "host and device paths disagree"
 
+    ingest = None
+    if rank == 0 and world == 1 and not args.no_ingest:
+        ingest = ingest_leg(V, ctx, host_pool[:, :, :W], idx, cap, (h_k, h_a, h_d, h_n), n_kp)
+
     total_frames = F * world
     value = total_frames * args.steps / (ms_dev * 1e-3)
     e2e_value = total_frames * e2e_steps / (ms_e2e * 1e-3)
@@ -335,7 +383,7 @@ def main():
                    "cache_hygiene": "input batch %.0f MB > 126 MB L2; scratch arena reused per chunk" % (F * H * PITCH / 1e6),
                    "stage_names": names,
                    "stage_ms_per_step": [m / prof_steps for m in st_ms], "stage_share": stage_share,
-                   "match_knn2_ms_per_step": ms_match, "match_pairs_per_step": F - 1,
+                   "match_knn2_ms_per_step": ms_match, "match_pairs_per_step": F - 1, "ingest_png": ingest,
                    "pass_b_min_bytes_per_frame": b_min, "pass_hbm_gbs_per_gpu": pass_gbs, "pass_hbm_frac": pass_gbs / peak,
                    "peak_source": peak_src},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(F * H * PITCH) * world,

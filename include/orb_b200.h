@@ -40,7 +40,9 @@ typedef enum {
   ORB_E_CUDA = -2,         /* CUDA runtime error (see orb_last_error)             */
   ORB_E_CAPACITY = -3,     /* image / batch larger than the context was built for */
   ORB_E_OVERFLOW = -4,     /* more corner candidates than the arena holds         */
-  ORB_E_NOMEM = -5
+  ORB_E_NOMEM = -5,
+  ORB_E_IO = -6,           /* a frame file could not be read                      */
+  ORB_E_FORMAT = -7        /* a frame file is not a PNG this library decodes      */
 } orb_status;
 
 /* selection policy for the per-level keypoint cap */
@@ -149,6 +151,31 @@ int  orb_match_knn2_batch(orb_ctx* ctx, const orb_descriptor* desc, const int* n
                           orb_match* out);
 /* the reference's ratio test, src/feature_matching.cpp:174-182: keep[i] = has two neighbours && dist1 < ratio * dist2 */
 void orb_ratio_test(const orb_match* m, int n, float ratio, uint8_t* keep);
+
+/* ---- frame ingest: the step before the path ---------------------------------------------------
+ * Replaces cv::imread(path, cv::IMREAD_GRAYSCALE) of the reference's VO loops (src/feature_matching.cpp:55,59;
+ * src/feature_tracking.cpp:56,196).  Decodes non-interlaced PNG of bit depth 8 / 16, gray, gray+alpha, RGB, RGBA to
+ * 8-bit gray with the results of OpenCV 4.13's imread (libpng's rgb_to_gray coefficients, 16 -> 8 by the high byte);
+ * palette, interlaced and sub-byte files are rejected with ORB_E_FORMAT.  Chunk CRCs and the zlib checksum are
+ * verified, corrupt files fail like they do in libpng. */
+typedef struct orb_image_info { int32_t width, height, bit_depth, channels; } orb_image_info;
+/* header of an encoded PNG held in memory (ctx-less; message via orb_last_error(NULL)) */
+int  orb_png_info(const uint8_t* file, size_t file_bytes, orb_image_info* info);
+/* host decode into a caller buffer of `pitch` bytes per row (ctx-less; w, h must equal the file's size) */
+int  orb_png_decode_gray8(const uint8_t* file, size_t file_bytes, uint8_t* dst, size_t pitch, int w, int h);
+/* == cv::imread(path, IMREAD_GRAYSCALE) into a caller buffer of cap_w x cap_h at `pitch`; size returned in w, h */
+int  orb_imread_gray8(const char* path, uint8_t* dst, size_t pitch, int cap_w, int cap_h, int* w, int* h);
+/* detect-and-compute over a list of PNG files of one size: n_threads host threads (0 = all cores) read and decode
+ * the files straight into the context's pinned staging area while earlier waves of frames are copied and processed
+ * on the device; outputs as orb_detect_and_compute_batch.  A frame that fails to load aborts the call with
+ * ORB_E_IO / ORB_E_FORMAT and names the file in orb_last_error.
+ * decode_on_device = 1 moves inflate + unfilter to the GPU for 8-bit gray files (the host only reads the files and
+ * uploads the compressed bytes); files of other layouts make the call fail with ORB_E_FORMAT. */
+int  orb_detect_and_compute_files(orb_ctx* ctx, const char* const* paths, int n_frames, int n_threads,
+                                  int decode_on_device, int cap, orb_keypoint* kps, float* angles, orb_descriptor* desc,
+                                  int* n_out, int outputs_on_device);
+/* the decoded frame `frame` of the last orb_detect_and_compute_files call (level 0 as the kernels saw it) */
+int  orb_get_ingested_frame(orb_ctx* ctx, int frame, uint8_t* dst, size_t dst_pitch, int* w, int* h);
 
 /* ---- side arrays of the LAST orb_detect_and_compute[_batch] call (testing / diagnostics) ----
  * level-space coordinates, level id and Harris response of output record i of `frame`

@@ -7,10 +7,12 @@ repository root.  The product is csrc/ (CUDA kernels + C ABI, built to liborb_b2
 mirror in orb.py; the CPU parity checker is never imported from here.
 """
 from .orb import (KP, MATCH, ORB, ORBCPU, Context, OrbError, OrientedFAST, Params, RotatedBRIEF, SELECT_HARRIS_TOP_N,
-                  SELECT_RASTER_FIRST_N, EXPORTS, default_params, lib_path, load_library, make_params)
+                  SELECT_RASTER_FIRST_N, EXPORTS, default_params, imdecode_gray8, imread_gray8, lib_path, load_library, make_params,
+                  png_info)
 from .sharding import shard_range
+from . import synth
 from .synth import synth_frames
 
 __all__ = ["KP", "MATCH", "ORB", "ORBCPU", "Context", "OrbError", "OrientedFAST", "Params", "RotatedBRIEF",
            "SELECT_HARRIS_TOP_N", "SELECT_RASTER_FIRST_N", "EXPORTS", "default_params", "lib_path", "load_library",
-           "make_params", "shard_range", "synth_frames"]
+           "make_params", "shard_range", "synth_frames", "imdecode_gray8", "imread_gray8", "png_info"]

@@ -11,12 +11,22 @@
 #include <cstdlib>
 #include <cstdint>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "../../include/orb_b200.h"
 #include "../../include/orb_brief_pattern.h"
 #include "orb_kernels.cuh"
 #include "orb_plan.h"
+#include "orb_png.h"
 
 using orbk::Bufs;
 using orbk::DescribeJob;
@@ -60,6 +70,8 @@ struct orb_ctx {
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_start = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_done;
+  // frame ingest: pinned host area the decode threads fill (same layout as d_frames)
+  uint8_t* h_ingest = nullptr; size_t h_ingest_bytes = 0;
   // optional per-kernel event timing
   bool profiling = false;
   struct Span { int stage; cudaEvent_t a, b; };
@@ -353,6 +365,7 @@ void orb_destroy(orb_ctx* ctx) {
   for (void* q : ptrs) if (q) cudaFree(q);
   for (auto& sp : ctx->spans) { if (sp.a) cudaEventDestroy(sp.a); if (sp.b) cudaEventDestroy(sp.b); }
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  if (ctx->h_ingest) cudaFreeHost(ctx->h_ingest);
   for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->ev_done) cudaEventDestroy(e);
   if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
@@ -541,12 +554,20 @@ int orb_get_stage_ms(orb_ctx* ctx, float ms[5], int launches[5]) {
   return ORB_OK;
 }
 
-int orb_detect_and_compute_batch(orb_ctx* ctx, const uint8_t* frames, int frames_on_device, int n_frames, int w, int h,
-                                 size_t pitch, size_t frame_stride, int cap, orb_keypoint* kps, float* angles,
-                                 orb_descriptor* desc, int* n_out, int outputs_on_device) {
+// How the frames of a wave reach the staging area when they do not come from a caller buffer (frame ingest):
+// stage() runs on the calling thread just before the wave's kernels are queued, may block on host work, and queues on
+// ctx->s_h2d whatever brings frames [c0, c0 + nc) into ctx->d_frames.
+struct WaveSource {
+  virtual int stage(orb_ctx* ctx, int c0, int nc) = 0;
+  virtual ~WaveSource() {}
+};
+
+static int run_batch(orb_ctx* ctx, const uint8_t* frames, int frames_on_device, int n_frames, int w, int h,
+                     size_t pitch, size_t frame_stride, int cap, orb_keypoint* kps, float* angles,
+                     orb_descriptor* desc, int* n_out, int outputs_on_device, WaveSource* source) {
   if (!ctx) return ORB_E_INVALID;
-  if (!frames || !kps || !angles || !desc || !n_out) return fail(ctx, ORB_E_INVALID, "null buffer");
-  if (n_frames < 1 || cap < 1 || pitch < (size_t)w || frame_stride < pitch * (size_t)(h - 1) + w)
+  if ((!frames && !source) || !kps || !angles || !desc || !n_out) return fail(ctx, ORB_E_INVALID, "null buffer");
+  if (n_frames < 1 || cap < 1 || (!source && (pitch < (size_t)w || frame_stride < pitch * (size_t)(h - 1) + w)))
     return fail(ctx, ORB_E_INVALID, "bad batch geometry");
   if (n_frames > ctx->p.max_batch) return fail(ctx, ORB_E_CAPACITY, "batch %d exceeds max_batch %d", n_frames, ctx->p.max_batch);
   if (!outputs_on_device && cap > ctx->max_kp)
@@ -563,7 +584,7 @@ int orb_detect_and_compute_batch(orb_ctx* ctx, const uint8_t* frames, int frames
   // copy stream so that the transfer of chunk i+1 overlaps the kernels of chunk i; host outputs leave on a third
   // stream as soon as their chunk is described.
   // (and pitch > w: k_pyramid reads the byte after a row's last pixel, which must belong to the caller's buffer)
-  const bool direct = frames_on_device && ((uintptr_t)frames % 16 == 0) && pitch % 16 == 0 && frame_stride % 16 == 0 && pitch > (size_t)w;
+  const bool direct = !source && frames_on_device && ((uintptr_t)frames % 16 == 0) && pitch % 16 == 0 && frame_stride % 16 == 0 && pitch > (size_t)w;
   const uint8_t* src = direct ? frames : ctx->d_frames;
   const size_t stride = direct ? frame_stride : ctx->frames_slot_bytes;
   const int sp = direct ? (int)pitch : ctx->frames_pitch;
@@ -602,7 +623,7 @@ int orb_detect_and_compute_batch(orb_ctx* ctx, const uint8_t* frames, int frames
     CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_start, 0));
     CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_start, 0));
   }
-  if (!direct) {
+  if (!direct && !source) {
     const cudaMemcpyKind kind = frames_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     for (int ci = 0; ci < nchunks; ci++) {
       const int c0 = wave_begin[ci], nc = wave_begin[ci + 1] - c0;
@@ -623,6 +644,14 @@ int orb_detect_and_compute_batch(orb_ctx* ctx, const uint8_t* frames, int frames
 
   for (int ci = 0; ci < nchunks; ci++) {
     const int c0 = wave_begin[ci], nc = wave_begin[ci + 1] - c0;
+    if (source) {
+      if ((rc = source->stage(ctx, c0, nc))) {
+        // frames of earlier waves are still in flight: drain before handing the buffers back
+        cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->s_d2h);
+        return rc;
+      }
+      CK(cudaEventRecord(ctx->ev_in[ci], ctx->s_h2d));
+    }
     if (!direct) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[ci], 0));
     Bufs B;
     fill_bufs(ctx, &B);
@@ -658,6 +687,14 @@ int orb_detect_and_compute_batch(orb_ctx* ctx, const uint8_t* frames, int frames
     return check_flags(ctx);
   }
   return ORB_OK;
+}
+
+int orb_detect_and_compute_batch(orb_ctx* ctx, const uint8_t* frames, int frames_on_device, int n_frames, int w, int h,
+                                 size_t pitch, size_t frame_stride, int cap, orb_keypoint* kps, float* angles,
+                                 orb_descriptor* desc, int* n_out, int outputs_on_device) {
+  if (ctx && !frames) return fail(ctx, ORB_E_INVALID, "null buffer");
+  return run_batch(ctx, frames, frames_on_device, n_frames, w, h, pitch, frame_stride, cap, kps, angles, desc, n_out,
+                   outputs_on_device, nullptr);
 }
 
 int orb_detect_and_compute(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch, int cap, orb_keypoint* kps,
@@ -888,6 +925,178 @@ int orb_debug_eval_math(orb_ctx* ctx, int op, const float* a, const float* b, in
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaMemcpy(out, dout, sizeof(float) * n, cudaMemcpyDeviceToHost));
   cudaFree(da); cudaFree(db); cudaFree(dout);
+  return ORB_OK;
+}
+
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Frame ingest: PNG files -> staging area -> the wave pipeline above.
+namespace {
+
+// whole file into `buf`; returns false with errno-style message
+bool read_file(const char* path, std::vector<uint8_t>* buf, std::string* err) {
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) { *err = std::string("cannot open ") + path; return false; }
+  struct stat st;
+  if (fstat(fd, &st) != 0 || st.st_size <= 0) { close(fd); *err = std::string("cannot stat ") + path; return false; }
+  buf->resize((size_t)st.st_size);
+  size_t got = 0;
+  while (got < buf->size()) {
+    const ssize_t r = read(fd, buf->data() + got, buf->size() - got);
+    if (r <= 0) break;
+    got += (size_t)r;
+  }
+  close(fd);
+  if (got != buf->size()) { *err = std::string("short read on ") + path; return false; }
+  return true;
+}
+
+// Host-decode source: a pool of threads decodes the files in order straight into the pinned area; stage() waits for
+// the frames of its wave and queues their copy.
+struct HostDecodeSource : WaveSource {
+  const char* const* paths; int n, w, h;
+  uint8_t* area; size_t slot; int pitch;
+  std::vector<std::thread> pool;
+  std::atomic<int> next{0};
+  std::atomic<bool> stop{false};
+  std::mutex mu; std::condition_variable cv;
+  std::vector<uint8_t> done;
+  int ready = 0;                 // frames [0, ready) are decoded (guarded by mu)
+  int err_code = 0; std::string err_msg;
+
+  void work() {
+    std::vector<uint8_t> file;
+    orbpng::Scratch scratch;
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= n || stop.load()) return;
+      std::string msg;
+      int code = 0;
+      if (!read_file(paths[i], &file, &msg)) code = ORB_E_IO;
+      else {
+        const char* e = orbpng::decode_gray8(file.data(), file.size(), area + (size_t)i * slot, (size_t)pitch, w, h, &scratch);
+        if (e) { code = ORB_E_FORMAT; msg = std::string(paths[i]) + ": " + e; }
+      }
+      std::lock_guard<std::mutex> lk(mu);
+      if (code && !err_code) { err_code = code; err_msg = msg; stop.store(true); }
+      done[i] = 1;
+      cv.notify_all();
+    }
+  }
+  void start(int n_threads) {
+    done.assign(n, 0);
+    for (int t = 0; t < n_threads; t++) pool.emplace_back([this] { work(); });
+  }
+  int stage(orb_ctx* ctx, int c0, int nc) override {
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] {
+        while (ready < n && done[ready]) ready++;
+        return err_code != 0 || ready >= c0 + nc;
+      });
+      if (err_code) return fail(ctx, err_code, "%s", err_msg.c_str());
+    }
+    CK(cudaMemcpyAsync(ctx->d_frames + (size_t)c0 * slot, area + (size_t)c0 * slot, slot * nc, cudaMemcpyHostToDevice, ctx->s_h2d));
+    return ORB_OK;
+  }
+  ~HostDecodeSource() override {
+    stop.store(true);
+    for (auto& t : pool) t.join();
+  }
+};
+
+int png_status(const char* e) {
+  if (!e) return ORB_OK;
+  snprintf(g_create_error, sizeof(g_create_error), "%s", e);
+  return ORB_E_FORMAT;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orb_png_info(const uint8_t* file, size_t file_bytes, orb_image_info* info) {
+  if (!file || !info) return ORB_E_INVALID;
+  orbpng::Info I;
+  const int rc = png_status(orbpng::read_info(file, file_bytes, &I));
+  if (rc) return rc;
+  info->width = I.width; info->height = I.height; info->bit_depth = I.bit_depth; info->channels = I.channels;
+  return ORB_OK;
+}
+
+int orb_png_decode_gray8(const uint8_t* file, size_t file_bytes, uint8_t* dst, size_t pitch, int w, int h) {
+  if (!file || !dst) return ORB_E_INVALID;
+  return png_status(orbpng::decode_gray8(file, file_bytes, dst, pitch, w, h, nullptr));
+}
+
+int orb_imread_gray8(const char* path, uint8_t* dst, size_t pitch, int cap_w, int cap_h, int* w, int* h) {
+  if (!path || !dst) return ORB_E_INVALID;
+  std::vector<uint8_t> file;
+  std::string msg;
+  if (!read_file(path, &file, &msg)) { snprintf(g_create_error, sizeof(g_create_error), "%s", msg.c_str()); return ORB_E_IO; }
+  orbpng::Info I;
+  int rc = png_status(orbpng::read_info(file.data(), file.size(), &I));
+  if (rc) return rc;
+  if (w) *w = I.width;
+  if (h) *h = I.height;
+  if (I.width > cap_w || I.height > cap_h) { snprintf(g_create_error, sizeof(g_create_error), "%s: image %dx%d exceeds the buffer", path, I.width, I.height); return ORB_E_CAPACITY; }
+  return png_status(orbpng::decode_gray8(file.data(), file.size(), dst, pitch, I.width, I.height, nullptr));
+}
+
+int orb_detect_and_compute_files(orb_ctx* ctx, const char* const* paths, int n_frames, int n_threads, int decode_on_device,
+                                 int cap, orb_keypoint* kps, float* angles, orb_descriptor* desc, int* n_out,
+                                 int outputs_on_device) {
+  if (!ctx) return ORB_E_INVALID;
+  if (!paths || n_frames < 1) return fail(ctx, ORB_E_INVALID, "no frame files");
+  if (n_frames > ctx->p.max_batch) return fail(ctx, ORB_E_CAPACITY, "batch %d exceeds max_batch %d", n_frames, ctx->p.max_batch);
+  CK(cudaSetDevice(ctx->p.device));
+  // the first file fixes the frame size of the call
+  int w = 0, h = 0;
+  {
+    uint8_t head[64];
+    const int fd = open(paths[0], O_RDONLY);
+    const ssize_t got = fd >= 0 ? read(fd, head, sizeof(head)) : -1;
+    if (fd >= 0) close(fd);
+    if (got < 33) return fail(ctx, ORB_E_IO, "cannot read %s", paths[0]);
+    orbpng::Info I;
+    const char* e = orbpng::read_info(head, (size_t)got, &I);
+    if (e) return fail(ctx, ORB_E_FORMAT, "%s: %s", paths[0], e);
+    w = I.width; h = I.height;
+  }
+  int rc = get_plan(ctx, w, h);
+  if (rc) return rc;
+  if (decode_on_device) return fail(ctx, ORB_E_INVALID, "device decode is not available in this build");
+  const size_t need = ctx->frames_slot_bytes * (size_t)n_frames;
+  if (need > ctx->h_ingest_bytes) {
+    if (ctx->h_ingest) CK(cudaFreeHost(ctx->h_ingest));
+    ctx->h_ingest = nullptr; ctx->h_ingest_bytes = 0;
+    CK(cudaHostAlloc((void**)&ctx->h_ingest, need, cudaHostAllocDefault));
+    ctx->h_ingest_bytes = need;
+    memset(ctx->h_ingest, 0, need);
+  }
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  n_threads = std::min(n_threads, n_frames);
+  HostDecodeSource src;
+  src.paths = paths; src.n = n_frames; src.w = w; src.h = h;
+  src.area = ctx->h_ingest; src.slot = ctx->frames_slot_bytes; src.pitch = ctx->frames_pitch;
+  src.start(n_threads);
+  return run_batch(ctx, nullptr, 0, n_frames, w, h, 0, 0, cap, kps, angles, desc, n_out, outputs_on_device, &src);
+}
+
+int orb_get_ingested_frame(orb_ctx* ctx, int frame, uint8_t* dst, size_t dst_pitch, int* w, int* h) {
+  if (!ctx || !dst) return ORB_E_INVALID;
+  if (!ctx->plan_valid || ctx->last_frames != ctx->d_frames || frame < 0 || frame >= ctx->last_n)
+    return fail(ctx, ORB_E_INVALID, "frame %d is not in the staging area", frame);
+  const int W = ctx->plan.lv[0].w, H = ctx->plan.lv[0].h;
+  if (dst_pitch < (size_t)W) return fail(ctx, ORB_E_INVALID, "dst_pitch too small");
+  CK(cudaSetDevice(ctx->p.device));
+  CK(cudaMemcpy2DAsync(dst, dst_pitch, ctx->d_frames + (size_t)frame * ctx->frames_slot_bytes, ctx->frames_pitch, W, H,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (w) *w = W;
+  if (h) *h = H;
   return ORB_OK;
 }
 

@@ -41,11 +41,16 @@ class Params(C.Structure):
                 ("max_keypoints", C.c_int32), ("keep_side_arrays", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
+class ImageInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bit_depth", C.c_int32), ("channels", C.c_int32)]
+
+
 EXPORTS = [
     "orb_abi_version", "orb_default_params", "orb_create", "orb_destroy", "orb_last_error", "orb_set_stream", "orb_use_own_stream",
     "orb_synchronize", "orb_detect_and_compute", "orb_detect_and_compute_batch", "orb_get_level", "orb_level_size",
     "orb_level_quota", "orb_fast_detect", "orb_harris", "orb_orientations", "orb_brief", "orb_get_side_arrays",
     "orb_get_candidates", "orb_get_harris_weights", "orb_last_launch_count", "orb_set_profiling", "orb_get_stage_ms", "orb_match_knn2", "orb_match_knn2_batch", "orb_ratio_test", "orb_debug_eval_math", "bit_pattern_31_",
+    "orb_png_info", "orb_png_decode_gray8", "orb_imread_gray8", "orb_detect_and_compute_files", "orb_get_ingested_frame",
 ]
 
 _lib = None
@@ -94,6 +99,11 @@ def load_library():
     L.orb_ratio_test.restype = None
     L.orb_set_profiling.argtypes = [vp, i]
     L.orb_get_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 5), C.POINTER(C.c_int * 5)]
+    L.orb_png_info.argtypes = [vp, sz, C.POINTER(ImageInfo)]
+    L.orb_png_decode_gray8.argtypes = [vp, sz, vp, sz, i, i]
+    L.orb_imread_gray8.argtypes = [C.c_char_p, vp, sz, i, i, C.POINTER(i), C.POINTER(i)]
+    L.orb_detect_and_compute_files.argtypes = [vp, C.POINTER(C.c_char_p), i, i, i, i, vp, vp, vp, vp, i]
+    L.orb_get_ingested_frame.argtypes = [vp, i, vp, sz, C.POINTER(i), C.POINTER(i)]
     _lib = L
     return L
 
@@ -102,6 +112,37 @@ def default_params():
     p = Params()
     load_library().orb_default_params(C.byref(p))
     return p
+
+
+def _ck_global(rc):
+    if rc != 0:
+        raise OrbError(rc, load_library().orb_last_error(None).decode())
+
+
+def png_info(data):
+    """(width, height, bit_depth, channels) of an encoded PNG held in a bytes object."""
+    info = ImageInfo()
+    _ck_global(load_library().orb_png_info(data, len(data), C.byref(info)))
+    return info.width, info.height, info.bit_depth, info.channels
+
+
+def imdecode_gray8(data):
+    """== cv2.imdecode(data, cv2.IMREAD_GRAYSCALE) for the PNG layouts of include/orb_b200.h (host decode)."""
+    w, h, _, _ = png_info(data)
+    out = np.empty((h, w), np.uint8)
+    _ck_global(load_library().orb_png_decode_gray8(data, len(data), _p(out), out.strides[0], w, h))
+    return out
+
+
+def imread_gray8(path):
+    """== cv::imread(path, cv::IMREAD_GRAYSCALE), reference src/feature_matching.cpp:55 (host decode)."""
+    with open(path, "rb") as f:
+        head = f.read(64)
+    w, h, _, _ = png_info(head)
+    out = np.empty((h, w), np.uint8)
+    ww, hh = C.c_int(), C.c_int()
+    _ck_global(load_library().orb_imread_gray8(os.fsencode(path), _p(out), out.strides[0], w, h, C.byref(ww), C.byref(hh)))
+    return out
 
 
 def _img(a):
@@ -198,6 +239,25 @@ class Context:
         self._ck(self.lib.orb_detect_and_compute_batch(self.h, _p(frames), 0, F, W, H, frames.strides[1],
                                                        frames.strides[0], cap, _p(kps), _p(ang), _p(des), _p(n), 0))
         return kps, ang, des, n
+
+    def detect_and_compute_files(self, paths, cap=None, threads=0, decode_on_device=False, out=None):
+        """PNG files of one size -> (kps[F,cap], angles[F,cap], desc[F,cap,32], n[F]); decode overlaps the device work."""
+        F = len(paths)
+        cap = cap or self.max_kp
+        arr = (C.c_char_p * F)(*[os.fsencode(p) for p in paths])
+        if out is None:
+            out = (np.zeros((F, cap), KP), np.zeros((F, cap), np.float32), np.zeros((F, cap, 32), np.uint8),
+                   np.zeros(F, np.int32))
+        kps, ang, des, n = out
+        self._ck(self.lib.orb_detect_and_compute_files(self.h, arr, F, int(threads), int(bool(decode_on_device)), cap,
+                                                       _p(kps), _p(ang), _p(des), _p(n), 0))
+        return kps, ang, des, n
+
+    def get_ingested_frame(self, frame, w, h):
+        out = np.empty((h, w), np.uint8)
+        ww, hh = C.c_int(), C.c_int()
+        self._ck(self.lib.orb_get_ingested_frame(self.h, frame, _p(out), out.strides[0], C.byref(ww), C.byref(hh)))
+        return out[:hh.value, :ww.value]
 
     def detect_and_compute_batch_ptr(self, frames_ptr, frames_on_device, n_frames, w, h, pitch, frame_stride, cap,
                                      kps_ptr, ang_ptr, des_ptr, n_ptr, outputs_on_device):

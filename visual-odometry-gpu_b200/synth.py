@@ -46,3 +46,25 @@ def synth_frames(n, W=1241, H=376, start=0, pitch=None):
     for k in range(n):
         out[k, :, :W] = synth_frame(start + k, W, H)
     return out
+
+
+def write_png_gray8(path, img, level=6):
+    """Minimal 8-bit gray PNG writer for the ingest bench / tests (Sub filter on every row, like the KITTI files,
+    IDAT chunks of 8 KB like libpng writes them).  Test-data generator, not part of the product path."""
+    import struct
+    import zlib
+    a = np.ascontiguousarray(img, np.uint8)
+    H, W = a.shape
+    rows = np.empty((H, W + 1), np.uint8)
+    rows[:, 0] = 1
+    rows[:, 1] = a[:, 0]
+    rows[:, 2:] = a[:, 1:] - a[:, :-1]
+    z = zlib.compress(rows.tobytes(), level)
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data))
+    out = [b"\x89PNG\r\n\x1a\n", chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, 8, 0, 0, 0, 0))]
+    out += [chunk(b"IDAT", z[i:i + 8192]) for i in range(0, len(z), 8192)]
+    out.append(chunk(b"IEND", b""))
+    with open(path, "wb") as f:
+        f.write(b"".join(out))
