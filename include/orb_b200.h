@@ -174,6 +174,11 @@ int  orb_imread_gray8(const char* path, uint8_t* dst, size_t pitch, int cap_w, i
 int  orb_detect_and_compute_files(orb_ctx* ctx, const char* const* paths, int n_frames, int n_threads,
                                   int decode_on_device, int cap, orb_keypoint* kps, float* angles, orb_descriptor* desc,
                                   int* n_out, int outputs_on_device);
+/* test hook of the device inflate kernel: n raw deflate streams (RFC 1951, no zlib header) concatenated in `streams`
+ * (stream i = bytes [offsets[i], offsets[i+1])), inflated into out[out_offsets[i] .. out_offsets[i+1]) which must be
+ * their exact sizes; status[i] = 0 or 1 corrupt / 2 size mismatch / 3 truncated / 4 table overflow.  Host pointers. */
+int  orb_debug_inflate(orb_ctx* ctx, const uint8_t* streams, const uint32_t* offsets, int n, uint8_t* out,
+                       const uint32_t* out_offsets, int* status);
 /* the decoded frame `frame` of the last orb_detect_and_compute_files call (level 0 as the kernels saw it) */
 int  orb_get_ingested_frame(orb_ctx* ctx, int frame, uint8_t* dst, size_t dst_pitch, int* w, int* h);
 

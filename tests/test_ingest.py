@@ -202,16 +202,102 @@ def _write_frames(tmp_path, frames, **kw):
     return paths
 
 
+def _raw_deflate(data, level, strategy):
+    co = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+    return co.compress(data) + co.flush()
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("threads", [1, 0])
-def test_files_pipeline_equals_batch(tmp_path, threads):
+def test_device_inflate_against_zlib():
+    """k_inflate on raw deflate streams of every block type; the expected bytes are the inputs of Python's zlib."""
+    rng = np.random.default_rng(11)
+    datas, streams = [], []
+    for trial in range(160):
+        kind = trial % 8
+        n = int(rng.integers(0, 120000)) if trial % 16 else int(rng.integers(0, 40))
+        if kind == 0:
+            d = rng.integers(0, 256, n, dtype=np.uint8)
+        elif kind == 1:
+            d = rng.integers(0, 4, n, dtype=np.uint8)
+        elif kind == 2:
+            d = (np.arange(n) % 251).astype(np.uint8)
+        elif kind == 3:
+            d = np.zeros(n, np.uint8)
+        elif kind == 4:
+            d = np.repeat(rng.integers(0, 256, n // 50 + 1, dtype=np.uint8), 50)[:n]
+        elif kind == 5:
+            d = rng.normal(128, 6, n).clip(0, 255).astype(np.uint8)
+        elif kind == 6:   # far matches: a block repeated at distances up to 32 KiB
+            blk = rng.integers(0, 256, int(rng.integers(100, 33000)), dtype=np.uint8)
+            d = np.tile(blk, n // len(blk) + 2)[:n]
+        else:             # skewed alphabet: long Huffman codes (second-level tables)
+            d = np.minimum(rng.geometric(0.35, n), 255).astype(np.uint8)
+        level = int(rng.integers(0, 10))
+        strat = int(rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]))
+        datas.append(d.tobytes())
+        streams.append(_raw_deflate(datas[-1], level, strat))
+    p = orb.make_params(nfeatures=500, max_width=320, max_height=200, max_batch=4)
+    ctx = orb.Context(p)
+    try:
+        outs, st = ctx.debug_inflate(streams, [len(d) for d in datas])
+        assert not st.any(), st
+        for k, (o, d) in enumerate(zip(outs, datas)):
+            assert o == d, k
+        # wrong expected size, truncated and bit-flipped streams end with a status (or, for a flip that still decodes
+        # to the right size, with some output): they never hang
+        big = [k for k in range(len(datas)) if len(datas[k]) > 2000][:24]
+        bad_streams, sizes = [], []
+        for k in big:
+            s = bytearray(streams[k])
+            s[int(rng.integers(0, len(s)))] ^= 1 << int(rng.integers(0, 8))
+            bad_streams += [bytes(s), streams[k][:len(streams[k]) // 2], streams[k]]
+            sizes += [len(datas[k]), len(datas[k]), len(datas[k]) - 1]
+        outs, st = ctx.debug_inflate(bad_streams, sizes)
+        assert all(st[3 * j + 1] != 0 and st[3 * j + 2] != 0 for j in range(len(big))), st
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_device_decode_all_filter_types(tmp_path):
+    rng = np.random.default_rng(2)
+    frames = synth_frames(5, 320, 200)
+    frames[3] = rng.integers(0, 256, (200, 320), dtype=np.uint8)
+    frames[4, 50:120] = 9
+    paths = []
+    for i, f in enumerate(frames):
+        p = os.path.join(str(tmp_path), "%d.png" % i)
+        open(p, "wb").write(make_png(f, filters=[(4,), (3,), (2, 1), (0, 4, 3, 2, 1), (4, 4, 1, 3)][i], level=[6, 1, 9, 0, 6][i],
+                                     idat_split=[None, (8192,), (1, 77), (5000,), (3,)][i]))
+        paths.append(p)
+    p = orb.make_params(nfeatures=500, max_width=320, max_height=200, max_batch=8)
+    ctx = orb.Context(p)
+    try:
+        want = ctx.detect_and_compute_batch(frames)
+        got = ctx.detect_and_compute_files(paths, decode_on_device=True)
+        for f in range(5):
+            assert np.array_equal(ctx.get_ingested_frame(f, 320, 200), frames[f]), f
+        assert np.array_equal(got[3], want[3]) and np.array_equal(got[2], want[2]) and np.array_equal(got[0], want[0])
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("threads,device", [(1, False), (0, False), (0, True)])
+def test_files_pipeline_equals_batch(tmp_path, threads, device):
     frames = synth_frames(37, 1241, 376)
-    paths = _write_frames(tmp_path, frames, level=1)
+    paths = []
+    for i, f in enumerate(frames):
+        paths.append(os.path.join(str(tmp_path), "%06d.png" % i))
+        importlib.import_module("visual-odometry-gpu_b200.synth").write_png_gray8(paths[-1], f, level=[6, 1, 9][i % 3])
+    paths[5] = os.path.join(GOLDEN_DIR, "kitti_000000.png")          # a real KITTI file (Huffman-only stream)
+    import cv2
+    frames[5] = cv2.imread(paths[5], cv2.IMREAD_GRAYSCALE)
     p = orb.make_params(nfeatures=2000, max_width=1241, max_height=376, max_batch=64, chunk_frames=8)
     ctx = orb.Context(p)
     try:
         want = ctx.detect_and_compute_batch(frames)
-        got = ctx.detect_and_compute_files(paths, threads=threads)
+        got = ctx.detect_and_compute_files(paths, threads=threads, decode_on_device=device)
         for f in (0, 17, 36):
             assert np.array_equal(ctx.get_ingested_frame(f, 1241, 376), frames[f])
         assert np.array_equal(got[3], want[3])
@@ -245,7 +331,24 @@ def test_files_pipeline_errors(tmp_path):
         open(other, "wb").write(make_png(np.zeros((100, 100), np.uint8)))
         with pytest.raises(orb.OrbError):
             ctx.detect_and_compute_files(paths[:2] + [other])
+        # device decode: a stream that is corrupt inside valid chunk CRCs is reported by the kernel's status
+        z = bytearray(zlib.compress(filter_rows(frames[0], 1, (1,)), 6))
+        z[len(z) // 3] ^= 0x04
+        crafted = os.path.join(str(tmp_path), "crafted.png")
+        open(crafted, "wb").write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 320, 200, 8, 0, 0, 0, 0)) +
+                                  chunk(b"IDAT", bytes(z)) + chunk(b"IEND", b""))
+        with pytest.raises(orb.OrbError) as e:
+            ctx.detect_and_compute_files(paths[:2] + [crafted] + paths[2:], decode_on_device=True)
+        assert e.value.code == -7 and "crafted.png" in str(e.value)
+        rgb = os.path.join(str(tmp_path), "rgb.png")
+        open(rgb, "wb").write(make_png(np.zeros((200, 320, 3), np.uint8), color_type=2))
+        with pytest.raises(orb.OrbError) as e:
+            ctx.detect_and_compute_files(paths[:2] + [rgb], decode_on_device=True)
+        assert e.value.code == -7
         # the context stays usable
+        got = ctx.detect_and_compute_files(paths, decode_on_device=True)
+        want = ctx.detect_and_compute_batch(frames)
+        assert np.array_equal(got[3], want[3]) and np.array_equal(got[2], want[2])
         got = ctx.detect_and_compute_files(paths)
         want = ctx.detect_and_compute_batch(frames)
         assert np.array_equal(got[3], want[3]) and np.array_equal(got[2], want[2])

@@ -25,6 +25,7 @@
 #include "../../include/orb_b200.h"
 #include "../../include/orb_brief_pattern.h"
 #include "orb_kernels.cuh"
+#include "orb_ingest_kernels.cuh"
 #include "orb_plan.h"
 #include "orb_png.h"
 
@@ -72,6 +73,13 @@ struct orb_ctx {
   std::vector<cudaEvent_t> ev_in, ev_done;
   // frame ingest: pinned host area the decode threads fill (same layout as d_frames)
   uint8_t* h_ingest = nullptr; size_t h_ingest_bytes = 0;
+  // device decode: compressed streams (pinned + device), inflated scanlines, per-frame descriptors and status
+  uint8_t* h_comp = nullptr; uint8_t* d_comp = nullptr; uint8_t* d_raw = nullptr;
+  size_t comp_slot = 0, raw_slot = 0; int ingest_cap = 0;
+  orbk::InflateDesc* h_descs = nullptr; orbk::InflateDesc* d_descs = nullptr;
+  int* h_inf_status = nullptr; int* d_inf_status = nullptr; uint32_t* d_adler = nullptr;
+  static constexpr int N_INGEST = 4;
+  cudaStream_t s_ingest[N_INGEST] = {nullptr, nullptr, nullptr, nullptr};
   // optional per-kernel event timing
   bool profiling = false;
   struct Span { int stage; cudaEvent_t a, b; };
@@ -366,6 +374,15 @@ void orb_destroy(orb_ctx* ctx) {
   for (auto& sp : ctx->spans) { if (sp.a) cudaEventDestroy(sp.a); if (sp.b) cudaEventDestroy(sp.b); }
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   if (ctx->h_ingest) cudaFreeHost(ctx->h_ingest);
+  if (ctx->h_comp) cudaFreeHost(ctx->h_comp);
+  if (ctx->h_descs) cudaFreeHost(ctx->h_descs);
+  if (ctx->h_inf_status) cudaFreeHost(ctx->h_inf_status);
+  if (ctx->d_comp) cudaFree(ctx->d_comp);
+  if (ctx->d_raw) cudaFree(ctx->d_raw);
+  if (ctx->d_descs) cudaFree(ctx->d_descs);
+  if (ctx->d_inf_status) cudaFree(ctx->d_inf_status);
+  if (ctx->d_adler) cudaFree(ctx->d_adler);
+  for (cudaStream_t q : ctx->s_ingest) if (q) cudaStreamDestroy(q);
   for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->ev_done) cudaEventDestroy(e);
   if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
@@ -558,7 +575,9 @@ int orb_get_stage_ms(orb_ctx* ctx, float ms[5], int launches[5]) {
 // stage() runs on the calling thread just before the wave's kernels are queued, may block on host work, and queues on
 // ctx->s_h2d whatever brings frames [c0, c0 + nc) into ctx->d_frames.
 struct WaveSource {
-  virtual int stage(orb_ctx* ctx, int c0, int nc) = 0;
+  // queues the work for frames [c0, c0 + nc) of wave ci and records `ready` behind it (on whichever stream it used)
+  virtual int stage(orb_ctx* ctx, int ci, int c0, int nc, cudaEvent_t ready) = 0;
+  virtual int preferred_wave(const orb_ctx*) const { return 0; }      // 0 = the context's staged wave size
   virtual ~WaveSource() {}
 };
 
@@ -600,7 +619,8 @@ static int run_batch(orb_ctx* ctx, const uint8_t* frames, int frames_on_device, 
   // (chunk/8, chunk/4, chunk/2) so that the kernels start while most of the batch is still in flight over PCIe
   std::vector<int> wave_begin;
   {
-    const int wave = (direct && outputs_on_device) ? ctx->chunk : ctx->chunk_staged;
+    int wave = (direct && outputs_on_device) ? ctx->chunk : ctx->chunk_staged;
+    if (source && source->preferred_wave(ctx) > 0) wave = std::min(ctx->chunk, source->preferred_wave(ctx));
     int c0 = 0, ramp = (!direct && n_frames > wave) ? std::max(1, wave / 8) : wave;
     while (c0 < n_frames) {
       wave_begin.push_back(c0);
@@ -645,12 +665,11 @@ static int run_batch(orb_ctx* ctx, const uint8_t* frames, int frames_on_device, 
   for (int ci = 0; ci < nchunks; ci++) {
     const int c0 = wave_begin[ci], nc = wave_begin[ci + 1] - c0;
     if (source) {
-      if ((rc = source->stage(ctx, c0, nc))) {
+      if ((rc = source->stage(ctx, ci, c0, nc, ctx->ev_in[ci]))) {
         // frames of earlier waves are still in flight: drain before handing the buffers back
-        cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->s_d2h);
+        cudaDeviceSynchronize();
         return rc;
       }
-      CK(cudaEventRecord(ctx->ev_in[ci], ctx->s_h2d));
     }
     if (!direct) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[ci], 0));
     Bufs B;
@@ -989,7 +1008,7 @@ struct HostDecodeSource : WaveSource {
     done.assign(n, 0);
     for (int t = 0; t < n_threads; t++) pool.emplace_back([this] { work(); });
   }
-  int stage(orb_ctx* ctx, int c0, int nc) override {
+  int stage(orb_ctx* ctx, int, int c0, int nc, cudaEvent_t ready_ev) override {
     {
       std::unique_lock<std::mutex> lk(mu);
       cv.wait(lk, [&] {
@@ -999,9 +1018,131 @@ struct HostDecodeSource : WaveSource {
       if (err_code) return fail(ctx, err_code, "%s", err_msg.c_str());
     }
     CK(cudaMemcpyAsync(ctx->d_frames + (size_t)c0 * slot, area + (size_t)c0 * slot, slot * nc, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaEventRecord(ready_ev, ctx->s_h2d));
     return ORB_OK;
   }
   ~HostDecodeSource() override {
+    stop.store(true);
+    for (auto& t : pool) t.join();
+  }
+};
+
+const char* inflate_status_text(int st) {
+  switch (st) {
+    case orbk::INF_CORRUPT: return "corrupt deflate data";
+    case orbk::INF_SIZE: return "image data does not match the frame size";
+    case orbk::INF_TRUNCATED: return "truncated deflate data";
+    case orbk::INF_TABLE: return "Huffman table larger than the device decoder holds";
+    case orbk::INF_FILTER: return "unknown PNG filter type";
+    case orbk::INF_CHECKSUM: return "zlib: incorrect data check";
+    default: return "unknown decode error";
+  }
+}
+
+// (re)allocates the device-decode areas for n frames of w x h
+int ensure_device_decode(orb_ctx* ctx, int n, int w, int h) {
+  const size_t raw = ((size_t)(w + 1) * h + orbk::UNF_LEAD + 48 + 15) / 16 * 16;
+  const size_t comp = (raw + raw / 64 + 1024 + 511) / 512 * 512 + 512;
+  if (n <= ctx->ingest_cap && raw <= ctx->raw_slot && comp <= ctx->comp_slot) return ORB_OK;
+  if (ctx->h_comp) cudaFreeHost(ctx->h_comp);
+  if (ctx->h_descs) cudaFreeHost(ctx->h_descs);
+  if (ctx->h_inf_status) cudaFreeHost(ctx->h_inf_status);
+  cudaFree(ctx->d_comp); cudaFree(ctx->d_raw); cudaFree(ctx->d_descs); cudaFree(ctx->d_inf_status); cudaFree(ctx->d_adler);
+  ctx->d_adler = nullptr;
+  ctx->h_comp = nullptr; ctx->h_descs = nullptr; ctx->h_inf_status = nullptr;
+  ctx->d_comp = ctx->d_raw = nullptr; ctx->d_descs = nullptr; ctx->d_inf_status = nullptr;
+  ctx->ingest_cap = 0;
+  const int cap = std::max(n, ctx->p.max_batch);
+  CK(cudaHostAlloc((void**)&ctx->h_comp, comp * cap, cudaHostAllocDefault));
+  CK(cudaHostAlloc((void**)&ctx->h_descs, sizeof(orbk::InflateDesc) * cap, cudaHostAllocDefault));
+  CK(cudaHostAlloc((void**)&ctx->h_inf_status, sizeof(int) * cap, cudaHostAllocDefault));
+  CK(cudaMalloc((void**)&ctx->d_comp, comp * cap));
+  CK(cudaMalloc((void**)&ctx->d_raw, raw * cap));
+  CK(cudaMalloc((void**)&ctx->d_descs, sizeof(orbk::InflateDesc) * cap));
+  CK(cudaMalloc((void**)&ctx->d_inf_status, sizeof(int) * cap));
+  CK(cudaMalloc((void**)&ctx->d_adler, sizeof(uint32_t) * cap));
+  CK(cudaMemset(ctx->d_comp, 0, comp * cap));
+  for (cudaStream_t& q : ctx->s_ingest) if (!q) CK(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+  ctx->comp_slot = comp; ctx->raw_slot = raw; ctx->ingest_cap = cap;
+  return ORB_OK;
+}
+
+// Device-decode source: host threads only read the files, check the framing and lay the deflate streams out in the pinned
+// area; stage() uploads the compressed bytes of a wave and queues k_inflate + k_unfilter on the copy stream.
+struct DeviceDecodeSource : WaveSource {
+  const char* const* paths; int n, w, h;
+  orb_ctx* ctx;
+  std::vector<std::thread> pool;
+  std::atomic<int> next{0};
+  std::atomic<bool> stop{false};
+  std::mutex mu; std::condition_variable cv;
+  std::vector<uint8_t> done;
+  std::vector<uint32_t> bytes;
+  int ready = 0;
+  int err_code = 0; std::string err_msg;
+
+  void work() {
+    std::vector<uint8_t> file;
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= n || stop.load()) return;
+      std::string msg;
+      int code = 0;
+      if (!read_file(paths[i], &file, &msg)) code = ORB_E_IO;
+      else {
+        orbpng::Info I;
+        size_t nb = 0;
+        const char* e = orbpng::extract_deflate(file.data(), file.size(), &I, ctx->h_comp + (size_t)i * ctx->comp_slot,
+                                                ctx->comp_slot - 512, &nb);
+        if (!e && (I.width != w || I.height != h)) e = "png: image size differs from the expected frame size";
+        if (!e && (I.color_type != 0 || I.bit_depth != 8)) e = "png: the device decoder takes 8-bit gray files only";
+        if (e) { code = ORB_E_FORMAT; msg = std::string(paths[i]) + ": " + e; }
+        bytes[i] = (uint32_t)nb;
+      }
+      std::lock_guard<std::mutex> lk(mu);
+      if (code && !err_code) { err_code = code; err_msg = msg; stop.store(true); }
+      done[i] = 1;
+      cv.notify_all();
+    }
+  }
+  void start(int n_threads) {
+    done.assign(n, 0);
+    bytes.assign(n, 0);
+    for (int t = 0; t < n_threads; t++) pool.emplace_back([this] { work(); });
+  }
+  int preferred_wave(const orb_ctx* c) const override { return c->chunk; }   // a stream is one warp: many frames per launch
+  int stage(orb_ctx* c, int ci, int c0, int nc, cudaEvent_t ready_ev) override {
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] {
+        while (ready < n && done[ready]) ready++;
+        return err_code != 0 || ready >= c0 + nc;
+      });
+      if (err_code) return fail(c, err_code, "%s", err_msg.c_str());
+    }
+    orb_ctx* ctx = c;
+    // waves rotate over a few streams so that the inflate kernels of consecutive waves overlap (a deflate stream is
+    // serial: throughput is the number of streams in flight over the latency of one)
+    cudaStream_t q = ctx->s_ingest[ci % orb_ctx::N_INGEST];
+    if (ci < orb_ctx::N_INGEST) CK(cudaStreamWaitEvent(q, ctx->ev_start, 0));
+    const uint32_t out_bytes = (uint32_t)((size_t)(w + 1) * h);
+    for (int i = c0; i < c0 + nc; i++) {
+      const size_t up = ((size_t)bytes[i] + 4 + 16 + 15) / 16 * 16;    // stream + Adler trailer + zero pad
+      CK(cudaMemcpyAsync(ctx->d_comp + (size_t)i * ctx->comp_slot, ctx->h_comp + (size_t)i * ctx->comp_slot, up,
+                         cudaMemcpyHostToDevice, q));
+      ctx->h_descs[i] = orbk::InflateDesc{ctx->d_comp + (size_t)i * ctx->comp_slot, bytes[i], out_bytes, ctx->d_raw + (size_t)i * ctx->raw_slot + orbk::UNF_LEAD};
+    }
+    CK(cudaMemcpyAsync(ctx->d_descs + c0, ctx->h_descs + c0, sizeof(orbk::InflateDesc) * nc, cudaMemcpyHostToDevice, q));
+    orbk::k_inflate<<<nc, 32, 0, q>>>(ctx->d_descs + c0, ctx->d_inf_status + c0, ctx->d_adler + c0);
+    orbk::k_unfilter<<<(nc + orbk::UNF_WARPS - 1) / orbk::UNF_WARPS, orbk::UNF_WARPS * 32, 0, q>>>(
+        ctx->d_raw + (size_t)c0 * ctx->raw_slot, ctx->raw_slot, ctx->d_frames + (size_t)c0 * ctx->frames_slot_bytes,
+        ctx->frames_slot_bytes, ctx->frames_pitch, w, h, nc, ctx->d_inf_status + c0, ctx->d_adler + c0);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ready_ev, q));
+    ctx->launches += 2;
+    return ORB_OK;
+  }
+  ~DeviceDecodeSource() override {
     stop.store(true);
     for (auto& t : pool) t.join();
   }
@@ -1067,7 +1208,22 @@ int orb_detect_and_compute_files(orb_ctx* ctx, const char* const* paths, int n_f
   }
   int rc = get_plan(ctx, w, h);
   if (rc) return rc;
-  if (decode_on_device) return fail(ctx, ORB_E_INVALID, "device decode is not available in this build");
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  n_threads = std::min(n_threads, n_frames);
+  if (decode_on_device) {
+    if ((rc = ensure_device_decode(ctx, n_frames, w, h))) return rc;
+    DeviceDecodeSource src;
+    src.paths = paths; src.n = n_frames; src.w = w; src.h = h; src.ctx = ctx;
+    src.start(n_threads);
+    rc = run_batch(ctx, nullptr, 0, n_frames, w, h, 0, 0, cap, kps, angles, desc, n_out, outputs_on_device, &src);
+    if (rc) return rc;
+    // decode failures are per-frame flags on the device: the results of a failed frame are meaningless, report it
+    for (cudaStream_t q : ctx->s_ingest) CK(cudaStreamSynchronize(q));
+    CK(cudaMemcpy(ctx->h_inf_status, ctx->d_inf_status, sizeof(int) * n_frames, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n_frames; i++)
+      if (ctx->h_inf_status[i]) return fail(ctx, ORB_E_FORMAT, "%s: %s", paths[i], inflate_status_text(ctx->h_inf_status[i]));
+    return ORB_OK;
+  }
   const size_t need = ctx->frames_slot_bytes * (size_t)n_frames;
   if (need > ctx->h_ingest_bytes) {
     if (ctx->h_ingest) CK(cudaFreeHost(ctx->h_ingest));
@@ -1076,8 +1232,6 @@ int orb_detect_and_compute_files(orb_ctx* ctx, const char* const* paths, int n_f
     ctx->h_ingest_bytes = need;
     memset(ctx->h_ingest, 0, need);
   }
-  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
-  n_threads = std::min(n_threads, n_frames);
   HostDecodeSource src;
   src.paths = paths; src.n = n_frames; src.w = w; src.h = h;
   src.area = ctx->h_ingest; src.slot = ctx->frames_slot_bytes; src.pitch = ctx->frames_pitch;
@@ -1097,6 +1251,42 @@ int orb_get_ingested_frame(orb_ctx* ctx, int frame, uint8_t* dst, size_t dst_pit
   CK(cudaStreamSynchronize(ctx->stream));
   if (w) *w = W;
   if (h) *h = H;
+  return ORB_OK;
+}
+
+
+int orb_debug_inflate(orb_ctx* ctx, const uint8_t* streams, const uint32_t* offsets, int n, uint8_t* out,
+                      const uint32_t* out_offsets, int* status) {
+  if (!ctx || !streams || !offsets || !out || !out_offsets || !status || n < 1) return ORB_E_INVALID;
+  CK(cudaSetDevice(ctx->p.device));
+  // every stream in its own zero-padded, 512-byte aligned slot; outputs 16-byte aligned
+  std::vector<size_t> in_at(n + 1, 0), out_at(n + 1, 0);
+  for (int i = 0; i < n; i++) {
+    in_at[i + 1] = in_at[i] + ((size_t)(offsets[i + 1] - offsets[i]) + 16 + 511) / 512 * 512 + 512;
+    out_at[i + 1] = out_at[i] + ((size_t)(out_offsets[i + 1] - out_offsets[i]) + 32 + 15) / 16 * 16;
+  }
+  std::vector<uint8_t> packed(in_at[n], 0);
+  for (int i = 0; i < n; i++) memcpy(packed.data() + in_at[i], streams + offsets[i], offsets[i + 1] - offsets[i]);
+  uint8_t *d_in = nullptr, *d_out = nullptr;
+  orbk::InflateDesc* d_desc = nullptr;
+  int* d_st = nullptr;
+  CK(cudaMalloc((void**)&d_in, in_at[n]));
+  CK(cudaMalloc((void**)&d_out, out_at[n]));
+  CK(cudaMalloc((void**)&d_desc, sizeof(orbk::InflateDesc) * n));
+  CK(cudaMalloc((void**)&d_st, sizeof(int) * n));
+  std::vector<orbk::InflateDesc> descs(n);
+  for (int i = 0; i < n; i++)
+    descs[i] = orbk::InflateDesc{d_in + in_at[i], offsets[i + 1] - offsets[i], out_offsets[i + 1] - out_offsets[i], d_out + out_at[i]};
+  CK(cudaMemcpy(d_in, packed.data(), in_at[n], cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_desc, descs.data(), sizeof(orbk::InflateDesc) * n, cudaMemcpyHostToDevice));
+  CK(cudaMemset(d_out, 0xEE, out_at[n]));
+  orbk::k_inflate<<<n, 32, 0, ctx->stream>>>(d_desc, d_st, nullptr);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(status, d_st, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; i++)
+    CK(cudaMemcpy(out + out_offsets[i], d_out + out_at[i], out_offsets[i + 1] - out_offsets[i], cudaMemcpyDeviceToHost));
+  cudaFree(d_in); cudaFree(d_out); cudaFree(d_desc); cudaFree(d_st);
   return ORB_OK;
 }
 

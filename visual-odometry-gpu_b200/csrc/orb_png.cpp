@@ -465,7 +465,7 @@ struct Parsed {
 };
 
 // walks the chunk list; when `idat` is given, concatenates the IDAT payloads into it
-const char* parse(const uint8_t* f, size_t n, Parsed* P, uint8_t* idat, bool check_crc) {
+const char* parse(const uint8_t* f, size_t n, Parsed* P, uint8_t* idat, bool check_crc, size_t skip = 0, size_t idat_cap = ~(size_t)0) {
   if (n < 8 + 25 || memcmp(f, PNG_SIG, 8)) return "png: bad signature";
   size_t pos = 8;
   bool have_ihdr = false, have_iend = false;
@@ -484,7 +484,12 @@ const char* parse(const uint8_t* f, size_t n, Parsed* P, uint8_t* idat, bool che
       if (e) return e;
       have_ihdr = true;
     } else if (is_idat) {
-      if (idat) memcpy(idat + total, data, len);
+      if (idat) {
+        // the first `skip` bytes of the concatenated payload are dropped (zlib header for the device path)
+        const size_t drop = total < skip ? (skip - total < len ? skip - total : len) : 0;
+        if (total + len - skip > idat_cap && total + len > skip) return "png: compressed data larger than the frame slot";
+        if (len > drop) memcpy(idat + (total + drop - skip), data + drop, len - drop);
+      }
       total += len;
     } else if (is_iend) {
       have_iend = true;
@@ -509,6 +514,34 @@ const char* read_info(const uint8_t* file, size_t n, Info* info) {
   if (crc32(file + 12, 17) != be32(file + 29)) return "png: chunk CRC mismatch";
   Info& I = *info;
   return parse_ihdr(file + 16, &I);
+}
+
+const char* extract_deflate(const uint8_t* file, size_t n, Info* info, uint8_t* dst, size_t dst_cap, size_t* deflate_bytes) {
+  Parsed P;
+  const char* e = parse(file, n, &P, nullptr, false);
+  if (e) return e;
+  *info = P.info;
+  if (P.idat_total < 2 + 4 + 1) return "zlib: stream too short";
+  if (P.idat_total - 2 + 16 > dst_cap) return "png: compressed data larger than the frame slot";
+  // zlib header: find the first two payload bytes (they may be split over chunks, so walk again below with skip = 2)
+  uint8_t head[2];
+  {
+    size_t pos = 8, got = 0;
+    while (got < 2 && pos + 12 <= n) {
+      const uint32_t len = be32(file + pos);
+      if (!memcmp(file + pos + 4, "IDAT", 4))
+        for (uint32_t i = 0; i < len && got < 2; i++) head[got++] = file[pos + 8 + i];
+      pos += 12 + (size_t)len;
+    }
+  }
+  if ((head[0] & 15) != 8 || (head[0] >> 4) > 7) return "zlib: unknown compression method";
+  if (((head[0] << 8) | head[1]) % 31) return "zlib: header check failed";
+  if (head[1] & 0x20) return "zlib: preset dictionary";
+  if ((e = parse(file, n, &P, dst, true, 2, dst_cap))) return e;
+  const size_t body = P.idat_total - 2;
+  memset(dst + body, 0, 16);
+  *deflate_bytes = body - 4;      // without the Adler-32 trailer
+  return nullptr;
 }
 
 const char* decode_gray8(const uint8_t* file, size_t n, uint8_t* dst, size_t pitch, int expect_w, int expect_h, Scratch* scratch) {

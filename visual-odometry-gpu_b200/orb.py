@@ -50,7 +50,7 @@ EXPORTS = [
     "orb_synchronize", "orb_detect_and_compute", "orb_detect_and_compute_batch", "orb_get_level", "orb_level_size",
     "orb_level_quota", "orb_fast_detect", "orb_harris", "orb_orientations", "orb_brief", "orb_get_side_arrays",
     "orb_get_candidates", "orb_get_harris_weights", "orb_last_launch_count", "orb_set_profiling", "orb_get_stage_ms", "orb_match_knn2", "orb_match_knn2_batch", "orb_ratio_test", "orb_debug_eval_math", "bit_pattern_31_",
-    "orb_png_info", "orb_png_decode_gray8", "orb_imread_gray8", "orb_detect_and_compute_files", "orb_get_ingested_frame",
+    "orb_png_info", "orb_png_decode_gray8", "orb_imread_gray8", "orb_detect_and_compute_files", "orb_get_ingested_frame", "orb_debug_inflate",
 ]
 
 _lib = None
@@ -104,6 +104,7 @@ def load_library():
     L.orb_imread_gray8.argtypes = [C.c_char_p, vp, sz, i, i, C.POINTER(i), C.POINTER(i)]
     L.orb_detect_and_compute_files.argtypes = [vp, C.POINTER(C.c_char_p), i, i, i, i, vp, vp, vp, vp, i]
     L.orb_get_ingested_frame.argtypes = [vp, i, vp, sz, C.POINTER(i), C.POINTER(i)]
+    L.orb_debug_inflate.argtypes = [vp, vp, vp, i, vp, vp, vp]
     _lib = L
     return L
 
@@ -252,6 +253,19 @@ class Context:
         self._ck(self.lib.orb_detect_and_compute_files(self.h, arr, F, int(threads), int(bool(decode_on_device)), cap,
                                                        _p(kps), _p(ang), _p(des), _p(n), 0))
         return kps, ang, des, n
+
+    def debug_inflate(self, streams, out_sizes):
+        """Device inflate of raw deflate streams (test hook): returns (list of bytes, status array)."""
+        n = len(streams)
+        offs = np.zeros(n + 1, np.uint32)
+        offs[1:] = np.cumsum([len(s) for s in streams])
+        oofs = np.zeros(n + 1, np.uint32)
+        oofs[1:] = np.cumsum(out_sizes)
+        blob = np.frombuffer(b"".join(streams) + b"\0", np.uint8)
+        out = np.zeros(int(oofs[-1]) + 1, np.uint8)
+        st = np.zeros(n, np.int32)
+        self._ck(self.lib.orb_debug_inflate(self.h, _p(blob), _p(offs), n, _p(out), _p(oofs), _p(st)))
+        return [out[oofs[k]:oofs[k + 1]].tobytes() for k in range(n)], st
 
     def get_ingested_frame(self, frame, w, h):
         out = np.empty((h, w), np.uint8)
