@@ -69,7 +69,7 @@ struct orb_ctx {
   int launches = 0;
   // chunk pipeline: staging copies and result copies run on their own streams
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-  cudaEvent_t ev_start = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_chain = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_done;
   // frame ingest: pinned host area the decode threads fill (same layout as d_frames)
   uint8_t* h_ingest = nullptr; size_t h_ingest_bytes = 0;
@@ -386,6 +386,7 @@ void orb_destroy(orb_ctx* ctx) {
   for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->ev_done) cudaEventDestroy(e);
   if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+  if (ctx->ev_chain) cudaEventDestroy(ctx->ev_chain);
   if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
   if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -429,6 +430,7 @@ int orb_create(const orb_params* p, orb_ctx** out) {
     CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming));
     build_plan(ctx->p, p->max_width, p->max_height, p->nlevels, p->select_policy, -1, &ctx->max_plan);
     const OrbPlan& M = ctx->max_plan;
     // single-image stages reuse slot 0 with a 1-level plan whose kept list may hold ORB_SORT_CAP entries
@@ -1062,7 +1064,10 @@ int ensure_device_decode(orb_ctx* ctx, int n, int w, int h) {
   CK(cudaMalloc((void**)&ctx->d_inf_status, sizeof(int) * cap));
   CK(cudaMalloc((void**)&ctx->d_adler, sizeof(uint32_t) * cap));
   CK(cudaMemset(ctx->d_comp, 0, comp * cap));
-  for (cudaStream_t& q : ctx->s_ingest) if (!q) CK(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+  // the inflate kernels are latency chains (one busy lane per warp): give their blocks the first free slots
+  int prio_least = 0, prio_greatest = 0;
+  CK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  for (cudaStream_t& q : ctx->s_ingest) if (!q) CK(cudaStreamCreateWithPriority(&q, cudaStreamNonBlocking, prio_greatest));
   ctx->comp_slot = comp; ctx->raw_slot = raw; ctx->ingest_cap = cap;
   return ORB_OK;
 }
@@ -1110,36 +1115,68 @@ struct DeviceDecodeSource : WaveSource {
     bytes.assign(n, 0);
     for (int t = 0; t < n_threads; t++) pool.emplace_back([this] { work(); });
   }
-  int preferred_wave(const orb_ctx* c) const override { return c->chunk; }   // a stream is one warp: many frames per launch
-  int stage(orb_ctx* c, int ci, int c0, int nc, cudaEvent_t ready_ev) override {
-    {
-      std::unique_lock<std::mutex> lk(mu);
-      cv.wait(lk, [&] {
-        while (ready < n && done[ready]) ready++;
-        return err_code != 0 || ready >= c0 + nc;
-      });
-      if (err_code) return fail(c, err_code, "%s", err_msg.c_str());
-    }
-    orb_ctx* ctx = c;
-    // waves rotate over a few streams so that the inflate kernels of consecutive waves overlap (a deflate stream is
-    // serial: throughput is the number of streams in flight over the latency of one)
-    cudaStream_t q = ctx->s_ingest[ci % orb_ctx::N_INGEST];
-    if (ci < orb_ctx::N_INGEST) CK(cudaStreamWaitEvent(q, ctx->ev_start, 0));
+  // Inflate waves are independent of the ORB waves: a deflate stream is serial (one warp, ~15 ms per KITTI frame), so
+  // the decoder wants as many streams in flight as the host has read, while the ORB kernels want short waves that
+  // start early.  Inflate wave k covers frames [k * IW, (k + 1) * IW) and runs on ingest stream k % N_INGEST, so
+  // consecutive inflate waves overlap; an ORB wave waits for the inflate wave that holds its last frame.
+  static constexpr int IW = 256;
+  int preferred_wave(const orb_ctx* c) const override { return c->chunk; }   // frames are resident before the ORB waves start
+  int inflated = 0, inflate_waves = 0;
+  cudaStream_t last_q = nullptr;
+  int launch_inflate(orb_ctx* ctx, int f0, int nf) {
+    cudaStream_t q = ctx->s_ingest[inflate_waves % orb_ctx::N_INGEST];
+    if (inflate_waves < orb_ctx::N_INGEST) CK(cudaStreamWaitEvent(q, ctx->ev_start, 0));
     const uint32_t out_bytes = (uint32_t)((size_t)(w + 1) * h);
-    for (int i = c0; i < c0 + nc; i++) {
-      const size_t up = ((size_t)bytes[i] + 4 + 16 + 15) / 16 * 16;    // stream + Adler trailer + zero pad
-      CK(cudaMemcpyAsync(ctx->d_comp + (size_t)i * ctx->comp_slot, ctx->h_comp + (size_t)i * ctx->comp_slot, up,
-                         cudaMemcpyHostToDevice, q));
+    // one strided copy for the wave: every slot up to the longest stream in it (stream + Adler trailer + zero pad)
+    size_t up = 0;
+    for (int i = f0; i < f0 + nf; i++) up = std::max(up, ((size_t)bytes[i] + 4 + 16 + 15) / 16 * 16);
+    CK(cudaMemcpy2DAsync(ctx->d_comp + (size_t)f0 * ctx->comp_slot, ctx->comp_slot, ctx->h_comp + (size_t)f0 * ctx->comp_slot,
+                         ctx->comp_slot, up, nf, cudaMemcpyHostToDevice, q));
+    for (int i = f0; i < f0 + nf; i++) {
       ctx->h_descs[i] = orbk::InflateDesc{ctx->d_comp + (size_t)i * ctx->comp_slot, bytes[i], out_bytes, ctx->d_raw + (size_t)i * ctx->raw_slot + orbk::UNF_LEAD};
     }
-    CK(cudaMemcpyAsync(ctx->d_descs + c0, ctx->h_descs + c0, sizeof(orbk::InflateDesc) * nc, cudaMemcpyHostToDevice, q));
-    orbk::k_inflate<<<nc, 32, 0, q>>>(ctx->d_descs + c0, ctx->d_inf_status + c0, ctx->d_adler + c0);
-    orbk::k_unfilter<<<(nc + orbk::UNF_WARPS - 1) / orbk::UNF_WARPS, orbk::UNF_WARPS * 32, 0, q>>>(
-        ctx->d_raw + (size_t)c0 * ctx->raw_slot, ctx->raw_slot, ctx->d_frames + (size_t)c0 * ctx->frames_slot_bytes,
-        ctx->frames_slot_bytes, ctx->frames_pitch, w, h, nc, ctx->d_inf_status + c0, ctx->d_adler + c0);
+    CK(cudaMemcpyAsync(ctx->d_descs + f0, ctx->h_descs + f0, sizeof(orbk::InflateDesc) * nf, cudaMemcpyHostToDevice, q));
+    orbk::k_inflate<<<nf, 32, 0, q>>>(ctx->d_descs + f0, ctx->d_inf_status + f0, ctx->d_adler + f0);
+    orbk::k_unfilter<<<(nf + orbk::UNF_WARPS - 1) / orbk::UNF_WARPS, orbk::UNF_WARPS * 32, 0, q>>>(
+        ctx->d_raw + (size_t)f0 * ctx->raw_slot, ctx->raw_slot, ctx->d_frames + (size_t)f0 * ctx->frames_slot_bytes,
+        ctx->frames_slot_bytes, ctx->frames_pitch, w, h, nf, ctx->d_inf_status + f0, ctx->d_adler + f0);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(ready_ev, q));
     ctx->launches += 2;
+    inflate_waves++;
+    last_q = q;
+    return ORB_OK;
+  }
+  int stage(orb_ctx* ctx, int, int c0, int nc, cudaEvent_t ready_ev) override {
+    cudaStream_t also[8];
+    int n_also = 0;
+    // Measured on B200: ORB kernels and inflate kernels sharing the SMs slow each other far more than the overlap gains
+    // (126 ms vs 69 ms per 1024 KITTI frames), so every frame is inflated -- in waves that follow the host reads -- before
+    // the first ORB wave starts.  ORB_INGEST_SEPARATE=0 restores the interleaved schedule for experiments.
+    static const bool separate = !(getenv("ORB_INGEST_SEPARATE") && atoi(getenv("ORB_INGEST_SEPARATE")) == 0);
+    const int want = separate ? n : c0 + nc;
+    while (inflated < want) {
+      if (last_q && n_also < 8 && inflated > c0) also[n_also++] = last_q;     // this ORB wave spans several inflate waves
+      const int f0 = inflated, nf = std::min(IW, n - f0);
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] {
+          while (ready < n && done[ready]) ready++;
+          return err_code != 0 || ready >= f0 + nf;
+        });
+        if (err_code) return fail(ctx, err_code, "%s", err_msg.c_str());
+      }
+      const int rc = launch_inflate(ctx, f0, nf);
+      if (rc) return rc;
+      inflated = f0 + nf;
+    }
+    // frames of this ORB wave come from the inflate wave queued last at the latest (earlier ORB waves have waited for
+    // the earlier inflate waves, except for those first needed by this very wave)
+    for (int k = 0; k < n_also; k++) {
+      if (also[k] == last_q) continue;
+      CK(cudaEventRecord(ctx->ev_chain, also[k]));
+      CK(cudaStreamWaitEvent(last_q, ctx->ev_chain, 0));
+    }
+    CK(cudaEventRecord(ready_ev, last_q));
     return ORB_OK;
   }
   ~DeviceDecodeSource() override {

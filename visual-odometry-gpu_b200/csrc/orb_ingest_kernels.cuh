@@ -374,11 +374,17 @@ __global__ void __launch_bounds__(32) k_inflate(const InflateDesc* __restrict__ 
             uint32_t wnext = S.in[in_pos & (INF_IN_WORDS - 1)];      // next input word, loaded ahead of its use
             uint32_t seen = 0;
             do {
-              while (nbits <= 32) {          // at most twice (second time only when the buffer was empty)
+              if (nbits <= 32) {
                 bitbuf |= (uint64_t)wnext << nbits;
                 nbits += 32;
                 in_pos++;
                 wnext = S.in[in_pos & (INF_IN_WORDS - 1)];
+                if (nbits == 32) {           // the buffer was empty: one word is one bit short of three probes
+                  bitbuf |= (uint64_t)wnext << 32;
+                  nbits = 64;
+                  in_pos++;
+                  wnext = S.in[in_pos & (INF_IN_WORDS - 1)];
+                }
               }
 #pragma unroll
               for (int k = 0; k < 3; k++) {
