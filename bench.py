@@ -346,6 +346,37 @@ def main():
     sampler.stop()
     assert int(h_n.sum().item()) == n_kp, "host and device paths disagree"
 
+    # SURVEY 8(f) rank 4 (not part of the headline metric): pyramidal LK of the reference's feature_tracking loop on the KITTI
+    # fixture pair, from the ORB keypoints of the first frame; host call including both frame uploads and the result copy
+    lk = None
+    if rank == 0 and world == 1:
+        try:
+            import time
+            g = os.path.join(ROOT, "tests", "golden")
+            f0, f1 = V.imread_gray8(os.path.join(g, "kitti_000000.png")), V.imread_gray8(os.path.join(g, "kitti_000001.png"))
+            ctx_lk = V.Context(V.make_params(nfeatures=3000, max_width=f0.shape[1], max_height=f0.shape[0], max_batch=1, device=local_rank))
+            kp0 = ctx_lk.detect_and_compute(f0)[0]
+            pts = np.stack([kp0["x"], kp0["y"]], 1).astype(np.float32)
+            ctx_lk.lk_track(f0, f1, pts)
+            t0 = time.perf_counter()
+            for _ in range(10):
+                _, st_lk, _ = ctx_lk.lk_track(f0, f1, pts)
+            lk = {"ms_per_pair": (time.perf_counter() - t0) / 10 * 1e3, "points": int(len(pts)), "tracked": int(st_lk.sum()),
+                  "call": "win 21, 3 levels, 30 iterations, eps 0.01 (reference src/feature_tracking.cpp:174-180)"}
+            try:
+                import cv2
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    cv2.calcOpticalFlowPyrLK(f0, f1, pts.reshape(-1, 1, 2), None, winSize=(21, 21), maxLevel=3,
+                                             criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01), flags=0, minEigThreshold=0.001)
+                lk["cv2_ms_per_pair"] = (time.perf_counter() - t0) / 3 * 1e3
+                lk["cv2_threads"] = cv2.getNumThreads()
+            except ImportError:
+                pass
+            ctx_lk.close()
+        except Exception as e:      # the fixture pair is optional for the headline number
+            lk = {"error": str(e)}
+
     ingest = None
     if rank == 0 and world == 1 and not args.no_ingest:
         ingest = ingest_leg(V, ctx, host_pool[:, :, :W], idx, cap, (h_k, h_a, h_d, h_n), n_kp)
@@ -391,7 +422,7 @@ def main():
                    "cache_hygiene": "input batch %.0f MB > 126 MB L2; scratch arena reused per chunk" % (F * H * PITCH / 1e6),
                    "stage_names": names,
                    "stage_ms_per_step": [m / prof_steps for m in st_ms], "stage_share": stage_share,
-                   "match_knn2_ms_per_step": ms_match, "match_pairs_per_step": F - 1, "ingest_png": ingest,
+                   "match_knn2_ms_per_step": ms_match, "match_pairs_per_step": F - 1, "ingest_png": ingest, "lk_track": lk,
                    "pass_b_min_bytes_per_frame": b_min, "pass_hbm_gbs_per_gpu": pass_gbs, "pass_hbm_frac": pass_gbs / peak,
                    "peak_source": peak_src},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(F * H * PITCH) * world,

@@ -182,6 +182,21 @@ int  orb_debug_inflate(orb_ctx* ctx, const uint8_t* streams, const uint32_t* off
 /* the decoded frame `frame` of the last orb_detect_and_compute_files call (level 0 as the kernels saw it) */
 int  orb_get_ingested_frame(orb_ctx* ctx, int frame, uint8_t* dst, size_t dst_pitch, int* w, int* h);
 
+/* ---- pyramidal Lucas-Kanade tracker: the other front end of the reference's VO loop -------------
+ * == cv::calcOpticalFlowPyrLK(prev, next, prev_pts, next_pts, status, err, Size(win, win), max_level,
+ *                             TermCriteria(COUNT+EPS, max_iter, eps), 0, min_eig)
+ * as called at reference src/feature_tracking.cpp:174-180 with win 21, max_level 3, 30 iterations, eps 0.01, min_eig 0.001.
+ * Follows OpenCV 4.x lkpyramid.cpp (pyrDown pyramid, Scharr derivatives with a zero border, 14-bit fixed-point window
+ * samples, float normal equations, the same termination rules and L1 error).  Host pointers: 8-bit frames of w x h at
+ * `pitch`, prev_pts / next_pts [n][2] float (x, y), status [n], err [n] (may be NULL).  win in [3, 33]. */
+int  orb_lk_track(orb_ctx* ctx, const uint8_t* prev, const uint8_t* next, int w, int h, size_t pitch, const float* prev_pts,
+                  int n, int win, int max_level, int max_iter, double eps, float min_eig, float* next_pts, uint8_t* status,
+                  float* err);
+/* highest pyramid level index the tracker uses for this frame size (OpenCV stops before a level <= the window) */
+int  orb_lk_levels(int w, int h, int win, int max_level);
+/* pyramid level of the last orb_lk_track call (which: 0 = prev, 1 = next), packed rows; size returned in w, h */
+int  orb_lk_get_level(orb_ctx* ctx, int which, int level, uint8_t* dst, int* w, int* h);
+
 /* ---- side arrays of the LAST orb_detect_and_compute[_batch] call (testing / diagnostics) ----
  * level-space coordinates, level id and Harris response of output record i of `frame`
  * (the reference drops them, src/orb.cpp:94-102).  Any pointer may be NULL. */

@@ -430,3 +430,193 @@ int orc_detect_and_compute_batch(const uint8_t* frames, int n_frames, size_t fra
 }
 
 }  // extern "C"
+
+// =============================================================================================
+// Pyramidal Lucas-Kanade.  The reference calls
+//   cv::calcOpticalFlowPyrLK(img_1, img_2, points1, points2, status, err, Size(21,21), 3,
+//                            TermCriteria(COUNT+EPS, 30, 0.01), 0, 0.001)      (src/feature_tracking.cpp:174-180)
+// OpenCV is a third-party dependency that is absent from /root/reference, so this restates the published algorithm of
+// OpenCV 4.x modules/video/src/lkpyramid.cpp (scalar path): pyrDown pyramid (5x5 [1 4 6 4 1], REFLECT_101), Scharr
+// derivatives as int16 (zero outside the image: derivBorder = BORDER_CONSTANT), 14-bit fixed-point bilinear window samples
+// (intensity with 5 fractional bits), float normal equations, the iteration / termination rules, the L1 error.  Float sums
+// over the window are taken in a fixed order -- 32 interleaved partial sums (element i goes to partial i % 32) combined by
+// an xor-butterfly 16, 8, 4, 2, 1 -- which is the order the CUDA kernel uses, so that product and checker agree bit for bit;
+// OpenCV's own SIMD order differs in the last float bits, hence the tolerance when this checker is pinned against cv2.
+namespace {
+inline int lk_reflect101(int p, int n) {
+  if (n == 1) return 0;
+  while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
+  return p;
+}
+struct LkLevel { int w, h; std::vector<uint8_t> img; };
+inline int lk_px(const LkLevel& L, int x, int y) { return L.img[(size_t)lk_reflect101(y, L.h) * L.w + lk_reflect101(x, L.w)]; }
+// Scharr derivative of the level at (x, y): calcSharrDeriv with its REFLECT_101 rows / columns; 0 outside the image
+inline void lk_deriv(const LkLevel& L, int x, int y, int* dx, int* dy) {
+  if (x < 0 || x >= L.w || y < 0 || y >= L.h) { *dx = 0; *dy = 0; return; }
+  int t0[3], t1[3];
+  for (int k = -1; k <= 1; k++) {
+    const int a = lk_px(L, x + k, y - 1), b = lk_px(L, x + k, y), c = lk_px(L, x + k, y + 1);
+    t0[k + 1] = (a + c) * 3 + b * 10;
+    t1[k + 1] = c - a;
+  }
+  *dx = t0[2] - t0[0];
+  *dy = (t1[2] + t1[0]) * 3 + t1[1] * 10;
+}
+inline int lk_descale(int v, int n) { return (v + (1 << (n - 1))) >> n; }
+inline float lk_tree_sum(float* part) {
+  for (int d = 16; d; d >>= 1)
+    for (int i = 0; i < 32; i++) if (!(i & d)) { const float s = part[i] + part[i ^ d]; part[i] = s; part[i ^ d] = s; }
+  return part[0];
+}
+void lk_pyr_down(const LkLevel& S, LkLevel* D) {
+  D->w = (S.w + 1) / 2; D->h = (S.h + 1) / 2;
+  D->img.resize((size_t)D->w * D->h);
+  static const int k[5] = {1, 4, 6, 4, 1};
+  for (int y = 0; y < D->h; y++)
+    for (int x = 0; x < D->w; x++) {
+      int s = 0;
+      for (int j = 0; j < 5; j++) {
+        int r = 0;
+        for (int i = 0; i < 5; i++) r += k[i] * lk_px(S, 2 * x + i - 2, 2 * y + j - 2);
+        s += k[j] * r;
+      }
+      D->img[(size_t)y * D->w + x] = (uint8_t)((s + 128) >> 8);
+    }
+}
+}  // namespace
+
+int orc_lk_levels(int w, int h, int win, int max_level) {
+  int L = 0;
+  while (L < max_level) {
+    w = (w + 1) / 2; h = (h + 1) / 2;
+    if (w <= win || h <= win) break;
+    L++;
+  }
+  return L;   // highest level index actually used
+}
+
+void orc_lk_pyr_down(const uint8_t* src, int w, int h, size_t pitch, uint8_t* dst) {
+  LkLevel S{w, h, {}}, D;
+  S.img.resize((size_t)w * h);
+  for (int y = 0; y < h; y++) memcpy(&S.img[(size_t)y * w], src + (size_t)y * pitch, w);
+  lk_pyr_down(S, &D);
+  memcpy(dst, D.img.data(), D.img.size());
+}
+
+void orc_lk_track(const uint8_t* prev, const uint8_t* next, int w, int h, size_t pitch, const float* prev_pts, int n, int win,
+                  int max_level, int max_iter, double eps, float min_eig, float* next_pts, uint8_t* status, float* err) {
+  // TermCriteria handling of calcOpticalFlowPyrLK
+  max_iter = std::min(std::max(max_iter, 0), 100);
+  eps = std::min(std::max(eps, 0.), 10.);
+  eps *= eps;
+  const int top = orc_lk_levels(w, h, win, max_level);
+  std::vector<LkLevel> P(top + 1), N(top + 1);
+  P[0].w = N[0].w = w; P[0].h = N[0].h = h;
+  P[0].img.resize((size_t)w * h); N[0].img.resize((size_t)w * h);
+  for (int y = 0; y < h; y++) {
+    memcpy(&P[0].img[(size_t)y * w], prev + (size_t)y * pitch, w);
+    memcpy(&N[0].img[(size_t)y * w], next + (size_t)y * pitch, w);
+  }
+  for (int l = 1; l <= top; l++) { lk_pyr_down(P[l - 1], &P[l]); lk_pyr_down(N[l - 1], &N[l]); }
+  const int area = win * win;
+  std::vector<short> Iw(area), dIw(2 * area);
+  const float halfWin = (win - 1) * 0.5f;
+  const float FLT_SCALE = 1.f / (1 << 20);
+  for (int i = 0; i < n; i++) { status[i] = 1; if (err) err[i] = 0; }
+  for (int pt = 0; pt < n; pt++) {
+    float nx = 0, ny = 0;
+    for (int level = top; level >= 0; level--) {
+      const LkLevel& I = P[level];
+      const LkLevel& J = N[level];
+      const float sc = (float)(1. / (1 << level));
+      float px = prev_pts[2 * pt] * sc, py = prev_pts[2 * pt + 1] * sc;
+      if (level == top) { nx = px; ny = py; } else { nx = next_pts[2 * pt] * 2.f; ny = next_pts[2 * pt + 1] * 2.f; }
+      next_pts[2 * pt] = nx; next_pts[2 * pt + 1] = ny;
+      px -= halfWin; py -= halfWin;
+      const int ipx = (int)std::floor(px), ipy = (int)std::floor(py);
+      if (ipx < -win || ipx >= I.w || ipy < -win || ipy >= I.h) {
+        if (level == 0) { status[pt] = 0; if (err) err[pt] = 0; }
+        continue;
+      }
+      float a = px - ipx, b = py - ipy;
+      int iw00 = (int)std::nearbyint((1.f - a) * (1.f - b) * (1 << 14));
+      int iw01 = (int)std::nearbyint(a * (1.f - b) * (1 << 14));
+      int iw10 = (int)std::nearbyint((1.f - a) * b * (1 << 14));
+      int iw11 = (1 << 14) - iw00 - iw01 - iw10;
+      float p11[32] = {0}, p12[32] = {0}, p22[32] = {0};
+      for (int y = 0; y < win; y++)
+        for (int x = 0; x < win; x++) {
+          const int X = ipx + x, Y = ipy + y;
+          const int ival = lk_descale(lk_px(I, X, Y) * iw00 + lk_px(I, X + 1, Y) * iw01 + lk_px(I, X, Y + 1) * iw10 +
+                                      lk_px(I, X + 1, Y + 1) * iw11, 14 - 5);
+          int d00x, d00y, d01x, d01y, d10x, d10y, d11x, d11y;
+          lk_deriv(I, X, Y, &d00x, &d00y); lk_deriv(I, X + 1, Y, &d01x, &d01y);
+          lk_deriv(I, X, Y + 1, &d10x, &d10y); lk_deriv(I, X + 1, Y + 1, &d11x, &d11y);
+          const int ixval = lk_descale(d00x * iw00 + d01x * iw01 + d10x * iw10 + d11x * iw11, 14);
+          const int iyval = lk_descale(d00y * iw00 + d01y * iw01 + d10y * iw10 + d11y * iw11, 14);
+          const int e = y * win + x;
+          Iw[e] = (short)ival; dIw[2 * e] = (short)ixval; dIw[2 * e + 1] = (short)iyval;
+          p11[e & 31] += (float)(ixval * ixval); p12[e & 31] += (float)(ixval * iyval); p22[e & 31] += (float)(iyval * iyval);
+        }
+      const float A11 = lk_tree_sum(p11) * FLT_SCALE, A12 = lk_tree_sum(p12) * FLT_SCALE, A22 = lk_tree_sum(p22) * FLT_SCALE;
+      float D = A11 * A22 - A12 * A12;
+      const float minEig = (A22 + A11 - std::sqrt((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (2 * win * win);
+      if (minEig < min_eig || D < 1.1920928955078125e-07f) {   // FLT_EPSILON
+        if (level == 0) status[pt] = 0;
+        continue;
+      }
+      D = 1.f / D;
+      nx -= halfWin; ny -= halfWin;
+      float pdx = 0, pdy = 0;
+      for (int j = 0; j < max_iter; j++) {
+        const int inx = (int)std::floor(nx), iny = (int)std::floor(ny);
+        if (inx < -win || inx >= J.w || iny < -win || iny >= J.h) {
+          if (level == 0) status[pt] = 0;
+          break;
+        }
+        a = nx - inx; b = ny - iny;
+        iw00 = (int)std::nearbyint((1.f - a) * (1.f - b) * (1 << 14));
+        iw01 = (int)std::nearbyint(a * (1.f - b) * (1 << 14));
+        iw10 = (int)std::nearbyint((1.f - a) * b * (1 << 14));
+        iw11 = (1 << 14) - iw00 - iw01 - iw10;
+        float q1[32] = {0}, q2[32] = {0};
+        for (int y = 0; y < win; y++)
+          for (int x = 0; x < win; x++) {
+            const int X = inx + x, Y = iny + y, e = y * win + x;
+            const int diff = lk_descale(lk_px(J, X, Y) * iw00 + lk_px(J, X + 1, Y) * iw01 + lk_px(J, X, Y + 1) * iw10 +
+                                        lk_px(J, X + 1, Y + 1) * iw11, 14 - 5) - Iw[e];
+            q1[e & 31] += (float)(diff * dIw[2 * e]); q2[e & 31] += (float)(diff * dIw[2 * e + 1]);
+          }
+        const float b1 = lk_tree_sum(q1) * FLT_SCALE, b2 = lk_tree_sum(q2) * FLT_SCALE;
+        const float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
+        nx += dx; ny += dy;
+        next_pts[2 * pt] = nx + halfWin; next_pts[2 * pt + 1] = ny + halfWin;
+        if ((double)dx * dx + (double)dy * dy <= eps) break;
+        if (j > 0 && std::abs(dx + pdx) < 0.01 && std::abs(dy + pdy) < 0.01) {
+          next_pts[2 * pt] -= dx * 0.5f; next_pts[2 * pt + 1] -= dy * 0.5f;
+          break;
+        }
+        pdx = dx; pdy = dy;
+      }
+      if (status[pt] && err && level == 0) {
+        const float ex = next_pts[2 * pt] - halfWin, ey = next_pts[2 * pt + 1] - halfWin;
+        const int inx = (int)std::floor(ex), iny = (int)std::floor(ey);
+        if (inx < -win || inx >= J.w || iny < -win || iny >= J.h) { status[pt] = 0; continue; }
+        a = ex - inx; b = ey - iny;
+        iw00 = (int)std::nearbyint((1.f - a) * (1.f - b) * (1 << 14));
+        iw01 = (int)std::nearbyint(a * (1.f - b) * (1 << 14));
+        iw10 = (int)std::nearbyint((1.f - a) * b * (1 << 14));
+        iw11 = (1 << 14) - iw00 - iw01 - iw10;
+        float ev[32] = {0};
+        for (int y = 0; y < win; y++)
+          for (int x = 0; x < win; x++) {
+            const int X = inx + x, Y = iny + y, e = y * win + x;
+            const int diff = lk_descale(lk_px(J, X, Y) * iw00 + lk_px(J, X + 1, Y) * iw01 + lk_px(J, X, Y + 1) * iw10 +
+                                        lk_px(J, X + 1, Y + 1) * iw11, 14 - 5) - Iw[e];
+            ev[e & 31] += std::abs((float)diff);
+          }
+        err[pt] = lk_tree_sum(ev) * 1.f / (32 * win * win);
+      }
+    }
+  }
+}

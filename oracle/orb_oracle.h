@@ -81,6 +81,14 @@ int  orc_detect_and_compute_batch(const uint8_t* frames, int n_frames, size_t fr
 void orc_match_knn2(const orc_descriptor* query, int nq, const orc_descriptor* train, int nt, int32_t* out4, float ratio,
                     uint8_t* keep);
 
+/* pyramidal Lucas-Kanade == cv::calcOpticalFlowPyrLK(prev, next, prev_pts, next_pts, status, err, Size(win, win), max_level,
+ * TermCriteria(COUNT+EPS, max_iter, eps), 0, min_eig), the call of reference src/feature_tracking.cpp:174-180; OpenCV 4.x
+ * lkpyramid.cpp restated (scalar path, fixed summation order).  prev_pts / next_pts are [n][2] floats. */
+void orc_lk_track(const uint8_t* prev, const uint8_t* next, int w, int h, size_t pitch, const float* prev_pts, int n, int win,
+                  int max_level, int max_iter, double eps, float min_eig, float* next_pts, uint8_t* status, float* err);
+int  orc_lk_levels(int w, int h, int win, int max_level);
+void orc_lk_pyr_down(const uint8_t* src, int w, int h, size_t pitch, uint8_t* dst /* ((w+1)/2) x ((h+1)/2), packed */);
+
 /* helpers for property tests */
 long orc_lround_f(float v);                       /* std::lround(float)                   */
 float orc_atan2f(float y, float x);

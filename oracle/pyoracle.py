@@ -87,6 +87,10 @@ def lib():
         L.orc_brief.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.orc_brief_flags.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.orc_match_knn2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p]
+        L.orc_lk_track.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_double, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_lk_levels.argtypes = [C.c_int] * 4
+        L.orc_lk_pyr_down.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p]
         _lib = L
     return _lib
 
@@ -241,6 +245,28 @@ def match_knn2(query, train, ratio=0.8):
     keep = np.zeros(len(q), np.uint8)
     lib().orc_match_knn2(_ptr(q), len(q), _ptr(t), len(t), _ptr(out), ratio, _ptr(keep))
     return out, keep.astype(bool)
+
+
+def lk_track(prev, nxt, pts, win=21, max_level=3, max_iter=30, eps=0.01, min_eig=0.001):
+    """== cv2.calcOpticalFlowPyrLK(prev, nxt, pts, None, winSize=(win, win), maxLevel, criteria, 0, min_eig):
+    returns (next_pts [n,2] float32, status [n] uint8, err [n] float32)."""
+    prev, nxt = _img(prev), _img(nxt)
+    assert prev.shape == nxt.shape and prev.strides[0] == nxt.strides[0]
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+    out = np.zeros_like(pts)
+    st = np.zeros(len(pts), np.uint8)
+    er = np.zeros(len(pts), np.float32)
+    lib().orc_lk_track(_ptr(prev), _ptr(nxt), prev.shape[1], prev.shape[0], prev.strides[0], _ptr(pts), len(pts), win, max_level,
+                       max_iter, eps, min_eig, _ptr(out), _ptr(st), _ptr(er))
+    return out, st, er
+
+
+def lk_pyr_down(img):
+    img = _img(img)
+    h, w = img.shape
+    out = np.zeros(((h + 1) // 2, (w + 1) // 2), np.uint8)
+    lib().orc_lk_pyr_down(_ptr(img), w, h, img.strides[0], _ptr(out))
+    return out
 
 
 # ---------------------------------------------------------------- whole path

@@ -50,7 +50,7 @@ EXPORTS = [
     "orb_synchronize", "orb_detect_and_compute", "orb_detect_and_compute_batch", "orb_get_level", "orb_level_size",
     "orb_level_quota", "orb_fast_detect", "orb_harris", "orb_orientations", "orb_brief", "orb_get_side_arrays",
     "orb_get_candidates", "orb_get_harris_weights", "orb_last_launch_count", "orb_set_profiling", "orb_get_stage_ms", "orb_match_knn2", "orb_match_knn2_batch", "orb_ratio_test", "orb_debug_eval_math", "bit_pattern_31_",
-    "orb_png_info", "orb_png_decode_gray8", "orb_imread_gray8", "orb_detect_and_compute_files", "orb_get_ingested_frame", "orb_debug_inflate",
+    "orb_png_info", "orb_png_decode_gray8", "orb_imread_gray8", "orb_detect_and_compute_files", "orb_get_ingested_frame", "orb_debug_inflate", "orb_lk_track", "orb_lk_levels", "orb_lk_get_level",
 ]
 
 _lib = None
@@ -105,6 +105,9 @@ def load_library():
     L.orb_detect_and_compute_files.argtypes = [vp, C.POINTER(C.c_char_p), i, i, i, i, vp, vp, vp, vp, i]
     L.orb_get_ingested_frame.argtypes = [vp, i, vp, sz, C.POINTER(i), C.POINTER(i)]
     L.orb_debug_inflate.argtypes = [vp, vp, vp, i, vp, vp, vp]
+    L.orb_lk_track.argtypes = [vp, vp, vp, i, i, sz, vp, i, i, i, i, C.c_double, C.c_float, vp, vp, vp]
+    L.orb_lk_levels.argtypes = [i, i, i, i]
+    L.orb_lk_get_level.argtypes = [vp, i, i, vp, C.POINTER(i), C.POINTER(i)]
     _lib = L
     return L
 
@@ -253,6 +256,29 @@ class Context:
         self._ck(self.lib.orb_detect_and_compute_files(self.h, arr, F, int(threads), int(bool(decode_on_device)), cap,
                                                        _p(kps), _p(ang), _p(des), _p(n), 0))
         return kps, ang, des, n
+
+    def lk_track(self, prev, nxt, pts, win=21, max_level=3, max_iter=30, eps=0.01, min_eig=0.001):
+        """== cv2.calcOpticalFlowPyrLK(prev, nxt, pts, None, winSize=(win, win), maxLevel=max_level,
+        criteria=(COUNT+EPS, max_iter, eps), flags=0, minEigThreshold=min_eig) (reference src/feature_tracking.cpp:174-180):
+        returns (next_pts [n,2] float32, status [n] uint8, err [n] float32)."""
+        prev, nxt = _img(prev), _img(nxt)
+        if prev.shape != nxt.shape or prev.strides[0] != nxt.strides[0]:
+            nxt = np.ascontiguousarray(nxt)
+            prev = np.ascontiguousarray(prev)
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        out = np.zeros_like(pts)
+        st = np.zeros(len(pts), np.uint8)
+        er = np.zeros(len(pts), np.float32)
+        self._ck(self.lib.orb_lk_track(self.h, _p(prev), _p(nxt), prev.shape[1], prev.shape[0], prev.strides[0], _p(pts),
+                                       len(pts), win, max_level, max_iter, eps, min_eig, _p(out), _p(st), _p(er)))
+        return out, st, er
+
+    def lk_get_level(self, which, level, w0, h0):
+        """Pyramid level of the last lk_track call (which: 0 prev, 1 next); w0, h0 = frame size of that call."""
+        w, h = C.c_int(), C.c_int()
+        tmp = np.zeros(w0 * h0, np.uint8)
+        self._ck(self.lib.orb_lk_get_level(self.h, which, level, _p(tmp), C.byref(w), C.byref(h)))
+        return tmp[:w.value * h.value].reshape(h.value, w.value).copy()
 
     def debug_inflate(self, streams, out_sizes):
         """Device inflate of raw deflate streams (test hook): returns (list of bytes, status array)."""
