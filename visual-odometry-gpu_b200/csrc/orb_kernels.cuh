@@ -287,13 +287,19 @@ constexpr int B_SP = 160;              // pixel tile pitch (bytes); pixel x sits
 constexpr int B_PH = B_TH + 8;         // rows y0-4 .. y0+B_TH+3
 constexpr int B_SCP = 136;             // score pitch (u16); pixel x sits at column x - x0 + 4
 constexpr int B_SH = B_TH + 2;         // rows y0-1 .. y0+B_TH
-constexpr int B_LIST = 4096;           // pretest passers kept in the list; denser tiles take the dense fallback
+#ifndef ORB_B_LIST
+#define ORB_B_LIST 2816
+#endif
+#ifndef ORB_B_MINB
+#define ORB_B_MINB 6
+#endif
+constexpr int B_LIST = ORB_B_LIST;     // pretest passers kept in the list; denser tiles take the dense fallback
 constexpr int B_SURV = 1024;
 constexpr int B_PIX_BYTES = B_PH * B_SP, B_SCORE_BYTES = B_SH * B_SCP * 2;
 constexpr int B_LIST_BYTES = B_LIST * 2;
-constexpr int B_SMEM = B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES + B_SURV * 2 + 16 + B_TW * 4;   // 40.1 KB -> 5 CTAs / SM
+constexpr int B_SMEM = B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES + B_SURV * 2 + 16 + B_TW * 4;   // 37.7 KB and 40 registers -> 6 CTAs / SM
 
-__global__ void __launch_bounds__(B_THREADS) k_fast(const OrbPlan P, const Bufs B) {
+__global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P, const Bufs B) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint8_t* s_pix = smem;
   uint16_t* s_score = (uint16_t*)(smem + B_PIX_BYTES);
