@@ -934,7 +934,8 @@ __global__ void __launch_bounds__(K3_WARPS * 32, ORB_K3_MINB) k_describe(const O
     if (widx >= total) break;
     int l = 0, x, y;
     if (J.mode == 0) {
-      while (l + 1 < P.nlevels && widx >= s_pref[l + 1]) l++;
+      // level of output slot widx: the number of level starts (levels 1..) at or below it
+      l = __popc(__ballot_sync(0xffffffffu, lane + 1 < P.nlevels && widx >= s_pref[min(lane + 1, ORB_MAX_LEVELS)]));
       const uint32_t xy = B.kept_xy[(size_t)f * P.kept_per_frame + P.lv[l].kept_ofs + (widx - s_pref[l])];
       x = xy & 0xffff; y = xy >> 16;
     } else {
