@@ -152,7 +152,7 @@ def ingest_leg(V, ctx, pool_frames, idx, cap, outs, n_kp_expected):
         files = []
         for i in range(len(pool_frames)):
             files.append(os.path.join(d, "%06d.png" % i))
-            V.synth.write_png_gray8(files[-1], pool_frames[i])
+            V.synth.write_png_gray8(files[-1], pool_frames[i], huffman_only=True)     # like the KITTI files: no LZ77 matches
         paths = [files[i] for i in idx]
         png_bytes = float(np.mean([os.path.getsize(f) for f in files]))
         out = tuple(t.numpy() for t in outs)
@@ -165,7 +165,7 @@ def ingest_leg(V, ctx, pool_frames, idx, cap, outs, n_kp_expected):
         dt = (time.perf_counter() - t0) / reps
         assert int(out[3].sum()) == n_kp_expected, "file path and batch path disagree"
         res = {"host_decode_frames_per_s": len(paths) / dt, "frames": len(paths), "host_threads": threads,
-               "png_bytes_per_frame": png_bytes}
+               "png_bytes_per_frame": png_bytes, "png_encoding": "8-bit gray, Sub filter, Huffman-only deflate (as KITTI odometry files)"}
         # the same files with inflate + unfilter on the device (the host only reads, checks CRCs and uploads compressed bytes)
         ctx.detect_and_compute_files(paths, cap=cap, threads=threads, decode_on_device=True, out=out)
         t0 = time.perf_counter()
@@ -222,10 +222,13 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="frames per kernel wave (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ingest", action="store_true", help="skip the PNG-file ingest leg (SURVEY 8(f)-3)")
+    ap.add_argument("--hot-only", action="store_true", help="only the ORB step: no cpu_baseline, matcher, tracker or ingest legs (ncu runs)")
     ap.add_argument("--shape", default=None, help="WxH of the synthetic frames (default 1241x376 = the headline workload)")
     ap.add_argument("--levels", type=int, default=None)
     ap.add_argument("--nfeatures", type=int, default=None)
     args = ap.parse_args()
+    if args.hot_only:
+        args.no_cpu = args.no_ingest = True
     global W, H, LEVELS, NFEAT, PITCH, SUM_P, P0
     if args.shape:
         W, H = (int(v) for v in args.shape.lower().split("x"))
@@ -336,7 +339,7 @@ def main():
     # descriptors still resident on the device
     d_m = torch.zeros(F - 1, cap, 4, dtype=torch.int32, device=dev) if F > 1 else None
     ms_match = None
-    if d_m is not None:
+    if d_m is not None and not args.hot_only:
         def step_match():
             ctx.match_knn2_batch_ptr(d_d.data_ptr(), d_n.data_ptr(), F, cap, d_m.data_ptr())
         ms_match = timed(step_match, 2, 1) / 2
@@ -349,7 +352,7 @@ def main():
     # SURVEY 8(f) rank 4 (not part of the headline metric): pyramidal LK of the reference's feature_tracking loop on the KITTI
     # fixture pair, from the ORB keypoints of the first frame; host call including both frame uploads and the result copy
     lk = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.hot_only:
         try:
             import time
             g = os.path.join(ROOT, "tests", "golden")

@@ -8,7 +8,7 @@ python -m pytest tests -m gpu -q 2>&1 | tail -8 > $OUT/tests_$TAG.log; tail -3 $
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_$TAG.err; cat $OUT/bench_ref_$TAG.json
 python bench.py --steps 10 --warmup 3 > $OUT/bench_$TAG.json 2>> $OUT/bench_$TAG.err; cat $OUT/bench_$TAG.json; tail -5 $OUT/bench_$TAG.err
-SMALL="python bench.py --steps 2 --warmup 3 --frames 128 --no-cpu"
+SMALL="python bench.py --steps 2 --warmup 3 --frames 128 --hot-only"
 $SMALL > $OUT/plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv $SMALL > $OUT/ncu_list_$TAG.log 2>&1
 echo "ncu list rc=$?"

@@ -27,13 +27,18 @@ try:
             files.append(os.path.join(d, "%06d.png" % i))
             V.synth.write_png_gray8(files[-1], pool[i])
     paths = [files[i % len(files)] for i in range(F)]
+    import torch
+    KP = V.KP
+    outp = (torch.zeros(F, 2000, 2, dtype=torch.int32).pin_memory().numpy().view(KP).reshape(F, 2000),
+            torch.zeros(F, 2000, dtype=torch.float32).pin_memory().numpy(),
+            torch.zeros(F, 2000, 32, dtype=torch.uint8).pin_memory().numpy(), torch.zeros(F, dtype=torch.int32).pin_memory().numpy())
     for chunk in chunks:
         ctx = V.Context(V.make_params(nfeatures=2000, max_width=1241, max_height=376, max_batch=F, chunk_frames=chunk, max_keypoints=2000))
         res = {}
         for dev in (False, True):
-            ctx.detect_and_compute_files(paths, cap=2000, decode_on_device=dev)
+            ctx.detect_and_compute_files(paths, cap=2000, decode_on_device=dev, out=outp)
             t0 = time.perf_counter()
-            out = ctx.detect_and_compute_files(paths, cap=2000, decode_on_device=dev)
+            out = ctx.detect_and_compute_files(paths, cap=2000, decode_on_device=dev, out=outp)
             res[dev] = F / (time.perf_counter() - t0)
         print("frames %d kind %s chunk %d: host decode %.0f fps, device decode %.0f fps, kp %d" % (F, kind, chunk, res[False], res[True], int(out[3].sum())), flush=True)
         ctx.close()

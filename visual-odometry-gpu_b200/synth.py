@@ -48,9 +48,10 @@ def synth_frames(n, W=1241, H=376, start=0, pitch=None):
     return out
 
 
-def write_png_gray8(path, img, level=6):
+def write_png_gray8(path, img, level=6, huffman_only=False):
     """Minimal 8-bit gray PNG writer for the ingest bench / tests (Sub filter on every row, like the KITTI files,
-    IDAT chunks of 8 KB like libpng writes them).  Test-data generator, not part of the product path."""
+    IDAT chunks of 8 KB like libpng writes them; huffman_only=True gives match-free deflate streams, which is what the
+    KITTI odometry files contain).  Test-data generator, not part of the product path."""
     import struct
     import zlib
     a = np.ascontiguousarray(img, np.uint8)
@@ -59,7 +60,11 @@ def write_png_gray8(path, img, level=6):
     rows[:, 0] = 1
     rows[:, 1] = a[:, 0]
     rows[:, 2:] = a[:, 1:] - a[:, :-1]
-    z = zlib.compress(rows.tobytes(), level)
+    if huffman_only:
+        co = zlib.compressobj(level, zlib.DEFLATED, 15, 8, zlib.Z_HUFFMAN_ONLY)
+        z = co.compress(rows.tobytes()) + co.flush()
+    else:
+        z = zlib.compress(rows.tobytes(), level)
 
     def chunk(tag, data):
         return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data))
