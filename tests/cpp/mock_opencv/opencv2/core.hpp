@@ -23,6 +23,14 @@ template <typename T> using Ptr = std::shared_ptr<T>;
 template <typename T, typename... A> Ptr<T> makePtr(A&&... a) { return std::make_shared<T>(std::forward<A>(a)...); }
 
 struct Point2f { float x = 0, y = 0; Point2f() {} Point2f(float x_, float y_) : x(x_), y(y_) {} };
+struct Size { int width = 0, height = 0; Size() {} Size(int w, int h) : width(w), height(h) {} };
+struct TermCriteria {
+  enum Type { COUNT = 1, MAX_ITER = COUNT, EPS = 2 };
+  int type = 0, maxCount = 0; double epsilon = 0;
+  TermCriteria() {}
+  TermCriteria(int t, int c, double e) : type(t), maxCount(c), epsilon(e) {}
+};
+enum ImreadModes { IMREAD_GRAYSCALE = 0, IMREAD_COLOR = 1 };
 
 class KeyPoint {
  public:

@@ -98,3 +98,39 @@ def test_feature2d_adapter_matches_oracle(tmp_path, V, O, kitti0):
     assert np.allclose(kp[:, 3], deg, atol=1e-4) and (kp[:, 3] >= 0).all() and (kp[:, 3] < 360).all()
     size = np.float32(31) * np.float32(1.2) ** ref["level_id"].astype(np.float32)
     assert np.allclose(kp[:, 2], size, rtol=1e-6)
+
+
+def _build_frontend(tmp_path, V):
+    exe = str(tmp_path / "frontend_test")
+    libdir = os.path.dirname(V.lib_path())
+    cmd = ["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "tests", "cpp", "mock_opencv"), "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "cpp", "frontend_test.cpp"), "-o", exe, "-L" + libdir, "-lorb_b200", "-Wl,-rpath," + libdir]
+    env = {k: v for k, v in os.environ.items() if k not in ("CXX", "CC")}
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    assert r.returncode == 0, r.stdout
+    return exe
+
+
+def test_vo_frontend_compiles_against_mock_opencv(tmp_path, V):
+    """SURVEY 8(f) ranks 3, 4: orb_b200::imread / orb_b200::calcOpticalFlowPyrLK (include/orb_vo_frontend.hpp)."""
+    V.load_library()
+    _build_frontend(tmp_path, V)
+
+
+@pytest.mark.gpu
+def test_vo_frontend_matches_oracle(tmp_path, V, O, kitti0, kitti1):
+    V.load_library()
+    exe = _build_frontend(tmp_path, V)
+    g = os.path.join(ROOT, "tests", "golden")
+    ys, xs = np.mgrid[20:360:17, 20:1220:23]
+    pts = np.stack([xs.ravel(), ys.ravel()], 1).astype(np.float32) + np.float32(0.25)
+    pts.tofile(tmp_path / "pts.f32")
+    out = str(tmp_path / "out")
+    r = subprocess.run([exe, os.path.join(g, "kitti_000000.png"), os.path.join(g, "kitti_000001.png"), str(tmp_path / "pts.f32"), out],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "FRONTEND_OK 1241 x 376" in r.stdout, r.stdout
+    assert np.array_equal(np.fromfile(out + ".img", np.uint8).reshape(376, 1241), kitti0)      # orb_b200::imread == cv2.imread
+    n2, st2, er2 = O.lk_track(kitti0, kitti1, pts, win=21, max_level=3, max_iter=30, eps=0.01, min_eig=0.001)
+    assert np.array_equal(np.fromfile(out + ".st", np.uint8), st2)
+    assert np.array_equal(np.fromfile(out + ".pts", np.uint32), n2.view(np.uint32).ravel())
+    assert np.array_equal(np.fromfile(out + ".err", np.uint32), er2.view(np.uint32))
