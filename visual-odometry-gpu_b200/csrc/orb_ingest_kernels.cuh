@@ -203,6 +203,80 @@ __device__ __forceinline__ int inf_build_table(InflateShared& S, int first, int 
   return 0;
 }
 
+// ---- literal runs with all 32 lanes -----------------------------------------------------------
+// A Huffman stream is serial only until decoders that start at wrong bit positions fall into step with the true symbol
+// grid, which prefix codes do after a few symbols.  A round cuts the next 32 x INF_SEG bits into 32 segments; lane i decodes
+// the symbols that START inside segment i.  Pass 1 starts every lane at its segment boundary (a guess); after that lane i
+// restarts from the position where lane i-1 ended until no start changes any more -- lane 0 starts at the true position, so
+// the fixed point is the true decode (two or three passes in practice).  Counts are prefix-summed and a last pass writes
+// the bytes.  A lane stops at the first entry that is not a literal; the serial code takes over at the first such position.
+#ifndef ORB_INF_SEG
+#define ORB_INF_SEG 256
+#endif
+constexpr int INF_SEG = ORB_INF_SEG;    // bits per lane and round
+constexpr int INF_SEG_CAP = 220;        // bytes per lane and round: 32 lanes fit the free part of the window whatever the code lengths
+constexpr int INF_PAR_MIN = 192;        // a round that yields fewer bytes (match-heavy data) pauses the parallel rounds
+constexpr int INF_PAR_PAUSE = 8;
+
+#ifndef ORB_INF_VOTE
+#define ORB_INF_VOTE 4
+#endif
+constexpr int INF_STEPS_PER_VOTE = ORB_INF_VOTE;   // probes between two checks of "is any lane still inside its segment"
+#ifndef ORB_INF_COUNT_PAIRS
+#define ORB_INF_COUNT_PAIRS 1
+#endif
+// All 32 lanes call this together (lanes with run = false only keep the loop company): the loop is uniform and the body
+// is predicated rather than branched, because a divergent body costs every lane the sum of all paths.
+// Every pass steps by table probes (one or two literals; a second literal that starts in the next segment is left to the
+// next lane).  Stepping the counting passes one symbol at a time would let two decoders fall into step on ANY common symbol
+// boundary instead of only on common probe boundaries, but measured slower (10.7 vs 8.2 ms per KITTI frame): the extra
+// probes cost more than the extra fix-up passes.
+template <bool WRITE>
+__device__ __forceinline__ void inf_decode_segment(InflateShared& S, uint32_t start, uint32_t seg_end, uint32_t out_at, bool run,
+                                                   uint32_t* end, uint32_t* cnt, bool* stop) {
+  constexpr bool PAIRS = WRITE || ORB_INF_COUNT_PAIRS;
+  uint32_t pos = start, count = 0;
+  bool st = false;
+  bool active = run && pos < seg_end;
+  uint32_t wi = pos >> 5;
+  uint64_t bb = (uint64_t)(S.in[wi & (INF_IN_WORDS - 1)] >> (pos & 31));
+  int nb = 32 - (int)(pos & 31);
+  wi++;
+  uint32_t w = S.in[wi & (INF_IN_WORDS - 1)];            // next input word, fetched one step ahead of its use
+  while (__any_sync(0xffffffffu, active)) {
+#pragma unroll
+    for (int rep = 0; rep < INF_STEPS_PER_VOTE; rep++) {
+      if (nb <= 32) { bb |= (uint64_t)w << nb; nb += 32; wi++; }
+      w = S.in[wi & (INF_IN_WORDS - 1)];
+      uint32_t e = S.lit[(uint32_t)bb & ((1u << INF_LIT_ROOT) - 1)];
+      if (active && (e & 0x80u) && ((e >> 12) & 7) == IK_LINK) {
+        // a long code may still be a literal: fold it into a single-literal entry of root + sub bits
+        const uint32_t e2 = S.lit[((e >> 16) & 0xfff) + ((uint32_t)(bb >> INF_LIT_ROOT) & ((1u << (e >> 28)) - 1))];
+        if (!(e2 & 0x80u)) {
+          const uint32_t cbt = INF_LIT_ROOT + (e2 & 15);
+          e = (e2 & 0x00ff0000u) | (cbt << 12) | (1u << 4) | cbt;
+        }
+      }
+      const bool flagged = (e & 0x80u) != 0;
+      const int l1 = (e >> 12) & 15;
+      int cb = e & 15, n = (e >> 4) & 3;
+      if (!PAIRS || (n == 2 && pos + l1 >= seg_end)) { n = min(n, 1); cb = l1; }
+      const bool take = active && !flagged;
+      st = st || (active && flagged);
+      if (!take) { cb = 0; n = 0; }
+      if (WRITE && take) {
+        S.ring[(out_at + count) & (INF_RING - 1)] = (uint8_t)(e >> 16);
+        if (n == 2) S.ring[(out_at + count + 1) & (INF_RING - 1)] = (uint8_t)(e >> 24);
+      }
+      count += n; pos += cb;
+      bb >>= cb; nb -= cb;
+      if (take && count >= INF_SEG_CAP) st = true;      // (degenerate 1-bit codes) ends the round like a non-literal
+      active = take && pos < seg_end && count < INF_SEG_CAP;
+    }
+  }
+  *end = pos; *cnt = count; *stop = st;
+}
+
 __global__ void __launch_bounds__(32) k_inflate(const InflateDesc* __restrict__ descs, int* __restrict__ status,
                                                 uint32_t* __restrict__ trailer /* may be null: the 4 bytes after the stream */) {
   __shared__ InflateShared S;
@@ -214,11 +288,15 @@ __global__ void __launch_bounds__(32) k_inflate(const InflateDesc* __restrict__ 
   // warp-uniform state
   uint32_t in_loaded = 0;      // words of the stream that are in the input ring
   uint32_t flushed = 0;        // bytes of the output that are in global memory (multiple of 16)
+  uint32_t bitpos = 0;         // lane 0's position in the stream, in bits (broadcast after every serial section)
+  int huff = 0;                // lane 0 is inside a Huffman block whose tables are built
+  int pause = 0;               // rounds to go before the next parallel literal round is tried
   // lane-0 state
   uint64_t bitbuf = 0;
   int nbits = 0;
   uint32_t in_pos = 0, out_pos = 0;
   int stored_left = 0, last = 0;
+  int saw_match = 0;
   uint32_t consumed = 0;
   bool in_block = false;
   int st = INF_OK;
@@ -231,14 +309,69 @@ __global__ void __launch_bounds__(32) k_inflate(const InflateDesc* __restrict__ 
       for (uint32_t p = flushed + lane * 16; p < target; p += 512)
         *reinterpret_cast<uint4*>(D.out + p) = *reinterpret_cast<const uint4*>(S.ring + (p & (INF_RING - 1)));
       flushed = max(flushed, target);
-      while (in_loaded < in_words && in_loaded - in_pos <= INF_IN_WORDS - 128) {
+      // (lane 0 may still hold the two words before in_pos in its bit buffer, and a parallel round re-reads them)
+      while (in_loaded < in_words && in_loaded - in_pos <= INF_IN_WORDS - 128 - 4) {
         const uint4 v = __ldg(in4 + (in_loaded >> 2) + lane);
         *reinterpret_cast<uint4*>(&S.in[(in_loaded + lane * 4) & (INF_IN_WORDS - 1)]) = v;
         in_loaded += 128;
       }
       __syncwarp();
     }
+    // ---- parallel literal round ----
+    bool par = false;
+    uint32_t par_total = 0;
+    if (huff && pause == 0 && (uint64_t)bitpos + 32 * INF_SEG + 96 <= (uint64_t)in_loaded * 32 &&
+        INF_RING - INF_MARGIN - (out_pos - flushed) >= 32 * (INF_SEG_CAP + 2) && out_pos <= D.out_bytes) {
+      par = true;
+      const uint32_t base = bitpos;
+      uint32_t start = base + lane * INF_SEG;
+      const uint32_t seg_end = base + (lane + 1) * INF_SEG;
+      uint32_t end, cnt;
+      bool stop;
+      inf_decode_segment<false>(S, start, seg_end, 0, true, &end, &cnt, &stop);
+      for (int iter = 0; iter < 40; iter++) {
+        const unsigned stopmask = __ballot_sync(0xffffffffu, stop);
+        const int first = stopmask ? __ffs(stopmask) - 1 : 32;
+        const uint32_t prev_end = __shfl_up_sync(0xffffffffu, end, 1);
+        const uint32_t ns = lane == 0 ? base : prev_end;
+        const bool changed = lane <= first && ns != start;      // lanes behind the first stop do not matter
+        if (!__any_sync(0xffffffffu, changed)) break;
+        uint32_t e1, c1;
+        bool s1;
+        inf_decode_segment<false>(S, changed ? ns : start, seg_end, 0, changed, &e1, &c1, &s1);
+        if (changed) { start = ns; end = e1; cnt = c1; stop = s1; }
+      }
+      const unsigned stopmask = __ballot_sync(0xffffffffu, stop);
+      const int first = stopmask ? __ffs(stopmask) - 1 : 32;
+      const bool alive = lane <= first;
+      uint32_t incl = alive ? cnt : 0;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      {
+        uint32_t e2, c2;
+        bool s2;
+        inf_decode_segment<true>(S, start, seg_end, out_pos + incl - cnt, alive, &e2, &c2, &s2);
+      }
+      bitpos = __shfl_sync(0xffffffffu, end, min(first, 31));
+      out_pos += total;
+      par_total = total;
+      __syncwarp();
+      if (lane == 0) {
+        // the serial reader continues at the new position
+        in_pos = bitpos >> 5;
+        bitbuf = (uint64_t)(S.in[in_pos & (INF_IN_WORDS - 1)] >> (bitpos & 31));
+        nbits = 32 - (int)(bitpos & 31);
+        in_pos++;
+      }
+    } else if (pause > 0) {
+      pause--;
+    }
     int why = GO_ON;
+    saw_match = 0;
     if (lane == 0) {
       const bool in_done = in_loaded >= in_words;
 #define INF_REFILL()                                                             \
@@ -361,7 +494,11 @@ __global__ void __launch_bounds__(32) k_inflate(const InflateDesc* __restrict__ 
         }
         // ---- Huffman block: the serial walk ----
         INF_REFILL();
-        {
+        if (par) {
+          // literals belong to the next parallel round: only lengths, links and end-of-block are handled here
+          const uint32_t e0 = S.lit[(uint32_t)bitbuf & ((1u << INF_LIT_ROOT) - 1)];
+          if (!(e0 & 0x80u)) break;
+        } else {
           // Literal run.  No bookkeeping inside: a probe emits at most 2 bytes and takes at most INF_LIT_ROOT bits, so
           // the window room and the input words at hand bound the number of probes up front; a probe that meets a
           // length / end-of-block / link entry reads zeros in the fields used here and does nothing, and the run ends
@@ -446,6 +583,7 @@ __global__ void __launch_bounds__(32) k_inflate(const InflateDesc* __restrict__ 
         }
         const uint32_t distance = (d >> 16) + INF_TAKE((d >> 8) & 15);
         if (distance > out_pos) { st = INF_CORRUPT; why = DONE; break; }
+        saw_match = 1;
         uint32_t src = out_pos - distance;
         if (distance < INF_NEAR) {
           // source still in the window
@@ -480,6 +618,10 @@ __global__ void __launch_bounds__(32) k_inflate(const InflateDesc* __restrict__ 
     why = __shfl_sync(0xffffffffu, why, 0);
     out_pos = __shfl_sync(0xffffffffu, out_pos, 0);
     in_pos = __shfl_sync(0xffffffffu, in_pos, 0);
+    bitpos = __shfl_sync(0xffffffffu, in_pos * 32u - (uint32_t)nbits, 0);
+    huff = __shfl_sync(0xffffffffu, (int)(in_block && stored_left < 0), 0);
+    // short literal runs between matches do not pay for a parallel round: go serial for a while
+    if (par && par_total < INF_PAR_MIN && __shfl_sync(0xffffffffu, saw_match, 0)) pause = INF_PAR_PAUSE;
     __syncwarp();
     if (why == BUILD) {
       const int hlit = S.codes[318], hdist = S.codes[319];
