@@ -57,7 +57,7 @@ def main():
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     summary = {"tag": tag, "source": os.path.basename(rep), "kernels": {}}
     md = ["# ncu summary `%s`" % tag, "",
-          "`ncu --set full --clock-control none --import-source on` on `python bench.py --steps 2 --warmup 3 --frames 128 --no-cpu`"
+          "`ncu --set full --clock-control none --import-source on` on `python bench.py --steps 2 --warmup 3 --frames 128 --hot-only`"
           " (1 B200, one wave of 128 frames per launch). Times are per launch in microseconds, bytes per launch.", ""]
     if os.path.exists(rep):
         ks = read_rep(rep)

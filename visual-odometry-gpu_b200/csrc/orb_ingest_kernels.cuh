@@ -2,11 +2,12 @@
 // GPU, so that a frame crosses PCIe compressed and the host only reads files and checks chunk CRCs.  Replaces what
 // cv::imread(path, IMREAD_GRAYSCALE) does inside libpng/zlib (reference src/feature_matching.cpp:55,59).
 //
-//   k_inflate  : one warp per deflate stream (= one frame).  A deflate stream is serial, so the unit of parallelism is the
-//                stream: lane 0 walks the Huffman codes with a shared-memory lookup table that yields up to two literals per
-//                probe; the other lanes do everything that is not serial -- coalesced 16-byte refills of the input ring,
-//                16-byte flushes of the output window, and the per-block table construction (code assignment by
-//                match_any ranks, replicated fills, the two-literal augmentation pass).
+//   k_inflate  : one warp per deflate stream (= one frame).  Literal runs are decoded by all 32 lanes (self-synchronising
+//                segments, see inf_decode_segment); lengths / distances / block headers are walked by lane 0 with a
+//                shared-memory lookup table that yields up to two literals per probe; the other lanes do everything else
+//                that is not serial -- coalesced 16-byte refills of the input ring, 16-byte flushes of the output window,
+//                and the per-block table construction (code assignment by match_any ranks, replicated fills, the
+//                two-literal augmentation pass).
 //   k_unfilter : one warp per frame, lane = scanline, lanes skewed by one pixel so that left / up / up-left of the PNG
 //                predictors (Sub, Up, Average, Paeth) are a register, a shuffle from the lane above, and the previous
 //                shuffle.  Writes level 0 in the staging layout the ORB kernels read.
