@@ -13,9 +13,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "orb_internal.h"
+
 namespace orbk {
 
-constexpr int LK_MAX_LEVELS = 8;
+// LK_MAX_LEVELS (8) is defined in orb_internal.h: the context keeps the level layout of the last call
 constexpr int LK_MAX_WIN = 33;
 constexpr int LK_WARPS = 4;
 
