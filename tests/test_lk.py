@@ -128,3 +128,29 @@ def test_tracker_shapes_and_noise(O):
             ctx.lk_track(a, b, pts, win=35)
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_vo_front_end_chain_is_consistent():
+    """The pieces either side of the detector, chained the way the reference's two VO loops chain them: PNG files ->
+    (device decode) -> ORB -> Hamming 2-NN + ratio test (feature_matching.cpp) against FAST/ORB points followed by LK
+    (feature_tracking.cpp).  The two estimates of where a keypoint of frame 0 went in frame 1 must agree."""
+    paths = [os.path.join(GOLDEN, "kitti_000000.png"), os.path.join(GOLDEN, "kitti_000001.png")]
+    ctx = orb.Context(orb.make_params(nfeatures=2000, max_width=1241, max_height=376, max_batch=2))
+    try:
+        kps, ang, des, n = ctx.detect_and_compute_files(paths, decode_on_device=True)
+        a, b = ctx.get_ingested_frame(0, 1241, 376), ctx.get_ingested_frame(1, 1241, 376)
+        k0, k1 = kps[0][:n[0]], kps[1][:n[1]]
+        m = ctx.match_knn2(des[0][:n[0]], des[1][:n[1]])
+        keep = ctx.ratio_test(m, 0.8)
+        assert keep.sum() > 300
+        p0 = np.stack([k0["x"], k0["y"]], 1).astype(np.float32)
+        p1m = np.stack([k1["x"][m["idx1"]], k1["y"][m["idx1"]]], 1).astype(np.float32)
+        p1t, st, err = ctx.lk_track(a, b, p0, **CRIT)
+        both = keep & (st == 1) & (err < 15)
+        assert both.sum() > 200
+        d = np.abs(p1m[both] - p1t[both]).max(1)
+        # keypoints are integer pixels on pyramid levels (coordinates scaled by up to 1.2^7): a few pixels of slack
+        assert np.median(d) < 1.5 and (d < 4).mean() > 0.8, (np.median(d), (d < 4).mean())
+    finally:
+        ctx.close()
