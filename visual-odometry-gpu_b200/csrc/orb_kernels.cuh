@@ -558,9 +558,12 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
 // candidates of a frame.  Replaces HarrisScore() (ref src/cuda/HarrisScore.cu:42-89, call site src/orb.cpp:65): the
 // reference blurs three full-frame product images to read them at <= 2N points; here the 9x9 neighbourhood of each
 // candidate is read from the level (L2-resident, just written) and the response goes into the high word of its key.
+#ifndef ORB_C_MINB
+#define ORB_C_MINB 8
+#endif
 constexpr int C_THREADS = 128;
 
-__global__ void __launch_bounds__(C_THREADS, 8) k_harris(const OrbPlan P, const Bufs B) {
+__global__ void __launch_bounds__(C_THREADS, ORB_C_MINB) k_harris(const OrbPlan P, const Bufs B) {
   const int f = blockIdx.y;
   const int* cc = B.cand_count + (size_t)f * B.zero_stride;
   int total = 0;
