@@ -169,8 +169,8 @@ int  orb_imread_gray8(const char* path, uint8_t* dst, size_t pitch, int cap_w, i
  * the files straight into the context's pinned staging area while earlier waves of frames are copied and processed
  * on the device; outputs as orb_detect_and_compute_batch.  A frame that fails to load aborts the call with
  * ORB_E_IO / ORB_E_FORMAT and names the file in orb_last_error.
- * decode_on_device = 1 moves inflate + unfilter to the GPU for 8-bit gray files (the host only reads the files and
- * uploads the compressed bytes); files of other layouts make the call fail with ORB_E_FORMAT. */
+ * decode_on_device = 1 moves inflate, unfilter and the checksum tests to the GPU for 8-bit gray files (the host only
+ * reads the files and uploads the compressed bytes); files of other layouts make the call fail with ORB_E_FORMAT. */
 int  orb_detect_and_compute_files(orb_ctx* ctx, const char* const* paths, int n_frames, int n_threads,
                                   int decode_on_device, int cap, orb_keypoint* kps, float* angles, orb_descriptor* desc,
                                   int* n_out, int outputs_on_device);

@@ -340,6 +340,20 @@ def test_files_pipeline_errors(tmp_path):
         with pytest.raises(orb.OrbError) as e:
             ctx.detect_and_compute_files(paths[:2] + [crafted] + paths[2:], decode_on_device=True)
         assert e.value.code == -7 and "crafted.png" in str(e.value)
+        # ... and a damaged file is caught by the chunk CRCs, which the device checks (k_png_crc): a flipped data byte and a
+        # flipped byte of the stored CRC itself both fail, like they do in libpng
+        with pytest.raises(orb.OrbError) as e:
+            ctx.detect_and_compute_files(paths[:2] + [bad], decode_on_device=True)
+        assert e.value.code == -7 and "bad.png" in str(e.value) and "CRC" in str(e.value)
+        data = bytearray(open(paths[3], "rb").read())
+        at = data.rindex(b"IEND") - 8          # last byte of the last IDAT chunk's CRC field
+        data[at] ^= 0x01
+        crcflip = os.path.join(str(tmp_path), "crcflip.png")
+        open(crcflip, "wb").write(bytes(data))
+        for dev in (False, True):
+            with pytest.raises(orb.OrbError) as e:
+                ctx.detect_and_compute_files([crcflip] + paths[:2], decode_on_device=dev)
+            assert e.value.code == -7 and "CRC" in str(e.value)
         rgb = os.path.join(str(tmp_path), "rgb.png")
         open(rgb, "wb").write(make_png(np.zeros((200, 320, 3), np.uint8), color_type=2))
         with pytest.raises(orb.OrbError) as e:

@@ -316,6 +316,10 @@ void orb_destroy(orb_ctx* ctx) {
   if (ctx->d_descs) cudaFree(ctx->d_descs);
   if (ctx->d_inf_status) cudaFree(ctx->d_inf_status);
   if (ctx->d_adler) cudaFree(ctx->d_adler);
+  if (ctx->h_crc) cudaFreeHost(ctx->h_crc);
+  if (ctx->h_crc_n) cudaFreeHost(ctx->h_crc_n);
+  if (ctx->d_crc) cudaFree(ctx->d_crc);
+  if (ctx->d_crc_n) cudaFree(ctx->d_crc_n);
   for (cudaStream_t q : ctx->s_ingest) if (q) cudaStreamDestroy(q);
   for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->ev_done) cudaEventDestroy(e);

@@ -105,6 +105,7 @@ const char* inflate_status_text(int st) {
     case orbk::INF_TABLE: return "Huffman table larger than the device decoder holds";
     case orbk::INF_FILTER: return "unknown PNG filter type";
     case orbk::INF_CHECKSUM: return "zlib: incorrect data check";
+    case orbk::INF_CRC: return "png: chunk CRC mismatch";
     default: return "unknown decode error";
   }
 }
@@ -119,6 +120,10 @@ int ensure_device_decode(orb_ctx* ctx, int n, int w, int h) {
   if (ctx->h_inf_status) cudaFreeHost(ctx->h_inf_status);
   cudaFree(ctx->d_comp); cudaFree(ctx->d_raw); cudaFree(ctx->d_descs); cudaFree(ctx->d_inf_status); cudaFree(ctx->d_adler);
   ctx->d_adler = nullptr;
+  if (ctx->h_crc) cudaFreeHost(ctx->h_crc);
+  if (ctx->h_crc_n) cudaFreeHost(ctx->h_crc_n);
+  cudaFree(ctx->d_crc); cudaFree(ctx->d_crc_n);
+  ctx->h_crc = ctx->d_crc = nullptr; ctx->h_crc_n = ctx->d_crc_n = nullptr;
   ctx->h_comp = nullptr; ctx->h_descs = nullptr; ctx->h_inf_status = nullptr;
   ctx->d_comp = ctx->d_raw = nullptr; ctx->d_descs = nullptr; ctx->d_inf_status = nullptr;
   ctx->ingest_cap = 0;
@@ -131,6 +136,10 @@ int ensure_device_decode(orb_ctx* ctx, int n, int w, int h) {
   CK(cudaMalloc((void**)&ctx->d_descs, sizeof(orbk::InflateDesc) * cap));
   CK(cudaMalloc((void**)&ctx->d_inf_status, sizeof(int) * cap));
   CK(cudaMalloc((void**)&ctx->d_adler, sizeof(uint32_t) * cap));
+  CK(cudaHostAlloc((void**)&ctx->h_crc, sizeof(uint32_t) * 3 * orbk::PNG_CRC_CAP * cap, cudaHostAllocDefault));
+  CK(cudaHostAlloc((void**)&ctx->h_crc_n, sizeof(int) * cap, cudaHostAllocDefault));
+  CK(cudaMalloc((void**)&ctx->d_crc, sizeof(uint32_t) * 3 * orbk::PNG_CRC_CAP * cap));
+  CK(cudaMalloc((void**)&ctx->d_crc_n, sizeof(int) * cap));
   CK(cudaMemset(ctx->d_comp, 0, comp * cap));
   // the inflate kernels are latency chains (one busy lane per warp): give their blocks the first free slots
   int prio_least = 0, prio_greatest = 0;
@@ -165,8 +174,15 @@ struct DeviceDecodeSource : WaveSource {
       else {
         orbpng::Info I;
         size_t nb = 0;
-        const char* e = orbpng::extract_deflate(file.data(), file.size(), &I, ctx->h_comp + (size_t)i * ctx->comp_slot,
-                                                ctx->comp_slot - 512, &nb);
+        // the payload goes to slot + 14: the zlib header ends at + 16, where the (aligned) deflate data starts; the chunk
+        // checksums are listed for k_png_crc instead of being computed here (0.23 ms per frame on one core)
+        static_assert(sizeof(orbpng::ChunkCrc) == 12, "three words per chunk descriptor");
+        int ncrc = 0;
+        const char* e = orbpng::extract_deflate(file.data(), file.size(), &I, ctx->h_comp + (size_t)i * ctx->comp_slot + orbk::PNG_PAYLOAD_OFS,
+                                                ctx->comp_slot - 512 - orbk::PNG_PAYLOAD_OFS, &nb,
+                                                reinterpret_cast<orbpng::ChunkCrc*>(ctx->h_crc + (size_t)i * 3 * orbk::PNG_CRC_CAP),
+                                                orbk::PNG_CRC_CAP, &ncrc);
+        ctx->h_crc_n[i] = ncrc;
         if (!e && (I.width != w || I.height != h)) e = "png: image size differs from the expected frame size";
         if (!e && (I.color_type != 0 || I.bit_depth != 8)) e = "png: the device decoder takes 8-bit gray files only";
         if (e) { code = ORB_E_FORMAT; msg = std::string(paths[i]) + ": " + e; }
@@ -197,19 +213,24 @@ struct DeviceDecodeSource : WaveSource {
     const uint32_t out_bytes = (uint32_t)((size_t)(w + 1) * h);
     // one strided copy for the wave: every slot up to the longest stream in it (stream + Adler trailer + zero pad)
     size_t up = 0;
-    for (int i = f0; i < f0 + nf; i++) up = std::max(up, ((size_t)bytes[i] + 4 + 16 + 15) / 16 * 16);
+    for (int i = f0; i < f0 + nf; i++) up = std::max(up, ((size_t)bytes[i] + 16 + 4 + 16 + 15) / 16 * 16);
     CK(cudaMemcpy2DAsync(ctx->d_comp + (size_t)f0 * ctx->comp_slot, ctx->comp_slot, ctx->h_comp + (size_t)f0 * ctx->comp_slot,
                          ctx->comp_slot, up, nf, cudaMemcpyHostToDevice, q));
     for (int i = f0; i < f0 + nf; i++) {
-      ctx->h_descs[i] = orbk::InflateDesc{ctx->d_comp + (size_t)i * ctx->comp_slot, bytes[i], out_bytes, ctx->d_raw + (size_t)i * ctx->raw_slot + orbk::UNF_LEAD};
+      ctx->h_descs[i] = orbk::InflateDesc{ctx->d_comp + (size_t)i * ctx->comp_slot + 16, bytes[i], out_bytes, ctx->d_raw + (size_t)i * ctx->raw_slot + orbk::UNF_LEAD};
     }
     CK(cudaMemcpyAsync(ctx->d_descs + f0, ctx->h_descs + f0, sizeof(orbk::InflateDesc) * nf, cudaMemcpyHostToDevice, q));
     orbk::k_inflate<<<nf, 32, 0, q>>>(ctx->d_descs + f0, ctx->d_inf_status + f0, ctx->d_adler + f0);
     orbk::k_unfilter<<<(nf + orbk::UNF_WARPS - 1) / orbk::UNF_WARPS, orbk::UNF_WARPS * 32, 0, q>>>(
         ctx->d_raw + (size_t)f0 * ctx->raw_slot, ctx->raw_slot, ctx->d_frames + (size_t)f0 * ctx->frames_slot_bytes,
         ctx->frames_slot_bytes, ctx->frames_pitch, w, h, nf, ctx->d_inf_status + f0, ctx->d_adler + f0);
+    CK(cudaMemcpyAsync(ctx->d_crc + (size_t)f0 * 3 * orbk::PNG_CRC_CAP, ctx->h_crc + (size_t)f0 * 3 * orbk::PNG_CRC_CAP,
+                       sizeof(uint32_t) * 3 * orbk::PNG_CRC_CAP * nf, cudaMemcpyHostToDevice, q));
+    CK(cudaMemcpyAsync(ctx->d_crc_n + f0, ctx->h_crc_n + f0, sizeof(int) * nf, cudaMemcpyHostToDevice, q));
+    orbk::k_png_crc<<<nf, orbk::PNG_CRC_CAP, 0, q>>>(ctx->d_comp + (size_t)f0 * ctx->comp_slot, ctx->comp_slot,
+                                                     ctx->d_crc + (size_t)f0 * 3 * orbk::PNG_CRC_CAP, ctx->d_crc_n + f0, ctx->d_inf_status + f0);
     CK(cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches += 3;
     inflate_waves++;
     last_q = q;
     return ORB_OK;

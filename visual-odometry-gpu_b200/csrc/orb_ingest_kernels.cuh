@@ -24,7 +24,7 @@ struct InflateDesc {
   uint8_t* out;         // 16-byte aligned
 };
 
-enum : int { INF_OK = 0, INF_CORRUPT = 1, INF_SIZE = 2, INF_TRUNCATED = 3, INF_TABLE = 4, INF_FILTER = 5, INF_CHECKSUM = 6 };
+enum : int { INF_OK = 0, INF_CORRUPT = 1, INF_SIZE = 2, INF_TRUNCATED = 3, INF_TABLE = 4, INF_FILTER = 5, INF_CHECKSUM = 6, INF_CRC = 7 };
 
 constexpr int INF_LIT_ROOT = 11, INF_DIST_ROOT = 8;
 constexpr int INF_LIT_SUB = 1024, INF_DIST_SUB = 512;
@@ -753,6 +753,47 @@ __global__ void __launch_bounds__(UNF_WARPS * 32) k_unfilter(const uint8_t* __re
     if (bad) status[f] = INF_FILTER;
     else if (adler_expect && adler_expect[f] != ((b << 16) | a)) status[f] = INF_CHECKSUM;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CRC-32 of the IDAT chunks (PNG spec 5.3: over the chunk type and data), one thread per chunk, slicing-by-4 tables built in
+// shared memory.  The host lists (offset into the frame's concatenated payload, length, stored CRC) for up to
+// PNG_CRC_CAP chunks per frame while it copies the payloads; libpng writes 8 KB chunks, i.e. ~35 per KITTI frame.
+constexpr int PNG_CRC_CAP = 64;
+constexpr int PNG_PAYLOAD_OFS = 14;     // the zlib stream starts here in a frame's slot, so that the deflate data is 16-byte aligned
+
+__global__ void __launch_bounds__(PNG_CRC_CAP) k_png_crc(const uint8_t* __restrict__ comp, size_t slot, const uint32_t* __restrict__ descs,
+                                                        const int* __restrict__ counts, int* status) {
+  __shared__ uint32_t T[4][256];
+  const int t = threadIdx.x, f = blockIdx.x;
+  for (int i = t; i < 256; i += PNG_CRC_CAP) {
+    uint32_t c = i;
+#pragma unroll
+    for (int k = 0; k < 8; k++) c = (c & 1) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+    T[0][i] = c;
+  }
+  __syncthreads();
+  for (int i = t; i < 256; i += PNG_CRC_CAP) {
+    uint32_t c = T[0][i];
+#pragma unroll
+    for (int s = 1; s < 4; s++) { c = (c >> 8) ^ T[0][c & 0xff]; T[s][i] = c; }
+  }
+  __syncthreads();
+  if (t >= counts[f]) return;
+  const uint32_t* d = descs + ((size_t)f * PNG_CRC_CAP + t) * 3;
+  const uint8_t* p = comp + (size_t)f * slot + PNG_PAYLOAD_OFS + d[0];
+  uint32_t len = d[1];
+  uint32_t c = 0xffffffffu;
+  c = T[0][(c ^ 'I') & 0xff] ^ (c >> 8); c = T[0][(c ^ 'D') & 0xff] ^ (c >> 8);
+  c = T[0][(c ^ 'A') & 0xff] ^ (c >> 8); c = T[0][(c ^ 'T') & 0xff] ^ (c >> 8);
+  while (len && ((uintptr_t)p & 3)) { c = T[0][(c ^ *p++) & 0xff] ^ (c >> 8); len--; }
+  while (len >= 4) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(p) ^ c;
+    c = T[3][w & 0xff] ^ T[2][(w >> 8) & 0xff] ^ T[1][(w >> 16) & 0xff] ^ T[0][w >> 24];
+    p += 4; len -= 4;
+  }
+  while (len--) c = T[0][(c ^ *p++) & 0xff] ^ (c >> 8);
+  if (~c != d[2]) status[f] = INF_CRC;
 }
 
 }  // namespace orbk

@@ -52,6 +52,7 @@ struct orb_ctx {
   size_t comp_slot = 0, raw_slot = 0; int ingest_cap = 0;
   orbk::InflateDesc* h_descs = nullptr; orbk::InflateDesc* d_descs = nullptr;
   int* h_inf_status = nullptr; int* d_inf_status = nullptr; uint32_t* d_adler = nullptr;
+  uint32_t* h_crc = nullptr; uint32_t* d_crc = nullptr; int* h_crc_n = nullptr; int* d_crc_n = nullptr;   // IDAT chunk checksums
   static constexpr int N_INGEST = 4;
   cudaStream_t s_ingest[N_INGEST] = {nullptr, nullptr, nullptr, nullptr};
   // Lucas-Kanade tracker: two packed pyramids + point arrays

@@ -465,7 +465,8 @@ struct Parsed {
 };
 
 // walks the chunk list; when `idat` is given, concatenates the IDAT payloads into it
-const char* parse(const uint8_t* f, size_t n, Parsed* P, uint8_t* idat, bool check_crc, size_t skip = 0, size_t idat_cap = ~(size_t)0) {
+const char* parse(const uint8_t* f, size_t n, Parsed* P, uint8_t* idat, bool check_crc, size_t skip = 0, size_t idat_cap = ~(size_t)0,
+                  ChunkCrc* collect = nullptr, int collect_cap = 0, int* n_collected = nullptr) {
   if (n < 8 + 25 || memcmp(f, PNG_SIG, 8)) return "png: bad signature";
   size_t pos = 8;
   bool have_ihdr = false, have_iend = false;
@@ -477,7 +478,12 @@ const char* parse(const uint8_t* f, size_t n, Parsed* P, uint8_t* idat, bool che
     const uint8_t* data = f + pos + 8;
     const bool is_ihdr = !memcmp(type, "IHDR", 4), is_idat = !memcmp(type, "IDAT", 4), is_iend = !memcmp(type, "IEND", 4);
     if (!have_ihdr && !is_ihdr) return "png: IHDR is not the first chunk";
-    if (check_crc && (is_ihdr || is_idat) && crc32(type, (size_t)len + 4) != be32(data + len)) return "png: chunk CRC mismatch";
+    // with `collect`, the IDAT checksums are left to the caller (the device checks them): only IHDR is verified here
+    if (check_crc && (is_ihdr || (is_idat && !collect)) && crc32(type, (size_t)len + 4) != be32(data + len)) return "png: chunk CRC mismatch";
+    if (is_idat && collect) {
+      if (*n_collected >= collect_cap) return "png: too many IDAT chunks for the device checksum table";
+      collect[(*n_collected)++] = ChunkCrc{(uint32_t)total, len, be32(data + len)};
+    }
     if (is_ihdr) {
       if (len != 13) return "png: bad IHDR";
       const char* e = parse_ihdr(data, &P->info);
@@ -516,31 +522,29 @@ const char* read_info(const uint8_t* file, size_t n, Info* info) {
   return parse_ihdr(file + 16, &I);
 }
 
-const char* extract_deflate(const uint8_t* file, size_t n, Info* info, uint8_t* dst, size_t dst_cap, size_t* deflate_bytes) {
+const char* extract_deflate(const uint8_t* file, size_t n, Info* info, uint8_t* dst, size_t dst_cap, size_t* deflate_bytes,
+                            ChunkCrc* crcs, int crc_cap, int* n_crcs) {
   Parsed P;
   const char* e = parse(file, n, &P, nullptr, false);
   if (e) return e;
   *info = P.info;
   if (P.idat_total < 2 + 4 + 1) return "zlib: stream too short";
-  if (P.idat_total - 2 + 16 > dst_cap) return "png: compressed data larger than the frame slot";
-  // zlib header: find the first two payload bytes (they may be split over chunks, so walk again below with skip = 2)
-  uint8_t head[2];
-  {
-    size_t pos = 8, got = 0;
-    while (got < 2 && pos + 12 <= n) {
-      const uint32_t len = be32(file + pos);
-      if (!memcmp(file + pos + 4, "IDAT", 4))
-        for (uint32_t i = 0; i < len && got < 2; i++) head[got++] = file[pos + 8 + i];
-      pos += 12 + (size_t)len;
-    }
+  if (P.idat_total + 16 > dst_cap) return "png: compressed data larger than the frame slot";
+  int nc = 0;
+  if (crcs) {
+    // many tiny IDAT chunks (never seen from libpng, which writes 8 KB chunks): check them here after all
+    e = parse(file, n, &P, dst, true, 0, dst_cap, crcs, crc_cap, &nc);
+    if (e && !strcmp(e, "png: too many IDAT chunks for the device checksum table")) { crcs = nullptr; nc = 0; }
+    else if (e) return e;
   }
-  if ((head[0] & 15) != 8 || (head[0] >> 4) > 7) return "zlib: unknown compression method";
-  if (((head[0] << 8) | head[1]) % 31) return "zlib: header check failed";
-  if (head[1] & 0x20) return "zlib: preset dictionary";
-  if ((e = parse(file, n, &P, dst, true, 2, dst_cap))) return e;
-  const size_t body = P.idat_total - 2;
-  memset(dst + body, 0, 16);
-  *deflate_bytes = body - 4;      // without the Adler-32 trailer
+  if (!crcs && (e = parse(file, n, &P, dst, true, 0, dst_cap))) return e;
+  if (n_crcs) *n_crcs = nc;
+  // zlib framing (RFC 1950) in front of the deflate stream
+  if ((dst[0] & 15) != 8 || (dst[0] >> 4) > 7) return "zlib: unknown compression method";
+  if (((dst[0] << 8) | dst[1]) % 31) return "zlib: header check failed";
+  if (dst[1] & 0x20) return "zlib: preset dictionary";
+  memset(dst + P.idat_total, 0, 16);
+  *deflate_bytes = P.idat_total - 2 - 4;      // without the zlib header and the Adler-32 trailer
   return nullptr;
 }
 

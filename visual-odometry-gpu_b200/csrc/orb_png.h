@@ -26,10 +26,14 @@ struct Scratch {
 };
 const char* decode_gray8(const uint8_t* file, size_t n, uint8_t* dst, size_t pitch, int expect_w, int expect_h, Scratch* scratch);
 
-// Device-decode path: checks the framing (signature, chunk CRCs, zlib header) and concatenates the IDAT payloads without
-// the 2-byte zlib header into dst (16 zero bytes appended).  *deflate_bytes = length of the raw deflate stream (the
-// Adler-32 trailer that follows it in dst is not counted).
-const char* extract_deflate(const uint8_t* file, size_t n, Info* info, uint8_t* dst, size_t dst_cap, size_t* deflate_bytes);
+// Device-decode path: checks the framing (signature, IHDR, zlib header) and concatenates the IDAT payloads -- the whole
+// zlib stream, header included -- into dst (16 zero bytes appended).  *deflate_bytes = length of the raw deflate stream that
+// starts at dst + 2 (the Adler-32 trailer behind it is not counted).  With `crcs`, the IDAT chunk checksums are not verified
+// here but listed (offset into dst, length, stored CRC) for the device to verify; files with more than crc_cap chunks are
+// verified on the host instead (*n_crcs = 0).
+struct ChunkCrc { uint32_t offset, len, crc; };
+const char* extract_deflate(const uint8_t* file, size_t n, Info* info, uint8_t* dst, size_t dst_cap, size_t* deflate_bytes,
+                            ChunkCrc* crcs = nullptr, int crc_cap = 0, int* n_crcs = nullptr);
 
 // raw pieces, exported for the tests
 const char* inflate_zlib(const uint8_t* in, size_t n_in, uint8_t* out, size_t n_out, size_t* produced, bool verify_adler);
