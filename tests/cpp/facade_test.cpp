@@ -8,6 +8,7 @@
 #include "orb.hpp"
 #include "orb_cpu.hpp"
 #include "orb_pattern.hpp"
+#include "orb_stages.hpp"
 
 template <class T> static void dump(const std::string& path, const std::vector<T>& v) {
     FILE* f = fopen(path.c_str(), "wb");
@@ -46,6 +47,14 @@ int main(int argc, char** argv) {
         std::vector<float> as = fast.compute_orientations(image, ks);
         std::vector<ORBDescriptor> ds = brief.compute(image, ks, as);
         dump(out + ".stage.kps", ks); dump(out + ".stage.ang", as); dump(out + ".stage.desc", ds);
+        // the free functions of the reference's .cuh seam (src/orb.cpp:24,31,42,65)
+        std::vector<Keypoint> kf; std::vector<float> af, hf; std::vector<ORBDescriptor> df;
+        int kp_count = Fast(image, kf, 20, 9, 3, 700);
+        Orientations(image, kf, af, 31);
+        Brief(image, kf, af, df, 256, 31);
+        HarrisScore(image, kf, hf, 7, 0.04f);
+        if (kp_count != (int)kf.size() || kf.size() != ks.size()) { fprintf(stderr, "Fast() count\n"); return 5; }
+        dump(out + ".free.kps", kf); dump(out + ".free.ang", af); dump(out + ".free.desc", df); dump(out + ".free.harris", hf);
         long s = 0; for (int i = 0; i < 1024; i++) s += bit_pattern_31_[i];
         printf("FACADE_OK %zu %zu %zu pattern_sum %ld\n", first, kc.size(), ks.size(), s);
     } catch (const std::exception& e) {

@@ -58,6 +58,11 @@ def test_facade_matches_oracle(tmp_path, V, O, kitti0):
     assert np.array_equal(k, kr)
     ar = O.orientations(kitti0, kr, 31)
     assert np.array_equal(a.view(np.uint32), ar.view(np.uint32)) and np.array_equal(d, O.brief(kitti0, kr, ar))
+    # the free functions of include/orb_stages.hpp (reference Fast.cuh / Brief.cuh / HarrisScore.cuh)
+    k, a, d = load("free")
+    assert np.array_equal(k, kr) and np.array_equal(a.view(np.uint32), ar.view(np.uint32)) and np.array_equal(d, O.brief(kitti0, kr, ar))
+    hs = np.fromfile(out + ".free.harris", dtype=np.float32)
+    assert np.array_equal(hs.view(np.uint32), O.harris(kitti0, kr, 0.04).view(np.uint32))
 
 
 def _build_feature2d(tmp_path, V):
