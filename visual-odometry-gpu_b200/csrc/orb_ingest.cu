@@ -145,6 +145,7 @@ int ensure_device_decode(orb_ctx* ctx, int n, int w, int h) {
   int prio_least = 0, prio_greatest = 0;
   CK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
   for (cudaStream_t& q : ctx->s_ingest) if (!q) CK(cudaStreamCreateWithPriority(&q, cudaStreamNonBlocking, prio_greatest));
+  CK(cudaFuncSetAttribute(orbk::k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(orbk::InflateShared)));
   ctx->comp_slot = comp; ctx->raw_slot = raw; ctx->ingest_cap = cap;
   return ORB_OK;
 }
@@ -220,7 +221,7 @@ struct DeviceDecodeSource : WaveSource {
       ctx->h_descs[i] = orbk::InflateDesc{ctx->d_comp + (size_t)i * ctx->comp_slot + 16, bytes[i], out_bytes, ctx->d_raw + (size_t)i * ctx->raw_slot + orbk::UNF_LEAD};
     }
     CK(cudaMemcpyAsync(ctx->d_descs + f0, ctx->h_descs + f0, sizeof(orbk::InflateDesc) * nf, cudaMemcpyHostToDevice, q));
-    orbk::k_inflate<<<nf, 32, 0, q>>>(ctx->d_descs + f0, ctx->d_inf_status + f0, ctx->d_adler + f0);
+    orbk::k_inflate<<<nf, 32, sizeof(orbk::InflateShared), q>>>(ctx->d_descs + f0, ctx->d_inf_status + f0, ctx->d_adler + f0);
     orbk::k_unfilter<<<(nf + orbk::UNF_WARPS - 1) / orbk::UNF_WARPS, orbk::UNF_WARPS * 32, 0, q>>>(
         ctx->d_raw + (size_t)f0 * ctx->raw_slot, ctx->raw_slot, ctx->d_frames + (size_t)f0 * ctx->frames_slot_bytes,
         ctx->frames_slot_bytes, ctx->frames_pitch, w, h, nf, ctx->d_inf_status + f0, ctx->d_adler + f0);
@@ -406,7 +407,8 @@ int orb_debug_inflate(orb_ctx* ctx, const uint8_t* streams, const uint32_t* offs
   CK(cudaMemcpy(d_in, packed.data(), in_at[n], cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_desc, descs.data(), sizeof(orbk::InflateDesc) * n, cudaMemcpyHostToDevice));
   CK(cudaMemset(d_out, 0xEE, out_at[n]));
-  orbk::k_inflate<<<n, 32, 0, ctx->stream>>>(d_desc, d_st, nullptr);
+  CK(cudaFuncSetAttribute(orbk::k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(orbk::InflateShared)));
+  orbk::k_inflate<<<n, 32, sizeof(orbk::InflateShared), ctx->stream>>>(d_desc, d_st, nullptr);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaMemcpy(status, d_st, sizeof(int) * n, cudaMemcpyDeviceToHost));

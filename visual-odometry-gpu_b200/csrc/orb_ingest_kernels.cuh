@@ -28,7 +28,10 @@ enum : int { INF_OK = 0, INF_CORRUPT = 1, INF_SIZE = 2, INF_TRUNCATED = 3, INF_T
 
 constexpr int INF_LIT_ROOT = 11, INF_DIST_ROOT = 8;
 constexpr int INF_LIT_SUB = 1024, INF_DIST_SUB = 512;
-constexpr int INF_RING = 8192;        // output window kept in shared memory (bytes, power of two)
+#ifndef ORB_INF_RING
+#define ORB_INF_RING 8192
+#endif
+constexpr int INF_RING = ORB_INF_RING; // output window kept in shared memory (bytes, power of two)
 constexpr int INF_IN_WORDS = 512;     // input ring (32-bit words, power of two)
 constexpr int INF_MARGIN = 600;       // a decode step never adds more than 258 + 2 bytes; flush well before the ring wraps
 // match sources nearer than this are read from the window (valid up to INF_RING - 2 back), the others from global memory
@@ -280,7 +283,8 @@ __device__ __forceinline__ void inf_decode_segment(InflateShared& S, uint32_t st
 
 __global__ void __launch_bounds__(32) k_inflate(const InflateDesc* __restrict__ descs, int* __restrict__ status,
                                                 uint32_t* __restrict__ trailer /* may be null: the 4 bytes after the stream */) {
-  __shared__ InflateShared S;
+  extern __shared__ __align__(16) unsigned char inf_smem[];      // sizeof(InflateShared), opted in by the host when > 48 KB
+  InflateShared& S = *reinterpret_cast<InflateShared*>(inf_smem);
   const int lane = threadIdx.x;
   const InflateDesc D = descs[blockIdx.x];
   const uint32_t in_words = (D.in_bytes + 3) >> 2;
