@@ -499,11 +499,11 @@ __global__ void __launch_bounds__(32) k_inflate(const InflateDesc* __restrict__ 
         }
         // ---- Huffman block: the serial walk ----
         INF_REFILL();
+        const uint32_t e0 = S.lit[(uint32_t)bitbuf & ((1u << INF_LIT_ROOT) - 1)];
         if (par) {
           // literals belong to the next parallel round: only lengths, links and end-of-block are handled here
-          const uint32_t e0 = S.lit[(uint32_t)bitbuf & ((1u << INF_LIT_ROOT) - 1)];
           if (!(e0 & 0x80u)) break;
-        } else {
+        } else if (!(e0 & 0x80u)) {             // (a match right after a match skips the set-up of the literal run)
           // Literal run.  No bookkeeping inside: a probe emits at most 2 bytes and takes at most INF_LIT_ROOT bits, so
           // the window room and the input words at hand bound the number of probes up front; a probe that meets a
           // length / end-of-block / link entry reads zeros in the fields used here and does nothing, and the run ends
