@@ -256,6 +256,7 @@ def main():
     bind_to_gpu_numa_node(local_rank)            # pinned staging buffers get first-touched next to this GPU's PCIe root
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # stdout carries the JSON line only (NCCL prints a version banner)
         dist.init_process_group("nccl", device_id=dev)
     V = importlib.import_module("visual-odometry-gpu_b200")
 
