@@ -74,8 +74,8 @@ __device__ __forceinline__ float ord2f(uint32_t k) {
 // ---------------------------------------------------------------------------------------------
 // Harris response at a pixel, decision D5: integer 3x3 Sobel, float 7x7 window in
 // row-major order, separate multiply and add (no FMA), det - k * trace * trace.
-// REL(dy, dx) returns the pixel of the reflect-101 extended level at an offset from the keypoint.
-// The 9x9 neighbourhood is walked once, row by row: per window row the vertical [1 2 1] sums of the nine
+// ROW(dy, v) fills v[0..8] with the pixels of the reflect-101 extended level at row offset dy, columns -4..4 from the
+// keypoint.  The 9x9 neighbourhood is walked once, row by row: per window row the vertical [1 2 1] sums of the nine
 // columns give Ix = V[c+1] - V[c-1], the horizontal [1 2 1] sums of the rows above / below give Iy.
 __constant__ float c_harris_w[49];   // createGaussianKernel(7), ref src/GaussianBlur.cpp:7-37 (uploaded at orb_create)
 
@@ -83,18 +83,17 @@ __device__ __forceinline__ float int2float_exact(int v) {   // |v| < 2^22: exact
   return __fsub_rn(__int_as_float(0x4B400000 + v), 12582912.0f);
 }
 
-template <typename REL>
-__device__ __forceinline__ float harris_at(REL pix, float k) {
+template <typename ROW>
+__device__ __forceinline__ float harris_at(ROW row, float k) {
   float A = 0.f, B = 0.f, C = 0.f;
   int pm[9], pc[9], pp[9], hm[7], hc[7], hp[7];
-#pragma unroll
-  for (int c = 0; c < 9; c++) { pm[c] = pix(-4, c - 4); pc[c] = pix(-3, c - 4); }
+  row(-4, pm);
+  row(-3, pc);
 #pragma unroll
   for (int j = 0; j < 7; j++) { hm[j] = pm[j] + 2 * pm[j + 1] + pm[j + 2]; hc[j] = pc[j] + 2 * pc[j + 1] + pc[j + 2]; }
 #pragma unroll
   for (int dy = -3; dy <= 3; dy++) {
-#pragma unroll
-    for (int c = 0; c < 9; c++) pp[c] = pix(dy + 1, c - 4);
+    row(dy + 1, pp);
 #pragma unroll
     for (int j = 0; j < 7; j++) hp[j] = pp[j] + 2 * pp[j + 1] + pp[j + 2];
     int V[9];
@@ -165,13 +164,16 @@ __device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<
 constexpr int A_TW = 128, A_TH = 64, A_THREADS = 256;
 constexpr int A_RW = A_TW + 4, A_RH = A_TH + 4;   // resized region incl. blur halo 2
 constexpr int A_RP = 136;                          // shared pitch of resized rows (bytes)
+#ifndef ORB_A_SEG
+#define ORB_A_SEG 4
+#endif
+constexpr int A_SEG = ORB_A_SEG;                   // output rows per thread in the blur (4: all 256 threads, 8: 128)
 
 __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bufs B) {
   __shared__ uint32_t s_xs[A_RW];    // column taps: s0 | s1 << 16
   __shared__ uint32_t s_xa[A_RW];    //              a0 | a1 << 16
   __shared__ __align__(16) uint4 s_yt[A_RH];   // row taps: byte offsets of the two source rows inside the frame, b0, b1
   __shared__ __align__(16) uint8_t s_res[A_RH * A_RP];
-  __shared__ __align__(16) uint16_t s_h[A_RH * A_TW];
   const int tid = threadIdx.x, f = blockIdx.y;
   const uint32_t tt = __ldg(B.tile_a + blockIdx.x);
   const int l = tt & 15;
@@ -237,40 +239,44 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
     return;
   }
 
-  // horizontal [1 4 6 4 1]: 8 outputs per item, lanes hold pixels two apart: (o0,o2) (o1,o3) (o4,o6) (o5,o7)
-  const uint32_t M = 0x00ff00ffu;
-  for (int it = tid; it < A_RH * (A_TW / 8); it += A_THREADS) {
-    const int ry = it / (A_TW / 8), g = it - ry * (A_TW / 8);
-    const uint8_t* r = s_res + ry * A_RP + 8 * g;
-    const uint2 w01 = *(const uint2*)r;
-    const uint32_t w2 = *(const uint32_t*)(r + 8);
-    const uint32_t v1 = prmt(w01.x, w01.y, 0x5432), v2 = prmt(w01.y, w2, 0x5432);
-    const uint32_t q0 = w01.x & M, q1 = (w01.x >> 8) & M, q2 = v1 & M, q3 = (v1 >> 8) & M, q4 = w01.y & M,
-                   q5 = (w01.y >> 8) & M, q6 = v2 & M, q7 = (v2 >> 8) & M, q8 = w2 & M, q9 = (w2 >> 8) & M;
-    uint4 o;
-    o.x = q0 + q4 + 4 * (q1 + q3) + 6 * q2;
-    o.y = q1 + q5 + 4 * (q2 + q4) + 6 * q3;
-    o.z = q4 + q8 + 4 * (q5 + q7) + 6 * q6;
-    o.w = q5 + q9 + 4 * (q6 + q8) + 6 * q7;
-    *(uint4*)(s_h + ry * A_TW + 8 * g) = o;
-  }
-  __syncthreads();
-  // vertical [1 4 6 4 1], one rounding: (sum + 128) >> 8  (cv::GaussianBlur 5x5 sigma 0 on u8)
-  for (int it = tid; it < A_TH * (A_TW / 8); it += A_THREADS) {
-    const int oy = it / (A_TW / 8), g = it - oy * (A_TW / 8);
-    if (y0 + oy >= h || x0 + 8 * g >= G.pitch) continue;
-    const uint16_t* c = s_h + oy * A_TW + 8 * g;
-    const uint4 r0 = *(const uint4*)c, r1 = *(const uint4*)(c + A_TW), r2 = *(const uint4*)(c + 2 * A_TW),
-                r3 = *(const uint4*)(c + 3 * A_TW), r4 = *(const uint4*)(c + 4 * A_TW);
-    const uint32_t R = 0x00800080u;
-    const uint32_t a = r0.x + r4.x + 4 * (r1.x + r3.x) + 6 * r2.x + R;
-    const uint32_t b = r0.y + r4.y + 4 * (r1.y + r3.y) + 6 * r2.y + R;
-    const uint32_t cc = r0.z + r4.z + 4 * (r1.z + r3.z) + 6 * r2.z + R;
-    const uint32_t d = r0.w + r4.w + 4 * (r1.w + r3.w) + 6 * r2.w + R;
-    uint2 out;
-    out.x = prmt(a, b, 0x7351);    // (a>>8 lane0, b>>8 lane0, a>>8 lane1, b>>8 lane1) = pixels 0,1,2,3
-    out.y = prmt(cc, d, 0x7351);
-    *(uint2*)(dst + (size_t)(y0 + oy) * G.pitch + x0 + 8 * g) = out;
+  // [1 4 6 4 1] x [1 4 6 4 1] through registers: a thread owns an 8-pixel column group and A_SEG output rows.  The
+  // horizontal sums of its A_SEG + 4 resized rows are computed once each (16-bit lanes holding pixels two apart:
+  // (o0,o2) (o1,o3) (o4,o6) (o5,o7)) and kept in a five-row register window; the vertical pass reads only registers.
+  // One rounding: (sum + 128) >> 8  (cv::GaussianBlur 5x5 sigma 0 on u8).
+  if (tid < (A_TW / 8) * (A_TH / A_SEG)) {
+    const int g = tid & (A_TW / 8 - 1), oy0 = (tid / (A_TW / 8)) * A_SEG;
+    if (y0 + oy0 < h && x0 + 8 * g < G.pitch) {
+      const uint32_t M = 0x00ff00ffu, R = 0x00800080u;
+      const uint8_t* r = s_res + oy0 * A_RP + 8 * g;
+      uint8_t* d = dst + (size_t)(y0 + oy0) * G.pitch + x0 + 8 * g;
+      uint4 hs[5];
+#pragma unroll
+      for (int k = 0; k < A_SEG + 4; k++) {
+        const uint2 w01 = *(const uint2*)r;
+        const uint32_t w2 = *(const uint32_t*)(r + 8);
+        r += A_RP;
+        const uint32_t v1 = prmt(w01.x, w01.y, 0x5432), v2 = prmt(w01.y, w2, 0x5432);
+        const uint32_t q0 = w01.x & M, q1 = (w01.x >> 8) & M, q2 = v1 & M, q3 = (v1 >> 8) & M, q4 = w01.y & M,
+                       q5 = (w01.y >> 8) & M, q6 = v2 & M, q7 = (v2 >> 8) & M, q8 = w2 & M, q9 = (w2 >> 8) & M;
+        uint4 o;
+        o.x = q0 + q4 + 4 * (q1 + q3) + 6 * q2;
+        o.y = q1 + q5 + 4 * (q2 + q4) + 6 * q3;
+        o.z = q4 + q8 + 4 * (q5 + q7) + 6 * q6;
+        o.w = q5 + q9 + 4 * (q6 + q8) + 6 * q7;
+        hs[k % 5] = o;
+        if (k >= 4 && y0 + oy0 + k - 4 < h) {      // output row oy0 + k - 4 from resized rows k-4 .. k of this thread
+          const uint4 &m2 = hs[(k + 1) % 5], &m1 = hs[(k + 2) % 5], &c0 = hs[(k + 3) % 5], &p1 = hs[(k + 4) % 5];
+          const uint32_t a = m2.x + o.x + 4 * (m1.x + p1.x) + 6 * c0.x + R;
+          const uint32_t b = m2.y + o.y + 4 * (m1.y + p1.y) + 6 * c0.y + R;
+          const uint32_t cc = m2.z + o.z + 4 * (m1.z + p1.z) + 6 * c0.z + R;
+          const uint32_t dd = m2.w + o.w + 4 * (m1.w + p1.w) + 6 * c0.w + R;
+          uint2 out;
+          out.x = prmt(a, b, 0x7351);    // (a>>8 lane0, b>>8 lane0, a>>8 lane1, b>>8 lane1) = pixels 0,1,2,3
+          out.y = prmt(cc, dd, 0x7351);
+          *(uint2*)(d + (size_t)(k - 4) * G.pitch) = out;
+        }
+      }
+    }
   }
 }
 
@@ -584,10 +590,31 @@ __global__ void __launch_bounds__(C_THREADS, ORB_C_MINB) k_harris(const OrbPlan 
     const int dxl = x >= 4 ? -4 : 4 - 2 * x, dxr = x + 4 < w ? 4 : 2 * (w - 1 - x) - 4;   // offsets of columns x-4, x+4
     const int dyt = y >= 4 ? -4 : 4 - 2 * y, dyb = y + 4 < h ? 4 : 2 * (h - 1 - y) - 4;
     const uint8_t* ctr = img + (size_t)y * pitch + x;
-    const float r = harris_at([&](int dy, int dx) {
-      const int oy = dy == -4 ? dyt : (dy == 4 ? dyb : dy), ox = dx == -4 ? dxl : (dx == 4 ? dxr : dx);
-      return (int)ctr[oy * pitch + ox];
-    }, P.harris_k);
+    float r;
+    if (x >= 4 && x + 4 < w) {
+      // columns x-4 .. x+4 of a row lie in three aligned words (rows are 16-byte aligned and pitch >= w, so the third
+      // word, which holds column x+4 < w, is inside the row): 3 loads + 3 funnel shifts per row instead of 9 byte loads
+      const int sh = 8 * ((x - 4) & 3);
+      const uint8_t* base = ctr - 4 - ((x - 4) & 3);
+      r = harris_at([&](int dy, int (&v)[9]) {
+        const int oy = dy == -4 ? dyt : (dy == 4 ? dyb : dy);
+        const uint32_t* q = (const uint32_t*)(base + oy * pitch);
+        const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+        const uint32_t a = __funnelshift_r(w0, w1, sh), b = __funnelshift_r(w1, w2, sh), c = w2 >> sh;
+        v[0] = a & 0xff; v[1] = (a >> 8) & 0xff; v[2] = (a >> 16) & 0xff; v[3] = a >> 24;
+        v[4] = b & 0xff; v[5] = (b >> 8) & 0xff; v[6] = (b >> 16) & 0xff; v[7] = b >> 24;
+        v[8] = c & 0xff;
+      }, P.harris_k);
+    } else {
+      r = harris_at([&](int dy, int (&v)[9]) {
+        const int oy = dy == -4 ? dyt : (dy == 4 ? dyb : dy);
+        const uint8_t* q = ctr + oy * pitch;
+        v[0] = q[dxl];
+#pragma unroll
+        for (int c = 1; c < 8; c++) v[c] = q[c - 4];
+        v[8] = q[dxr];
+      }, P.harris_k);
+    }
     *slot = ((unsigned long long)(~f2ord(r)) << 32) | xy;
   }
 }
@@ -1009,8 +1036,11 @@ __global__ void k_harris_list(const uint8_t* __restrict__ img, int pitch, int w,
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int ky = kps[i].y, kx = kps[i].x;
-  auto pix = [&](int dy, int dx) { return (int)img[(size_t)reflect101(ky + dy, h) * pitch + reflect101(kx + dx, w)]; };
-  out[i] = harris_at(pix, k);
+  out[i] = harris_at([&](int dy, int (&v)[9]) {
+    const uint8_t* q = img + (size_t)reflect101(ky + dy, h) * pitch;
+#pragma unroll
+    for (int c = 0; c < 9; c++) v[c] = q[reflect101(kx + c - 4, w)];
+  }, k);
 }
 
 // =============================================================================================
