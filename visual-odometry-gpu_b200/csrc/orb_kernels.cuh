@@ -358,8 +358,8 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
       const uint32_t v8m = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
       vmask = (v8m & 0x55u) | ((v8m & 0xaau) << 16);       // pixel 2k -> bit 2k, pixel 2k+1 -> bit 17+2k
     }
-    uint32_t fl[NK];
-    int cnt = 0;
+    static_assert(NK <= 8, "passer masks of a thread: one byte per row item, two words");
+    uint32_t mlo = 0, mhi = 0;        // bit 8k + j: pixel j of row item k passed (k < 4 in mlo, the rest in mhi)
 #pragma unroll
     for (int k = 0; k < NK; k++) {
       const int sy = rt + NRT * k, y = y0 - 1 + sy;
@@ -387,9 +387,11 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
         }
         flags &= vmask;
       }
-      fl[k] = flags;
-      cnt += __popc(flags);
+      const uint32_t m8 = (flags & 0x55u) | ((flags >> 16) & 0xaau);       // bit j = pixel j
+      if (k < 4) mlo |= m8 << (8 * k);
+      else mhi |= m8 << (8 * (k - 4));
     }
+    const int cnt = __popc(mlo) + __popc(mhi);
     int incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -402,16 +404,20 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
       if (lane == 31) base = atomicAdd(&s_ctr[0], total);
       base = __shfl_sync(0xffffffffu, base, 31);
       int off = base + incl - cnt;
-#pragma unroll
-      for (int k = 0; k < NK; k++) {
-        uint32_t flags = fl[k];
-        const int rowbase = (rt + NRT * k) * B_SP + pc;
-        while (flags) {
-          const int b = __ffs(flags) - 1;
-          flags &= flags - 1;
-          if (off < B_LIST) s_list[off] = (uint16_t)(rowbase + (b & 15));
-          off++;
-        }
+      // one loop over all passers of the thread (row items flattened: the warp runs max-over-lanes of the thread totals,
+      // not the sum over row items of the per-item maxima)
+      const int e0 = rt * B_SP + pc;
+      while (mlo) {
+        const int b = __ffs(mlo) - 1;
+        mlo &= mlo - 1;
+        if (off < B_LIST) s_list[off] = (uint16_t)(e0 + (b >> 3) * (NRT * B_SP) + (b & 7));
+        off++;
+      }
+      while (mhi) {
+        const int b = __ffs(mhi) - 1;
+        mhi &= mhi - 1;
+        if (off < B_LIST) s_list[off] = (uint16_t)(e0 + (4 + (b >> 3)) * (NRT * B_SP) + (b & 7));
+        off++;
       }
     }
   }
