@@ -299,6 +299,9 @@ constexpr int B_SH = B_TH + 2;         // rows y0-1 .. y0+B_TH
 #ifndef ORB_B_MINB
 #define ORB_B_MINB 6
 #endif
+#ifndef ORB_PRETEST_SPLIT
+#define ORB_PRETEST_SPLIT 2
+#endif
 constexpr int B_LIST = ORB_B_LIST;     // pretest passers kept in the list; denser tiles take the dense fallback
 constexpr int B_SURV = 1024;
 constexpr int B_PIX_BYTES = B_PH * B_SP, B_SCORE_BYTES = B_SH * B_SCP * 2;
@@ -348,6 +351,14 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
   {
     constexpr int NG = 18, NRT = 14, NK = (B_SH + NRT - 1) / NRT;
     const uint32_t K = 0x64646464u;   // half(1024 + p) = 0x6400 | p
+    // Two equivalent formulations share the work between the ALU pipe (HMNMX2 / HSET2) and the half-precision adder:
+    // (a) ">= 3 of 4 have v >= Ip + thr" <=> the second smallest of the four >= Ip + thr (min/max network);
+    // (b) the count of such pixels is a sum of saturated differences, sat(v - Ip - thr + 1) in {0, 1} (small integers,
+    //     exact in half precision), and ">= 3" is sat(count - 2): HADD2(.SAT) only.
+    // The first ORB_PRETEST_SPLIT pixel pairs of an item use (a), the rest (b) (measured: 2 is best, by ~1.5 %).
+    // The darker side uses max(thr, 1) so that a pixel is never counted on both sides (ref src/orb_cpu.cpp:44-57).
+    const __half2 one_m_thr = __float2half2_rn((float)(1 - thr)), one_m_dthr = __float2half2_rn((float)(1 - max(thr, 1)));
+    const __half2 minus2 = __float2half2_rn(-2.0f);
     const __half2 thr2 = __float2half2_rn((float)thr), dthr2 = __float2half2_rn((float)max(thr, 1));
     const int g = tid % NG, rt = tid / NG;
     const int pc = 8 + 8 * g, xs = x0 - 8 + 8 * g;
@@ -356,10 +367,12 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
     uint32_t vmask = 0;
     if (lo < hi && rt < NRT) {
       const uint32_t v8m = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-      vmask = (v8m & 0x55u) | ((v8m & 0xaau) << 16);       // pixel 2k -> bit 2k, pixel 2k+1 -> bit 17+2k
+#pragma unroll
+      for (int q = 0; q < 4; q++)                          // pixel 2q -> bit 10+q, pixel 2q+1 -> bit 26+q (see below)
+        vmask |= (((v8m >> (2 * q)) & 1u) << (10 + q)) | (((v8m >> (2 * q + 1)) & 1u) << (26 + q));
     }
     static_assert(NK <= 8, "passer masks of a thread: one byte per row item, two words");
-    uint32_t mlo = 0, mhi = 0;        // bit 8k + j: pixel j of row item k passed (k < 4 in mlo, the rest in mhi)
+    uint32_t mlo = 0, mhi = 0;        // byte k: passers of row item k (k < 4 in mlo, the rest in mhi), bit order below
 #pragma unroll
     for (int k = 0; k < NK; k++) {
       const int sy = rt + NRT * k, y = y0 - 1 + sy;
@@ -378,16 +391,26 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
 #pragma unroll
         for (int q = 0; q < 4; q++) {
           const __half2 v0 = as_h2(T[q]), v4 = as_h2(Rt[q]), v8 = as_h2(Bm[q]), v12 = as_h2(Lf[q]), c2 = as_h2(C[q]);
-          const __half2 a = __hmin2(v0, v4), b = __hmax2(v0, v4), c = __hmin2(v8, v12), d = __hmax2(v8, v12);
-          const __half2 m1 = __hmax2(a, c), m2 = __hmin2(b, d);
-          const __half2 s2 = __hmin2(m1, m2), l2 = __hmax2(m1, m2);        // 2nd smallest / 2nd largest of the four
-          const uint32_t fb = __hge2_mask(__hsub2(s2, c2), thr2);           // >= 3 of 4 have v >= Ip + thr
-          const uint32_t fd = __hge2_mask(__hsub2(c2, l2), dthr2);          // >= 3 of 4 have v <= Ip - thr (and not brighter)
-          flags |= ((fb | fd) & 0x00020001u) << (2 * q);
+          if (q < ORB_PRETEST_SPLIT) {   // min/max network (ALU pipe): 2nd smallest / 2nd largest of the four against Ip +- thr
+            const __half2 a = __hmin2(v0, v4), b = __hmax2(v0, v4), c = __hmin2(v8, v12), d = __hmax2(v8, v12);
+            const __half2 m1 = __hmax2(a, c), m2 = __hmin2(b, d);
+            const __half2 s2 = __hmin2(m1, m2), l2 = __hmax2(m1, m2);
+            const uint32_t fb = __hge2_mask(__hsub2(s2, c2), thr2);
+            const uint32_t fd = __hge2_mask(__hsub2(c2, l2), dthr2);
+            flags |= (fb | fd) & (0x04000400u << q);
+          } else {                       // saturated counts (half-precision adds)
+            const __half2 nhi = __hsub2(one_m_thr, c2), plo = __hadd2(c2, one_m_dthr);
+            const __half2 nb = __hadd2(__hadd2(__hadd2_sat(v0, nhi), __hadd2_sat(v4, nhi)),
+                                       __hadd2(__hadd2_sat(v8, nhi), __hadd2_sat(v12, nhi)));
+            const __half2 nd = __hadd2(__hadd2(__hadd2_sat(plo, __hneg2(v0)), __hadd2_sat(plo, __hneg2(v4))),
+                                       __hadd2(__hadd2_sat(plo, __hneg2(v8)), __hadd2_sat(plo, __hneg2(v12))));
+            const __half2 pass = __hadd2(__hadd2_sat(nb, minus2), __hadd2_sat(nd, minus2));   // 0 or 1.0 (0x3c00) per pixel
+            flags |= (*reinterpret_cast<const uint32_t*>(&pass)) & (0x04000400u << q);
+          }
         }
         flags &= vmask;
       }
-      const uint32_t m8 = (flags & 0x55u) | ((flags >> 16) & 0xaau);       // bit j = pixel j
+      const uint32_t m8 = ((flags >> 10) & 0xfu) | ((flags >> 22) & 0xf0u);   // bits 0-3: pixels 0,2,4,6; bits 4-7: pixels 1,3,5,7
       if (k < 4) mlo |= m8 << (8 * k);
       else mhi |= m8 << (8 * (k - 4));
     }
@@ -410,13 +433,13 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
       while (mlo) {
         const int b = __ffs(mlo) - 1;
         mlo &= mlo - 1;
-        if (off < B_LIST) s_list[off] = (uint16_t)(e0 + (b >> 3) * (NRT * B_SP) + (b & 7));
+        if (off < B_LIST) s_list[off] = (uint16_t)(e0 + (b >> 3) * (NRT * B_SP) + ((b & 3) << 1) + ((b >> 2) & 1));
         off++;
       }
       while (mhi) {
         const int b = __ffs(mhi) - 1;
         mhi &= mhi - 1;
-        if (off < B_LIST) s_list[off] = (uint16_t)(e0 + (4 + (b >> 3)) * (NRT * B_SP) + (b & 7));
+        if (off < B_LIST) s_list[off] = (uint16_t)(e0 + (4 + (b >> 3)) * (NRT * B_SP) + ((b & 3) << 1) + ((b >> 2) & 1));
         off++;
       }
     }
