@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
       const uint8_t* rc = s_pix + (8 * seg + 2) * B_SP + 16 + 8 * g;   // input row yb - 2
       const int nstrip = min(8, h - 4 - yb);                         // owned rows that lie above row h-4
       uint4 hs[5];
-      uint4 strip = make_uint4(0, 0, 0, 0);
+      uint4 strip = make_uint4(0, 0, 0, 0), acc = make_uint4(0, 0, 0, 0);
 #pragma unroll
       for (int r = 0; r < 12; r++) {
         const uint32_t m = *(const uint32_t*)(rc - 4), p = *(const uint32_t*)(rc + 8);
@@ -540,18 +540,20 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
         const uint32_t w0 = prmt(m, cc.x, 0x5432), w1 = prmt(cc.x, cc.y, 0x5432), w2 = prmt(cc.y, p, 0x5432);
         const uint32_t q0 = w0 & M, q1 = (w0 >> 8) & M, q2 = cc.x & M, q3 = (cc.x >> 8) & M, q4 = w1 & M, q5 = (w1 >> 8) & M,
                        q6 = cc.y & M, q7 = (cc.y >> 8) & M, q8 = w2 & M, q9 = (w2 >> 8) & M;
+        // horizontal 5-sums from shared pair sums: (o0,o2) = (p-2+p-1, p0+p1) + (p0+p1, p2+p3) + (p2, p4), ...
+        const uint32_t t1 = q0 + q1, t2 = q2 + q3, t3 = q4 + q5, t4 = q6 + q7, t5 = q8 + q9;
         uint4 o;
-        o.x = q0 + q1 + q2 + q3 + q4;
-        o.y = q1 + q2 + q3 + q4 + q5;
-        o.z = q4 + q5 + q6 + q7 + q8;
-        o.w = q5 + q6 + q7 + q8 + q9;
+        o.x = t1 + t2 + q4;
+        o.y = q1 + t2 + t3;
+        o.z = t3 + t4 + q8;
+        o.w = q5 + t4 + t5;
+        if (r >= 5) { const uint4 old = hs[r % 5]; acc.x -= old.x; acc.y -= old.y; acc.z -= old.z; acc.w -= old.w; }
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;      // sliding sum of the last five rows (16-bit lanes)
         hs[r % 5] = o;
         if (r >= 2 && r - 2 < nstrip) { strip.x += o.x; strip.y += o.y; strip.z += o.z; strip.w += o.w; }
-        if (r >= 4 && yb + r - 4 < h) {                              // box row yb + r - 4 = sum of the last five
-          const uint32_t a = hs[0].x + hs[1].x + hs[2].x + hs[3].x + hs[4].x, b = hs[0].y + hs[1].y + hs[2].y + hs[3].y + hs[4].y;
-          const uint32_t c = hs[0].z + hs[1].z + hs[2].z + hs[3].z + hs[4].z, d = hs[0].w + hs[1].w + hs[2].w + hs[3].w + hs[4].w;
+        if (r >= 4 && yb + r - 4 < h) {                              // box row yb + r - 4
           uint4 v;   // lanes (o0,o2)(o1,o3) -> natural order
-          v.x = prmt(a, b, 0x5410); v.y = prmt(a, b, 0x7632); v.z = prmt(c, d, 0x5410); v.w = prmt(c, d, 0x7632);
+          v.x = prmt(acc.x, acc.y, 0x5410); v.y = prmt(acc.x, acc.y, 0x7632); v.z = prmt(acc.z, acc.w, 0x5410); v.w = prmt(acc.z, acc.w, 0x7632);
           *(uint4*)(box + (size_t)(r - 4) * G.bpitch) = v;
         }
       }
