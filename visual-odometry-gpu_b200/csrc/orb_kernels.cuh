@@ -220,7 +220,39 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
       s_res[ry * A_RP + col] = (uint8_t)min(v, 255);
     }
   };
-  {
+  // Two adjacent columns at once when the level shrinks by at most 3 (source columns of neighbours are then <= 3 apart):
+  // the four source bytes of a row (two taps x two columns) lie in two aligned words, so a row pair costs 4 word loads,
+  // 2 byte permutes and 4 two-way dot products (IDP.2A: a0 * S0 + a1 * S1) instead of 8 byte loads and 8 multiply-adds.
+  auto resize_pair = [&](int col, int r0, int r1) {    // col even
+    if (x0 - halo + col >= w + halo) return;
+    const uint32_t xa0 = s_xa[col], xa1 = s_xa[col + 1];
+    const int sa = s_xs[col] & 0xffff, sb = s_xs[col + 1] & 0xffff;
+    const int base = min(min(sa, sb) & ~3, (int)sp - 8);          // both words inside the row (pitch is a multiple of 16)
+    const int oa = sa - base, ob = sb - base;                      // <= 6: the second taps sit at <= 7
+    const uint32_t sel = (uint32_t)(oa | ((oa + 1) << 4) | (ob << 8) | ((ob + 1) << 12));
+    const uint8_t* p0 = src + base;
+    asm volatile("" : "+l"(p0));
+    r1 = min(r1, h + halo - (y0 - halo));
+#pragma unroll 3
+    for (int ry = r0; ry < r1; ry++) {
+      const uint4 ty = s_yt[ry];
+      const uint32_t* q0 = (const uint32_t*)(p0 + ty.x);
+      const uint32_t* q1 = (const uint32_t*)(p0 + ty.y);
+      const uint32_t t0 = prmt(__ldg(q0), __ldg(q0 + 1), sel), t1 = prmt(__ldg(q1), __ldg(q1 + 1), sel);
+      const int h0a = (int)__dp2a_lo(xa0, t0, 0u), h0b = (int)__dp2a_hi(xa1, t0, 0u);
+      const int h1a = (int)__dp2a_lo(xa0, t1, 0u), h1b = (int)__dp2a_hi(xa1, t1, 0u);
+      const int va = ((((int)ty.z * (h0a >> 4)) >> 16) + (((int)ty.w * (h1a >> 4)) >> 16) + 2) >> 2;
+      const int vb = ((((int)ty.z * (h0b >> 4)) >> 16) + (((int)ty.w * (h1b >> 4)) >> 16) + 2) >> 2;
+      *(uint16_t*)(s_res + ry * A_RP + col) = (uint16_t)(min(va, 255) | (min(vb, 255) << 8));
+    }
+  };
+  if (P.W <= 3 * w) {
+    const int quarter = tid >> 6, rows_q = (rh + 3) >> 2;
+    resize_pair(2 * (tid & 63), quarter * rows_q, min(rh, (quarter + 1) * rows_q));
+    if (rw > A_TW)                                     // the 4 extra halo columns: 2 pairs x rh rows, one item per thread
+      for (int extra = tid; extra < 2 * rh; extra += A_THREADS)
+        resize_pair(A_TW + 2 * (extra & 1), extra >> 1, (extra >> 1) + 1);
+  } else {
     const int half = tid >> 7, rows_half = (rh + 1) >> 1;
     resize_column(tid & 127, half * rows_half, min(rh, (half + 1) * rows_half));
     if (rw > A_TW)                                     // the 4 extra halo columns: 4 x rh pixels, one per thread
