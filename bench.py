@@ -209,7 +209,10 @@ def run_reference(args, rank):
                              "sample": "%d synthetic frames per step, frame-parallel over %d threads" % (sample, cores)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
+
+
+JSON_OUT = sys.stdout
 
 
 def main():
@@ -448,11 +451,16 @@ def main():
                                 "sample": "%d passes over %d synthetic frames of the workload, frame-parallel over %d threads, %.1f s"
                                           % (passes, sample, cores, dt * passes)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
+    # stdout carries the JSON line and nothing else: libraries that write to file descriptor 1 themselves (NCCL prints a
+    # version banner there) are pointed at stderr, the line goes to a private duplicate of the original stdout
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     main()
