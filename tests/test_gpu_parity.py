@@ -78,6 +78,24 @@ def test_pyramid_pixels_bit_exact(V, O, kitti0, shape, blur):
     c.close()
 
 
+def test_pyramid_every_width_residue(V, O):
+    """Every width mod 16 (row padding 1..16 bytes, so the last source words of a row sit at every distance from the
+    end of the pitch) and tile edges that fall anywhere: both resize paths of k_pyramid (column pairs from word loads
+    while a level shrinks by <= 3, byte gathers below) against the oracle, with and without the blur."""
+    for w in range(129, 161):
+        h = 67 + (w % 5)
+        img = noise_image(h, w, 1000 + w)
+        for blur in (1, 0):
+            c = V.Context(V.make_params(nfeatures=200, nlevels=8, blur_levels=blur, max_width=w, max_height=h))
+            c.detect_and_compute(img)
+            p = O.params(nlevels=8, blur_levels=blur)
+            for l in range(8):
+                got, ref = c.get_level(0, l, w, h), O.build_level(img, p, l)
+                assert got.shape == ref.shape
+                assert np.array_equal(got, ref), "w %d blur %d level %d differs in %d px" % (w, blur, l, int((got != ref).sum()))
+            c.close()
+
+
 def test_pyramid_matches_cv2_golden_hashes(V, golden, kitti0, kitti1, ctx_kitti):
     import hashlib
     for tag, img in (("k0", kitti0), ("k1", kitti1)):
@@ -301,6 +319,35 @@ def test_device_resident_batch_through_torch_pointers(V, O):
         assert np.array_equal(k[f, :n[f], 0], k_ref[f, :n[f]]["x"]) and np.array_equal(k[f, :n[f], 1], k_ref[f, :n[f]]["y"])
         assert np.array_equal(dd[f, :n[f]], d_ref[f, :n[f]])
     assert c.launch_count() == 2 * 5                                       # 5 kernels x 2 chunks
+    c.close()
+
+
+@pytest.mark.parametrize("W", [175, 176 - 3, 161])
+def test_device_frames_with_minimal_row_padding(V, O, W):
+    """Device-resident frames whose pitch leaves 1, 3 or 15 spare bytes per row are read in place (no staging copy):
+    the word loads of k_pyramid / k_harris must stay inside each row."""
+    import torch
+    F, H, cap, pitch = 3, 90, 600, 176
+    rng = np.random.default_rng(W)
+    frames = rng.integers(0, 256, (F, H, pitch), dtype=np.uint8)
+    c = V.Context(V.make_params(nfeatures=500, nlevels=6, max_width=W, max_height=H, max_batch=F))
+    d_frames = torch.from_numpy(frames).cuda()
+    d_k = torch.zeros(F, cap, 2, dtype=torch.int32, device="cuda")
+    d_a = torch.zeros(F, cap, dtype=torch.float32, device="cuda")
+    d_d = torch.zeros(F, cap, 32, dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(F, dtype=torch.int32, device="cuda")
+    c.set_stream(torch.cuda.current_stream().cuda_stream)
+    c.detect_and_compute_batch_ptr(d_frames.data_ptr(), 1, F, W, H, pitch, H * pitch, cap, d_k.data_ptr(),
+                                   d_a.data_ptr(), d_d.data_ptr(), d_n.data_ptr(), 1)
+    c.synchronize()
+    p = O.params(nfeatures=500, nlevels=6)
+    n_ref, k_ref, a_ref, d_ref = O.detect_and_compute_batch(np.ascontiguousarray(frames[:, :, :W]), p, cap, 2, keep=True)
+    n, k, a, dd = d_n.cpu().numpy(), d_k.cpu().numpy(), d_a.cpu().numpy(), d_d.cpu().numpy()
+    assert np.array_equal(n, n_ref) and n.min() > 100
+    for f in range(F):
+        assert np.array_equal(k[f, :n[f], 0], k_ref[f, :n[f]]["x"]) and np.array_equal(k[f, :n[f], 1], k_ref[f, :n[f]]["y"])
+        assert np.array_equal(bits(a[f, :n[f]]), bits(a_ref[f, :n[f]]))
+        assert np.array_equal(dd[f, :n[f]], d_ref[f, :n[f]])
     c.close()
 
 
