@@ -360,20 +360,24 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
   if (l == 0) { img = B.frames + (size_t)f * B.frame_stride; pitch = B.pitch0; }
   else { img = B.pyr + (size_t)f * P.pyr_frame_bytes + G.lvl_ofs; pitch = G.pitch; }
 
-  // ---- phase 0/1: clear the score map, stage the tile (16-byte loads; rows reflect-101) -------
-  for (int i = tid; i < B_SCORE_BYTES / 16; i += B_THREADS) ((uint4*)s_score)[i] = make_uint4(0, 0, 0, 0);
-  if (tid < 3) s_ctr[tid] = 0;
-  if (tid < B_TW) s_ey[tid] = 0;
+  // ---- phase 0/1: stage the tile (16-byte asynchronous copies global -> shared, rows reflect-101, columns outside the
+  // pitch zero-filled by a zero source size) and clear the score map while the copies are in flight ------------------
   for (int it = tid; it < B_PH * (B_SP / 16); it += B_THREADS) {
     const int py = it / (B_SP / 16), c = it - py * (B_SP / 16);
     const int xs = x0 - 16 + 16 * c;
     int y = y0 - 4 + py;                         // reflect-101 rows (one bounce is enough for a 4-pixel halo)
     y = y < 0 ? -y : (y >= h ? 2 * h - 2 - y : y);
     y = min(max(y, 0), h - 1);
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (xs >= 0 && xs < pitch) v = __ldg((const uint4*)(img + (size_t)y * pitch + xs));
-    *(uint4*)(s_pix + py * B_SP + 16 * c) = v;
+    const bool in = xs >= 0 && xs < pitch;
+    const uint8_t* g = img + (size_t)y * pitch + (in ? xs : 0);
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(s_pix + py * B_SP + 16 * c);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(g), "r"(in ? 16 : 0) : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = tid; i < B_SCORE_BYTES / 16; i += B_THREADS) ((uint4*)s_score)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < 3) s_ctr[tid] = 0;
+  if (tid < B_TW) s_ey[tid] = 0;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   // ---- phase 2: compass pretest, 8 pixels per item -------------------------------------------
