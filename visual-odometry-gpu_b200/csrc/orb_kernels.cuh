@@ -164,6 +164,10 @@ __device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<
 constexpr int A_TW = 128, A_TH = 64, A_THREADS = 256;
 constexpr int A_RW = A_TW + 4, A_RH = A_TH + 4;   // resized region incl. blur halo 2
 constexpr int A_RP = 136;                          // shared pitch of resized rows (bytes)
+#ifndef ORB_A_UNROLL
+#define ORB_A_UNROLL 3
+#endif
+constexpr int A_UNROLL = ORB_A_UNROLL;             // rows of the column-pair resize loop in flight together
 #ifndef ORB_A_SEG
 #define ORB_A_SEG 4
 #endif
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
     const uint8_t* p0 = src + base;
     asm volatile("" : "+l"(p0));
     r1 = min(r1, h + halo - (y0 - halo));
-#pragma unroll 3
+#pragma unroll (A_UNROLL)
     for (int ry = r0; ry < r1; ry++) {
       const uint4 ty = s_yt[ry];
       const uint32_t* q0 = (const uint32_t*)(p0 + ty.x);
