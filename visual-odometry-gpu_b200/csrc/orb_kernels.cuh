@@ -610,7 +610,13 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
       const int ncol = min(B_TW, w - 4 - x0);
       const uint8_t* r = s_pix + (iy + 4) * B_SP + 16;
       unsigned acc = 0;
-      for (int c = 0; c < ncol; c += 16) {
+      int c = 0;
+      for (; c + 16 <= ncol; c += 16) {              // whole 16-byte groups: four dot products with ones
+        const uint4 v = *(const uint4*)(r + c);
+        acc = __dp4a(v.x, 0x01010101u, acc); acc = __dp4a(v.y, 0x01010101u, acc);
+        acc = __dp4a(v.z, 0x01010101u, acc); acc = __dp4a(v.w, 0x01010101u, acc);
+      }
+      if (c < ncol) {                                // last, partial group of the level's right edge
         const uint4 v = *(const uint4*)(r + c);
         const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
