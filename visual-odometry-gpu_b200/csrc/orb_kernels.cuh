@@ -128,14 +128,16 @@ __device__ __forceinline__ int fast_ring_score(const uint8_t* __restrict__ c, in
   constexpr int ring_dy[16] = {-3, -3, -2, -1, 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3};
   const int Ip = c[0];
   const int hi = Ip + thr, lo = Ip - thr;
-  uint32_t mb = 0, md = 0, sad = 0;
+  uint32_t nb = 0, nd = 0, sad = 0;
 #pragma unroll
   for (int i = 0; i < 16; i++) {
-    int v = c[ring_dy[i] * SP + ring_dx[i]];
-    if (v >= hi) mb |= 1u << i;
-    if (v <= lo) md |= 1u << i;
+    const int v = c[ring_dy[i] * SP + ring_dx[i]];
+    nb = __funnelshift_l((uint32_t)(v - hi), nb, 1);   // shifts in the sign of v - hi: 1 = not brighter
+    nd = __funnelshift_l((uint32_t)(lo - v), nd, 1);   // 1 = not darker
     sad = __usad(v, Ip, sad);
   }
+  // ring pixel i sits at bit 15 - i: the circle runs the other way round, which the arc test does not see
+  uint32_t mb = ~nb & 0xffffu, md = ~nd & 0xffffu;
   mb |= mb << 16;
   md |= md << 16;
   uint32_t rb, rd;
