@@ -152,6 +152,8 @@ __device__ __forceinline__ int fast_ring_score(const uint8_t* __restrict__ c, in
 }
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
+// bytes 1 and 3 of w as two 16-bit lanes, (w >> 8) & 0x00ff00ff, in one byte permute
+__device__ __forceinline__ uint32_t odd_bytes(uint32_t w) { return __byte_perm(w, 0u, 0x4341); }
 __device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -294,8 +296,8 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
         const uint32_t w2 = *(const uint32_t*)(r + 8);
         r += A_RP;
         const uint32_t v1 = prmt(w01.x, w01.y, 0x5432), v2 = prmt(w01.y, w2, 0x5432);
-        const uint32_t q0 = w01.x & M, q1 = (w01.x >> 8) & M, q2 = v1 & M, q3 = (v1 >> 8) & M, q4 = w01.y & M,
-                       q5 = (w01.y >> 8) & M, q6 = v2 & M, q7 = (v2 >> 8) & M, q8 = w2 & M, q9 = (w2 >> 8) & M;
+        const uint32_t q0 = w01.x & M, q1 = odd_bytes(w01.x), q2 = v1 & M, q3 = odd_bytes(v1), q4 = w01.y & M,
+                       q5 = odd_bytes(w01.y), q6 = v2 & M, q7 = odd_bytes(v2), q8 = w2 & M, q9 = odd_bytes(w2);
         uint4 o;
         o.x = q0 + q4 + 4 * (q1 + q3) + 6 * q2;
         o.y = q1 + q5 + 4 * (q2 + q4) + 6 * q3;
@@ -580,8 +582,8 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
         const uint2 cc = *(const uint2*)rc;
         rc += B_SP;
         const uint32_t w0 = prmt(m, cc.x, 0x5432), w1 = prmt(cc.x, cc.y, 0x5432), w2 = prmt(cc.y, p, 0x5432);
-        const uint32_t q0 = w0 & M, q1 = (w0 >> 8) & M, q2 = cc.x & M, q3 = (cc.x >> 8) & M, q4 = w1 & M, q5 = (w1 >> 8) & M,
-                       q6 = cc.y & M, q7 = (cc.y >> 8) & M, q8 = w2 & M, q9 = (w2 >> 8) & M;
+        const uint32_t q0 = w0 & M, q1 = odd_bytes(w0), q2 = cc.x & M, q3 = odd_bytes(cc.x), q4 = w1 & M, q5 = odd_bytes(w1),
+                       q6 = cc.y & M, q7 = odd_bytes(cc.y), q8 = w2 & M, q9 = odd_bytes(w2);
         // horizontal 5-sums from shared pair sums: (o0,o2) = (p-2+p-1, p0+p1) + (p0+p1, p2+p3) + (p2, p4), ...
         const uint32_t t1 = q0 + q1, t2 = q2 + q3, t3 = q4 + q5, t4 = q6 + q7, t5 = q8 + q9;
         uint4 o;
