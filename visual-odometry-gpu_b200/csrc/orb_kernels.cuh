@@ -346,7 +346,7 @@ constexpr int B_LIST = ORB_B_LIST;     // pretest passers kept in the list; dens
 constexpr int B_SURV = 1024;
 constexpr int B_PIX_BYTES = B_PH * B_SP, B_SCORE_BYTES = B_SH * B_SCP * 2;
 constexpr int B_LIST_BYTES = B_LIST * 2;
-constexpr int B_SMEM = B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES + B_SURV * 2 + 16 + B_TW * 4;   // 37.7 KB and 40 registers -> 6 CTAs / SM
+constexpr int B_SMEM = B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES + B_SURV * 2 + 16 + B_TW * 4 + 64;   // 37.7 KB and 40 registers -> 6 CTAs / SM
 
 __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P, const Bufs B) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
   uint16_t* s_surv = (uint16_t*)(smem + B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES);
   int* s_ctr = (int*)(s_surv + B_SURV);   // [0] pretest list, [1] survivor list, [2] global base
   int* s_ey = s_ctr + 4;                  // [B_TW] column-strip sums of this tile (phase 5/6)
+  uint16_t* s_tab = (uint16_t*)(s_ey + B_TW);   // [32] passer bit -> tile offset (phase 2)
 
   const int tid = threadIdx.x, lane = tid & 31, f = blockIdx.y;
   const uint32_t tt = __ldg(B.tile_b + blockIdx.x);
@@ -385,6 +386,8 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
   for (int i = tid; i < B_SCORE_BYTES / 16; i += B_THREADS) ((uint4*)s_score)[i] = make_uint4(0, 0, 0, 0);
   if (tid < 3) s_ctr[tid] = 0;
   if (tid < B_TW) s_ey[tid] = 0;
+  // passer bit b of a thread's mask word: row item b >> 3 (rows 14 apart), pixel 0,2,4,6,1,3,5,7 for b & 7 = 0..7
+  if (tid < 32) s_tab[tid] = (uint16_t)((tid >> 3) * (14 * B_SP) + ((tid & 3) << 1) + ((tid >> 2) & 1));
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
@@ -394,6 +397,7 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
   const int thr = P.fast_threshold, fn = P.fast_n;
   {
     constexpr int NG = 18, NRT = 14, NK = (B_SH + NRT - 1) / NRT;
+    static_assert(NRT == 14, "s_tab is filled for rows 14 apart");
     const uint32_t K = 0x64646464u;   // half(1024 + p) = 0x6400 | p
     // Two equivalent formulations share the work between the ALU pipe (HMNMX2 / HSET2) and the half-precision adder:
     // (a) ">= 3 of 4 have v >= Ip + thr" <=> the second smallest of the four >= Ip + thr (min/max network);
@@ -477,13 +481,13 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
       while (mlo) {
         const int b = __ffs(mlo) - 1;
         mlo &= mlo - 1;
-        if (off < B_LIST) s_list[off] = (uint16_t)(e0 + (b >> 3) * (NRT * B_SP) + ((b & 3) << 1) + ((b >> 2) & 1));
+        if (off < B_LIST) s_list[off] = (uint16_t)(e0 + s_tab[b]);
         off++;
       }
       while (mhi) {
         const int b = __ffs(mhi) - 1;
         mhi &= mhi - 1;
-        if (off < B_LIST) s_list[off] = (uint16_t)(e0 + (4 + (b >> 3)) * (NRT * B_SP) + ((b & 3) << 1) + ((b >> 2) & 1));
+        if (off < B_LIST) s_list[off] = (uint16_t)(e0 + 4 * NRT * B_SP + s_tab[b]);
         off++;
       }
     }
