@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
       const int h0 = __ldg(q0) * a0 + __ldg(q0 + 1) * a1;
       const int h1 = __ldg(q1) * a0 + __ldg(q1 + 1) * a1;
       const int v = ((((int)ty.z * (h0 >> 4)) >> 16) + (((int)ty.w * (h1 >> 4)) >> 16) + 2) >> 2;
-      s_res[ry * A_RP + col] = (uint8_t)min(v, 255);
+      s_res[ry * A_RP + col] = (uint8_t)v;   // <= 255 without a clamp: weights sum to <= 2049 per axis, so v <= (floor(2049 * (255 * 2049 >> 4) / 65536) + 2) >> 2 = 255
     }
   };
   // Two adjacent columns at once when the level shrinks by at most 3 (source columns of neighbours are then <= 3 apart):
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
       const int h1a = (int)__dp2a_lo(xa0, t1, 0u), h1b = (int)__dp2a_hi(xa1, t1, 0u);
       const int va = ((((int)ty.z * (h0a >> 4)) >> 16) + (((int)ty.w * (h1a >> 4)) >> 16) + 2) >> 2;
       const int vb = ((((int)ty.z * (h0b >> 4)) >> 16) + (((int)ty.w * (h1b >> 4)) >> 16) + 2) >> 2;
-      *(uint16_t*)(s_res + ry * A_RP + col) = (uint16_t)(min(va, 255) | (min(vb, 255) << 8));
+      *(uint16_t*)(s_res + ry * A_RP + col) = (uint16_t)(va | (vb << 8));   // va, vb <= 255 (see resize_column)
     }
   };
   if (P.W <= 3 * w) {
