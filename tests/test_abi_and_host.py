@@ -117,3 +117,20 @@ def test_frame_sharding_world_size_2_gloo(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29611", str(script), ROOT],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "GLOO_OK" in r.stdout, r.stdout[-3000:]
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU port on the host cores) must put exactly one JSON line on stdout, with the
+    keys the driver reads; anything a library writes to file descriptor 1 is routed to stderr."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "orb_frames_per_s" and d["unit"] == "frames/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("kitti_synth_1241x376_L8_N2000")
