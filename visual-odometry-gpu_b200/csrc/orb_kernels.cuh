@@ -163,8 +163,10 @@ __device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<
 
 // =============================================================================================
 // Kernel A: pyramid level l >= 1 = GaussianBlur5x5( resize_linear(level 0) )  (ref src/orb_cpu.cpp:283-290).
-// One CTA per 128x64 output tile.  Bilinear taps come from host tables (no floating point on the device);
-// the blur runs in 16-bit lanes, two pixels per register, and each level is written exactly once.
+// One CTA per 128x64 output tile.  Bilinear taps come from host tables (no floating point on the device).  Resize:
+// two adjacent columns per thread from two aligned source words per row (PRMT + IDP.2A) while the level shrinks by
+// <= 3, one column per thread from byte loads below that.  Blur: 16-bit lanes, two pixels per register, horizontal
+// sums kept in a five-row register window; each level is written exactly once.
 constexpr int A_TW = 128, A_TH = 64, A_THREADS = 256;
 constexpr int A_RW = A_TW + 4, A_RH = A_TH + 4;   // resized region incl. blur halo 2
 constexpr int A_RP = 136;                          // shared pitch of resized rows (bytes)
@@ -321,13 +323,13 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
 }
 
 // =============================================================================================
-// Kernel B: FAST-n + SAD score + 3x3 NMS + Harris response + 5x5 box sums on one 128x64 tile of one level.
+// Kernel B: FAST-n + SAD score + 3x3 NMS + 5x5 box sums on one 128x64 tile of one level (tile staged by cp.async).
 //   pretest  : the >=3-of-4 compass test (ref src/orb_cpu.cpp:39-58) on packed half2 (2 pixels / instruction):
-//              second smallest / second largest of the four compass pixels against Ip +- thr;
+//              second smallest / second largest of the four compass pixels against Ip +- thr, or saturated counts;
 //   ring     : passers are compacted into a shared list and finished one pixel per thread (arc + SAD);
-//   NMS      : score == max of its 3x3 window, ties keep both (:126); survivors get their Harris response
-//              from the tile in shared memory and are appended to the level's candidate list;
-//   box sums : 5x5 sums of the level (u16) for BRIEF, 16-bit lanes, written once.
+//   NMS      : score == max of its 3x3 window, ties keep both (:126); survivors are appended to the level's
+//              candidate list (k_harris adds their response);
+//   box sums : 5x5 sums of the level (u16) for BRIEF, 16-bit lanes, written once; strip tables for the border rule.
 constexpr int B_TW = 128, B_TH = 64, B_THREADS = 256;
 constexpr int B_SP = 160;              // pixel tile pitch (bytes); pixel x sits at column x - x0 + 16
 constexpr int B_PH = B_TH + 8;         // rows y0-4 .. y0+B_TH+3
