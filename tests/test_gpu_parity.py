@@ -417,6 +417,17 @@ def test_full_path_other_scale_factors(V, O, kitti0, f, L):
     c.close()
 
 
+def test_sixteen_levels(V, O, kitti0):
+    """nlevels == ORB_MAX_LEVELS (16): the prefix of the per-level kept counts in k_describe spans all 32 lanes, so the
+    total includes level 0 (a 16-lane scan dropped it: ADVICE r1)."""
+    img = kitti0[:300, :700]
+    c = V.Context(V.make_params(nfeatures=1500, scaleFactor=1.12, nlevels=16, max_width=700, max_height=300, keep_side_arrays=1))
+    p = O.params(nfeatures=1500, scale_factor=1.12, nlevels=16)
+    n = _compare_full(c, O, img, p, c.max_kp)
+    assert n > 1000
+    c.close()
+
+
 def test_shape_changes_on_one_context(V, O, kitti0):
     """A context re-plans (level geometry, tap and tile tables) whenever the frame shape changes."""
     c = V.Context(V.make_params(nfeatures=800, nlevels=6, max_width=1241, max_height=376, max_batch=3, keep_side_arrays=1))

@@ -169,6 +169,49 @@ void fill_bufs(orb_ctx* ctx, Bufs* B) {
   B->zero_stride = (int)(ctx->zero_bytes_per_frame / sizeof(int)); B->kept_xy = ctx->d_kept_xy; B->kept_r = ctx->d_kept_r; B->kept_count = ctx->d_kept_count;
   B->xtab = ctx->d_xtab; B->ytab = ctx->d_ytab; B->tile_a = ctx->d_tile_a; B->tile_b = ctx->d_tile_b; B->pattern = ctx->d_pattern;
   B->flags = ctx->d_flags;
+  B->tmaps = ctx->d_tmaps; B->frame0 = 0;
+}
+
+// ---- TMA tensor maps -----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 3-D map (x, y, frame) over `n` images of w x h elements; out-of-range elements read as zero
+int encode_map(orb_ctx* ctx, CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, int w, int h, int n,
+               size_t pitch_bytes, size_t frame_bytes, int box_w, int box_h) {
+  if ((uintptr_t)base % 16 || pitch_bytes % 16 || frame_bytes % 16 || (size_t)box_w * esize % 16 || box_w > 256 || box_h > 256)
+    return fail(ctx, ORB_E_INVALID, "tensor map geometry not TMA-compatible (base %p pitch %zu stride %zu box %dx%d)", base, pitch_bytes,
+                frame_bytes, box_w, box_h);
+  cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)std::max(n, 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch_bytes, (cuuint64_t)frame_bytes};
+  cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = ((EncodeTiledFn)ctx->tmap_encode)(m, dt, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, ORB_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return ORB_OK;
+}
+
+// (re-)encode the maps of plan P for level-0 frames at `base` (n frames, row pitch / frame stride in bytes); the arena
+// levels and box-sum images are fixed per plan.  Stream-ordered upload: earlier launches keep the maps they were given.
+int update_tmaps(orb_ctx* ctx, const OrbPlan& P, const uint8_t* base, size_t pitch, size_t stride, int n) {
+  const orb_ctx::TmapKey key{base, pitch, stride, n, P.W, P.H, P.nlevels, P.patch_radius};
+  if (!memcmp(&key, &ctx->tmap_key, sizeof(key))) return ORB_OK;
+  memset(&ctx->tmap_key, 0, sizeof(ctx->tmap_key));
+  int rc;
+  for (int l = 0; l < P.nlevels; l++) {
+    const OrbLevel& G = P.lv[l];
+    const uint8_t* img = l == 0 ? base : ctx->d_pyr + G.lvl_ofs;
+    const size_t ip = l == 0 ? pitch : (size_t)G.pitch, is = l == 0 ? stride : (size_t)P.pyr_frame_bytes;
+    const int in = l == 0 ? n : ctx->chunk;
+    if ((rc = encode_map(ctx, &ctx->h_tmaps[orbk::TM_PIX + l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, img, G.w, G.h, in, ip, is, orbk::B_SP,
+                         orbk::B_PH)))
+      return rc;
+  }
+  CK(cudaMemcpyAsync(ctx->d_tmaps, ctx->h_tmaps, sizeof(ctx->h_tmaps), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->tmap_key = key;
+  return ORB_OK;
 }
 
 // event bracket around one kernel launch (only when profiling is on)
@@ -261,7 +304,7 @@ int stage_image(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch) {
   return ORB_OK;
 }
 
-void stage_plan(orb_ctx* ctx, int w, int h, int policy, int quota, OrbPlan* P, Bufs* B) {
+int stage_plan(orb_ctx* ctx, int w, int h, int policy, int quota, OrbPlan* P, Bufs* B) {
   build_plan(ctx->p, w, h, 1, policy, quota, P);
   P->lv[0].cand_cap = ctx->max_plan.lv[0].cand_cap;
   fill_bufs(ctx, B);
@@ -273,8 +316,13 @@ void stage_plan(orb_ctx* ctx, int w, int h, int policy, int quota, OrbPlan* P, B
     B->tile_b = ctx->d_tile_b1;
   }
   B->frames = ctx->d_frames; B->frame_stride = ctx->frames_slot_bytes; B->pitch0 = ctx->frames_pitch;
+  {
+    const int rc = update_tmaps(ctx, *P, ctx->d_frames, (size_t)ctx->frames_pitch, ctx->frames_slot_bytes, ctx->p.max_batch);
+    if (rc) return rc;
+  }
   B->out_kps = ctx->d_kps; B->out_angles = ctx->d_angles; B->out_desc = ctx->d_desc; B->out_n = ctx->d_nout;
   B->out_cap = ctx->list_cap;
+  return ORB_OK;
 }
 
 }  // namespace
@@ -302,7 +350,7 @@ void orb_destroy(orb_ctx* ctx) {
   void* ptrs[] = {ctx->d_frames, ctx->d_pyr, ctx->d_box, ctx->d_cand, ctx->d_cand_count, ctx->d_kept_xy, ctx->d_kept_r,
                   ctx->d_kept_count, ctx->d_xtab, ctx->d_ytab, ctx->d_tile_a, ctx->d_tile_b, ctx->d_tile_b1, ctx->d_harris_w, ctx->d_pattern, ctx->d_flags, ctx->d_kps,
                   ctx->d_angles, ctx->d_desc, ctx->d_nout, ctx->d_side_xy, ctx->d_side_level, ctx->d_side_resp,
-                  ctx->d_list_kps, ctx->d_list_angles, ctx->d_list_out};
+                  ctx->d_list_kps, ctx->d_list_angles, ctx->d_list_out, ctx->d_tmaps};
   for (void* q : ptrs) if (q) cudaFree(q);
   for (auto& sp : ctx->spans) { if (sp.a) cudaEventDestroy(sp.a); if (sp.b) cudaEventDestroy(sp.b); }
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
@@ -416,6 +464,12 @@ int orb_create(const orb_params* p, orb_ctx** out) {
     CK(cudaMalloc(&ctx->d_harris_w, sizeof(float) * 49));
     CK(cudaMalloc(&ctx->d_pattern, sizeof(float4) * 256));
     CK(cudaMalloc(&ctx->d_flags, sizeof(int)));
+    CK(cudaMalloc(&ctx->d_tmaps, sizeof(ctx->h_tmaps)));
+    {
+      cudaDriverEntryPointQueryResult q;
+      CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ctx->tmap_encode, cudaEnableDefault, &q));
+      if (q != cudaDriverEntryPointSuccess || !ctx->tmap_encode) return fail(ctx, ORB_E_CUDA, "driver has no cuTensorMapEncodeTiled (TMA)");
+    }
     CK(cudaMallocHost(&ctx->h_flags, sizeof(int)));
     ctx->list_cap = std::max(ORB_SORT_CAP, Bn * ctx->max_kp);
     size_t nrec = (size_t)ctx->list_cap;
@@ -544,6 +598,8 @@ int orb_internal_run_batch(orb_ctx* ctx, const uint8_t* frames, int frames_on_de
   orb_descriptor* o_desc = outputs_on_device ? desc : ctx->d_desc;
   int* o_n = outputs_on_device ? n_out : ctx->d_nout;
 
+  if ((rc = update_tmaps(ctx, P, src, (size_t)sp, stride, direct ? n_frames : ctx->p.max_batch))) return rc;
+
   int total_quota = 0;
   for (int l = 0; l < P.nlevels; l++) total_quota += P.lv[l].quota;
   const int nwarps = std::min(total_quota, cap);
@@ -606,7 +662,7 @@ int orb_internal_run_batch(orb_ctx* ctx, const uint8_t* frames, int frames_on_de
     if (!direct) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[ci], 0));
     Bufs B;
     fill_bufs(ctx, &B);
-    B.frames = src + (size_t)c0 * stride; B.frame_stride = stride; B.pitch0 = sp;
+    B.frames = src + (size_t)c0 * stride; B.frame_stride = stride; B.pitch0 = sp; B.frame0 = c0;
     B.out_kps = o_kps + (size_t)c0 * cap; B.out_angles = o_ang + (size_t)c0 * cap; B.out_desc = o_desc + (size_t)c0 * cap;
     B.out_n = o_n + c0; B.out_cap = cap;
     if (ctx->p.keep_side_arrays) {
@@ -734,7 +790,7 @@ int orb_fast_detect(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch
   int rc = stage_image(ctx, img, w, h, pitch);
   if (rc) return rc;
   OrbPlan P; Bufs B;
-  stage_plan(ctx, w, h, ORB_SELECT_RASTER_FIRST_N, nfeatures, &P, &B);
+  if ((rc = stage_plan(ctx, w, h, ORB_SELECT_RASTER_FIRST_N, nfeatures, &P, &B))) return rc;
   if ((rc = launch_pyramid_fast(ctx, P, B, 1))) return rc;
   if ((rc = launch_select(ctx, P, B, 1))) return rc;
   int m = 0;
@@ -774,7 +830,7 @@ static int describe_list(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t 
   for (int i = 0; i < n; i++)
     if (kps[i].x < 0 || kps[i].x >= w || kps[i].y < 0 || kps[i].y >= h) return fail(ctx, ORB_E_INVALID, "keypoint %d outside the image", i);
   OrbPlan P; Bufs B;
-  stage_plan(ctx, w, h, ORB_SELECT_RASTER_FIRST_N, 0, &P, &B);
+  if ((rc = stage_plan(ctx, w, h, ORB_SELECT_RASTER_FIRST_N, 0, &P, &B))) return rc;
   if (desc_out && (rc = launch_pyramid_fast(ctx, P, B, 1))) return rc;   // builds the box-sum image of the frame
   for (int o = 0; o < n; o += ctx->list_cap) {
     int m = std::min(ctx->list_cap, n - o);

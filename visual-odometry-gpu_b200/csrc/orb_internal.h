@@ -4,6 +4,7 @@
 //   orb_ingest.cu : PNG ingest, host and device decode                                 (kernels: orb_ingest_kernels.cuh)
 //   orb_lk.cu     : pyramidal Lucas-Kanade tracker                                     (kernels: orb_lk_kernels.cuh)
 #pragma once
+#include <cuda.h>            // CUtensorMap only: the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked
 #include <cuda_runtime.h>
 
 #include <cstdarg>
@@ -36,6 +37,10 @@ struct orb_ctx {
   orb_keypoint* d_side_xy = nullptr; int* d_side_level = nullptr; float* d_side_resp = nullptr;
   orb_keypoint* d_list_kps = nullptr; float* d_list_angles = nullptr; float* d_list_out = nullptr; int list_cap = 0;
   float harris_w[49];
+  // TMA tensor maps (orb_kernels.cuh: TM_*): device copy, host mirror and the geometry they were encoded for
+  CUtensorMap* d_tmaps = nullptr; CUtensorMap h_tmaps[3 * ORB_MAX_LEVELS];
+  void* tmap_encode = nullptr;     // cuTensorMapEncodeTiled
+  struct TmapKey { const void* base; size_t pitch, stride; int n, W, H, nlevels, patch_radius; } tmap_key = {nullptr, 0, 0, 0, 0, 0, 0, 0};
   // last detect call (for the read-back entry points)
   int last_n = 0, last_chunk_start = 0, last_chunk_n = 0, last_cap = 0;
   const uint8_t* last_frames = nullptr; size_t last_stride = 0; int last_pitch = 0;

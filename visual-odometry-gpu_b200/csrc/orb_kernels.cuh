@@ -16,6 +16,7 @@
 // plus k_match (exact Hamming 2-NN, the step after the descriptors: ref flann->knnMatch, src/feature_matching.cpp:168)
 // and two helpers for the single-image stage entry points (k_harris_list, k_eval_math).
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -52,7 +53,34 @@ struct Bufs {
   orb_keypoint* side_xy;         // nullable side arrays, [chunk][out_cap]
   int* side_level;
   float* side_resp;
+  const CUtensorMap* tmaps;      // TMA tensor maps, [3][ORB_MAX_LEVELS]: TM_PIX, TM_BOXW, TM_PATCH per level
+  int frame0;                    // index of the wave's first frame inside the level-0 tensor (the whole source batch)
 };
+
+// Tensor maps (3-D: x, y, frame; out-of-range elements read as 0).  TMA wants the box start 16-byte aligned in x.
+//   TM_PIX(l)  : u8 level image, box 160 x 72  -- the k_fast tile incl. halo (x0 - 16, y0 - 4)
+constexpr int TM_PIX = 0, TM_BOXW = ORB_MAX_LEVELS, TM_PATCH = 2 * ORB_MAX_LEVELS;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra WAIT_%=;\n}\n" ::"r"(smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
+// one box of a 3-D tensor map -> shared memory (dst 128-byte aligned), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 
 __device__ __forceinline__ int reflect101(int i, int n) {
   if (n == 1) return 0;
@@ -348,17 +376,18 @@ constexpr int B_LIST = ORB_B_LIST;     // pretest passers kept in the list; dens
 constexpr int B_SURV = 1024;
 constexpr int B_PIX_BYTES = B_PH * B_SP, B_SCORE_BYTES = B_SH * B_SCP * 2;
 constexpr int B_LIST_BYTES = B_LIST * 2;
-constexpr int B_SMEM = B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES + B_SURV * 2 + 16 + B_TW * 4 + 64;   // 37.7 KB and 40 registers -> 6 CTAs / SM
+constexpr int B_SMEM = B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES + B_SURV * 2 + 16 + B_TW * 4 + 64 + 16;   // 37.7 KB and 40 registers -> 6 CTAs / SM
 
 __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P, const Bufs B) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  uint8_t* s_pix = smem;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* s_pix = smem;                  // TMA destination: 128-byte aligned
   uint16_t* s_score = (uint16_t*)(smem + B_PIX_BYTES);
   uint16_t* s_list = (uint16_t*)(smem + B_PIX_BYTES + B_SCORE_BYTES);
   uint16_t* s_surv = (uint16_t*)(smem + B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES);
   int* s_ctr = (int*)(s_surv + B_SURV);   // [0] pretest list, [1] survivor list, [2] global base
   int* s_ey = s_ctr + 4;                  // [B_TW] column-strip sums of this tile (phase 5/6)
   uint16_t* s_tab = (uint16_t*)(s_ey + B_TW);   // [32] passer bit -> tile offset (phase 2)
+  uint64_t* s_bar = (uint64_t*)(s_tab + 32);    // mbarrier of the tile load
 
   const int tid = threadIdx.x, lane = tid & 31, f = blockIdx.y;
   const uint32_t tt = __ldg(B.tile_b + blockIdx.x);
@@ -366,32 +395,23 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
   const OrbLevel& G = P.lv[l];
   const int x0 = ((tt >> 4) & 0x3fff) * B_TW, y0 = (tt >> 18) * B_TH;
   const int w = G.w, h = G.h;
-  const uint8_t* __restrict__ img;
-  int pitch;
-  if (l == 0) { img = B.frames + (size_t)f * B.frame_stride; pitch = B.pitch0; }
-  else { img = B.pyr + (size_t)f * P.pyr_frame_bytes + G.lvl_ofs; pitch = G.pitch; }
 
-  // ---- phase 0/1: stage the tile (16-byte asynchronous copies global -> shared, rows reflect-101, columns outside the
-  // pitch zero-filled by a zero source size) and clear the score map while the copies are in flight ------------------
-  for (int it = tid; it < B_PH * (B_SP / 16); it += B_THREADS) {
-    const int py = it / (B_SP / 16), c = it - py * (B_SP / 16);
-    const int xs = x0 - 16 + 16 * c;
-    int y = y0 - 4 + py;                         // reflect-101 rows (one bounce is enough for a 4-pixel halo)
-    y = y < 0 ? -y : (y >= h ? 2 * h - 2 - y : y);
-    y = min(max(y, 0), h - 1);
-    const bool in = xs >= 0 && xs < pitch;
-    const uint8_t* g = img + (size_t)y * pitch + (in ? xs : 0);
-    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(s_pix + py * B_SP + 16 * c);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(g), "r"(in ? 16 : 0) : "memory");
+  // ---- phase 0/1: stage the tile with one TMA load (box 160 x 72 at (x0 - 16, y0 - 4); everything outside the level
+  // reads as 0 -- no valid output depends on it: FAST centres stay >= 3 pixels inside, the 5x5 sums that BRIEF may read
+  // have their centre >= 2 pixels inside) and clear the score map while the copy is in flight ---------------------------
+  if (tid == 0) {
+    mbar_init(s_bar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(s_bar, B_PIX_BYTES);
+    tma_load_3d(s_pix, B.tmaps + TM_PIX + l, s_bar, x0 - 16, y0 - 4, l == 0 ? f + B.frame0 : f);
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
   for (int i = tid; i < B_SCORE_BYTES / 16; i += B_THREADS) ((uint4*)s_score)[i] = make_uint4(0, 0, 0, 0);
   if (tid < 3) s_ctr[tid] = 0;
   if (tid < B_TW) s_ey[tid] = 0;
   // passer bit b of a thread's mask word: row item b >> 3 (rows 14 apart), pixel 0,2,4,6,1,3,5,7 for b & 7 = 0..7
   if (tid < 32) s_tab[tid] = (uint16_t)((tid >> 3) * (14 * B_SP) + ((tid & 3) << 1) + ((tid >> 2) & 1));
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
+  __syncthreads();          // the mbarrier is initialised for everybody
+  mbar_wait(s_bar, 0);
 
   // ---- phase 2: compass pretest, 8 pixels per item -------------------------------------------
   // Thread (g, rt) owns column group g (8 pixels from x0 - 8 + 8g) on rows rt, rt+14, ...; the column validity mask
@@ -1031,7 +1051,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32, ORB_K3_MINB) k_describe(const O
       const int c = lane < P.nlevels ? B.kept_count[f * ORB_MAX_LEVELS + lane] : 0;
       int incl = c;
 #pragma unroll
-      for (int d = 1; d < 16; d <<= 1) {
+      for (int d = 1; d < 32; d <<= 1) {                     // full 32-lane scan: lane 16 must see level 0 when nlevels == 16
         int v = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += v;
       }
