@@ -318,7 +318,7 @@ def test_device_resident_batch_through_torch_pointers(V, O):
     for f in range(F):
         assert np.array_equal(k[f, :n[f], 0], k_ref[f, :n[f]]["x"]) and np.array_equal(k[f, :n[f], 1], k_ref[f, :n[f]]["y"])
         assert np.array_equal(dd[f, :n[f]], d_ref[f, :n[f]])
-    assert c.launch_count() == 2 * 5                                       # 5 kernels x 2 chunks
+    assert c.launch_count() == 2 * 6                                       # 6 kernels x 2 chunks
     c.close()
 
 

@@ -87,7 +87,7 @@ void build_plan(const orb_params& p, int W, int H, int nlevels, int policy, int 
   P->fast_threshold = p.fast_threshold; P->fast_n = p.fast_n;
   P->nms_radius = p.nms_window / 2; P->patch_radius = p.orient_patch / 2;
   P->select_policy = policy; P->blur_levels = p.blur_levels; P->harris_k = p.harris_k;
-  int tile = 0, atile = 0, kept = 0, xo = 0, yo = 0, eo = 0;
+  int tile = 0, atile = 0, kept = 0, xo = 0, yo = 0, eo = 0, e2 = 0;
   unsigned long long lv = 0, bx = 0, cd = 0;
   for (int l = 0; l < nlevels; l++) {
     OrbLevel& G = P->lv[l];
@@ -108,12 +108,13 @@ void build_plan(const orb_params& p, int W, int H, int nlevels, int policy, int 
     G.kept_ofs = kept; kept += align_up(std::max(G.quota, 1), 4);
     G.xtab_ofs = xo; G.ytab_ofs = yo; xo += G.w; yo += G.h;
     G.edge_ofs = eo; G.edge_w = align_up(G.w, 4); eo += G.edge_w + align_up(G.h, 4);
+    G.edge2_ofs = e2; e2 += orbk::edge2_level_elems(G.edge_w, G.h);
     G.scale = level_scale(p.scale_factor, l);
     G.lvl_ofs = lv; if (l > 0) lv += (unsigned long long)align_up(G.h * G.pitch, 256);
     G.box_ofs = bx; bx += (unsigned long long)align_up((G.h + 1) * G.bpitch, 128);
     G.cand_ofs = cd; cd += (unsigned long long)align_up(G.cand_cap, 32);
   }
-  P->tiles_per_frame = tile; P->a_tiles_per_frame = atile; P->kept_per_frame = kept; P->edge_frame_elems = eo;
+  P->tiles_per_frame = tile; P->a_tiles_per_frame = atile; P->kept_per_frame = kept; P->edge_frame_elems = eo; P->edge2_frame_elems = e2;
   P->pyr_frame_bytes = std::max<unsigned long long>(lv, 256); P->box_frame_elems = bx; P->cand_frame_elems = cd;
 }
 
@@ -169,7 +170,7 @@ void fill_bufs(orb_ctx* ctx, Bufs* B) {
   B->zero_stride = (int)(ctx->zero_bytes_per_frame / sizeof(int)); B->kept_xy = ctx->d_kept_xy; B->kept_r = ctx->d_kept_r; B->kept_count = ctx->d_kept_count;
   B->xtab = ctx->d_xtab; B->ytab = ctx->d_ytab; B->tile_a = ctx->d_tile_a; B->tile_b = ctx->d_tile_b; B->pattern = ctx->d_pattern;
   B->flags = ctx->d_flags;
-  B->tmaps = ctx->d_tmaps; B->frame0 = 0;
+  B->tmaps = ctx->d_tmaps; B->frame0 = 0; B->edge2 = ctx->d_edge2;
 }
 
 // ---- TMA tensor maps -----------------------------------------------------------------------------
@@ -232,6 +233,10 @@ struct StageTimer {
 };
 
 int launch_pyramid_fast(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, int nframes) {
+  if (ctx->edges_pending) {      // a k_edges of an earlier call (one that did not describe) may still read the tables
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    ctx->edges_pending = false;
+  }
   // candidate counters and BRIEF border tables of the wave's frames (one small memset)
   CK(cudaMemsetAsync(ctx->d_cand_count, 0, ctx->zero_bytes_per_frame * nframes, ctx->stream));
   if (P.a_tiles_per_frame > 0) {
@@ -243,9 +248,21 @@ int launch_pyramid_fast(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, int nfram
   {
     StageTimer t(ctx, 1);
     orbk::k_fast<<<dim3(P.tiles_per_frame, nframes), orbk::B_THREADS, orbk::B_SMEM, ctx->stream>>>(P, B);
+    ctx->launches += 1;
   }
   CK(cudaGetLastError());
-  ctx->launches += 1;
+  {
+    // border-box tables for BRIEF from the strip tables k_fast has just finished (~2 (W + H) entries per level: a small,
+    // latency-bound kernel).  Nothing before k_describe needs them, so they are made on a side stream next to k_harris /
+    // k_select; launch_describe() joins.
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->s_side, ctx->ev_fork, 0));
+    orbk::k_edges<<<dim3(P.nlevels, nframes), orbk::E_THREADS, 0, ctx->s_side>>>(P, B);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev_join, ctx->s_side));
+    ctx->edges_pending = true;
+    ctx->launches += 1;
+  }
   if (P.select_policy == ORB_SELECT_HARRIS_TOP_N) {
     // grid sized for ~1.5 % of the pyramid pixels surviving NMS; denser frames take more grid-stride rounds
     int total_px = 0;
@@ -273,6 +290,10 @@ int launch_select(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, int nframes) {
   return ORB_OK;
 }
 int launch_describe(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, const DescribeJob& J, int nwarps, int nframes) {
+  if (ctx->edges_pending) {
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    ctx->edges_pending = false;
+  }
   if (nwarps <= 0) return ORB_OK;
   dim3 grid((nwarps + orbk::K3_KPS - 1) / orbk::K3_KPS, nframes);
   {
@@ -350,7 +371,7 @@ void orb_destroy(orb_ctx* ctx) {
   void* ptrs[] = {ctx->d_frames, ctx->d_pyr, ctx->d_box, ctx->d_cand, ctx->d_cand_count, ctx->d_kept_xy, ctx->d_kept_r,
                   ctx->d_kept_count, ctx->d_xtab, ctx->d_ytab, ctx->d_tile_a, ctx->d_tile_b, ctx->d_tile_b1, ctx->d_harris_w, ctx->d_pattern, ctx->d_flags, ctx->d_kps,
                   ctx->d_angles, ctx->d_desc, ctx->d_nout, ctx->d_side_xy, ctx->d_side_level, ctx->d_side_resp,
-                  ctx->d_list_kps, ctx->d_list_angles, ctx->d_list_out, ctx->d_tmaps};
+                  ctx->d_list_kps, ctx->d_list_angles, ctx->d_list_out, ctx->d_tmaps, ctx->d_edge2};
   for (void* q : ptrs) if (q) cudaFree(q);
   for (auto& sp : ctx->spans) { if (sp.a) cudaEventDestroy(sp.a); if (sp.b) cudaEventDestroy(sp.b); }
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
@@ -373,6 +394,9 @@ void orb_destroy(orb_ctx* ctx) {
   for (cudaEvent_t e : ctx->ev_done) cudaEventDestroy(e);
   if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
   if (ctx->ev_chain) cudaEventDestroy(ctx->ev_chain);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->s_side) cudaStreamDestroy(ctx->s_side);
   if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
   if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -417,6 +441,9 @@ int orb_create(const orb_params* p, orb_ctx** out) {
     CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&ctx->s_side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     build_plan(ctx->p, p->max_width, p->max_height, p->nlevels, p->select_policy, -1, &ctx->max_plan);
     const OrbPlan& M = ctx->max_plan;
     // single-image stages reuse slot 0 with a 1-level plan whose kept list may hold ORB_SORT_CAP entries
@@ -451,6 +478,7 @@ int orb_create(const orb_params* p, orb_ctx** out) {
       CK(cudaMalloc(&ctx->d_cand_count, ctx->zero_bytes_per_frame * C));
     }
     CK(cudaMalloc(&ctx->d_kept_count, sizeof(int) * ORB_MAX_LEVELS * C));
+    CK(cudaMalloc(&ctx->d_edge2, sizeof(int) * (size_t)std::max(M.edge2_frame_elems, S.edge2_frame_elems) * C));
     CK(cudaMalloc(&ctx->d_kept_xy, sizeof(uint32_t) * (size_t)kept_per_frame * C));
     CK(cudaMalloc(&ctx->d_kept_r, sizeof(float) * (size_t)kept_per_frame * C));
     ctx->xtab_cap = 0; ctx->ytab_cap = 0;

@@ -29,6 +29,7 @@ struct orb_ctx {
   // arena
   uint8_t* d_frames = nullptr; size_t frames_slot_bytes = 0; int frames_pitch = 0;
   uint8_t* d_pyr = nullptr; uint16_t* d_box = nullptr; unsigned long long* d_cand = nullptr;
+  int* d_edge2 = nullptr;
   int* d_cand_count = nullptr; size_t zero_bytes_per_frame = 0; uint32_t* d_kept_xy = nullptr; float* d_kept_r = nullptr; int* d_kept_count = nullptr;
   OrbTap *d_xtab = nullptr, *d_ytab = nullptr;
   uint32_t *d_tile_a = nullptr, *d_tile_b = nullptr, *d_tile_b1 = nullptr; int tile_a_cap = 0, tile_b_cap = 0;
@@ -49,6 +50,7 @@ struct orb_ctx {
   // chunk pipeline: staging copies and result copies run on their own streams
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_start = nullptr, ev_chain = nullptr;
+  cudaStream_t s_side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool edges_pending = false;   // k_edges next to k_harris / k_select
   std::vector<cudaEvent_t> ev_in, ev_done;
   // frame ingest: pinned host area the decode threads fill (same layout as d_frames)
   uint8_t* h_ingest = nullptr; size_t h_ingest_bytes = 0;

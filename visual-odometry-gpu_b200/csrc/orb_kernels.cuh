@@ -45,6 +45,7 @@ struct Bufs {
   const uint32_t* tile_b;        // same for k_fast
   const float4* pattern;         // 256 BRIEF tests (x1,y1,x2,y2) as floats
   int* flags;                    // bit 0: candidate overflow
+  int* edge2;                    // [chunk][edge2_frame_elems]: BRIEF border-box tables (k_edges)
   orb_keypoint* out_kps;         // [chunk][out_cap]
   float* out_angles;
   orb_descriptor* out_desc;
@@ -855,7 +856,7 @@ constexpr int ORIENT_UNROLL = ORB_ORIENT_UNROLL;
 #define ORB_K3_WARPS 4
 #endif
 #ifndef ORB_K3_MINB
-#define ORB_K3_MINB 8
+#define ORB_K3_MINB 7
 #endif
 constexpr int K3_WARPS = ORB_K3_WARPS;
 
@@ -866,6 +867,20 @@ struct EdgeSrc {
   const int* __restrict__ rs;   // rs[y]: row y over cols [0,W-4)
 };
 
+// Value tables for BRIEF boxes whose centre lies in the last two columns / rows of a level (decision D7), filled by
+// k_edges from the strip tables: what the reference's four wrapped integral taps add up to.
+//   bot[a * edge_w + cx]  : cy = H-2+a, 2 <= cx <= W-3      right[b * hh + cy] : cx = W-2+b, 2 <= cy <= H-3
+//   corner[a * 2 + b]     : cy = H-2+a, cx = W-2+b          (hh = h rounded up to a multiple of 4)
+struct EdgeTab {
+  const int* __restrict__ tab; int W, H, edge_w, hh;
+  __device__ __forceinline__ int at(int cx, int cy) const {
+    const int a = cy - (H - 2), b = cx - (W - 2);
+    const int idx = a >= 0 ? (b >= 0 ? 2 * edge_w + 2 * hh + 2 * a + b : a * edge_w + cx) : 2 * edge_w + b * hh + cy;
+    return __ldg(tab + idx);
+  }
+};
+__host__ __device__ inline int edge2_level_elems(int edge_w, int h) { return 2 * edge_w + 2 * ((h + 3) & ~3) + 4; }
+
 // ---- BRIEF boxes that leave the image on the right / bottom ---------------------------------------
 // The reference's sum5x5 (src/orb_cpu.cpp:190-201) indexes its (H+1)x(W+1) integral image flat, so for centres
 // in the last two columns / rows the column overruns wrap into the next row and the row overruns fall off the
@@ -873,31 +888,14 @@ struct EdgeSrc {
 //   bottom rows only : -(rows [0,cy-2) x cols [cx-2,cx+2])
 //   right cols only  : -(rows [cy-2,cy+2] x cols [0,cx-2)) + wrapped column-0 taps (when cx == W-1)
 //   corner           : +(rows [0,cy-2) x cols [0,cx-2)) - column-0 prefix
-// The first two come from the strip tables k_fast accumulates (+ at most 15 pixels), one lane per box.
-__device__ __noinline__ int box_edge_lane(const EdgeSrc& E, int cx, int cy) {
-  const int W = E.W, H = E.H, p = E.pitch;
-  if (cx <= W - 3) {
-    int s = E.ey[cx];
-    if (cy == H - 1) { const uint8_t* r = E.img + (size_t)(H - 4) * p + cx - 2; s += r[0] + r[1] + r[2] + r[3] + r[4]; }
-    return -s;
-  }
-  int s = E.rs[cy - 2] + E.rs[cy - 1] + E.rs[cy] + E.rs[cy + 1] + E.rs[cy + 2];
-  if (cx == W - 1) {
-    const uint8_t* c = E.img + (size_t)(cy - 2) * p + (W - 4);
-    s += c[0] + c[p] + c[2 * p] + c[3 * p] + c[4 * p];
-    int t;
-    if (cy + 4 <= H) { const uint8_t* z = E.img + (size_t)(cy - 1) * p; t = z[0] + z[p] + z[2 * p] + z[3 * p] + z[4 * p]; }
-    else t = -E.ey[0];
-    return t - s;
-  }
-  return -s;
-}
+// The first two come from the strip tables k_fast accumulates (+ at most 15 pixels); k_edges writes them out per level.
 
 // bottom-right corner box (cx > W-3 and cy > H-3), whole warp cooperates:
 //   +(rows [0,cy-2) x cols [0,cx-2)) - (column 0 over rows [0,cy-1) when cx == W-1)
 __device__ __noinline__ int box_corner(const EdgeSrc& E, int cx, int cy, int lane) {
   const int W = E.W, H = E.H, y0 = cy - 2;
   int s = 0;
+#pragma unroll 4
   for (int v = lane; v < y0; v += 32) {
     s += E.rs[v];
     if (cx == W - 1) s += E.img[(size_t)v * E.pitch + (W - 4)];
@@ -918,133 +916,255 @@ struct DescribeJob {             // where the keypoints of this launch come from
   int list_n;
 };
 
-// Intensity-centroid moments of the (2*pr+1)^2 patch, ref src/orb_cpu.cpp:158-176.  Moments are exact integers
-// (|m| < 2^24), so integer accumulation in any order equals the reference's float accumulation.  Lane j owns patch
-// column j - pr (and j + 32 - pr): m10 = sum_c c * colsum(c), m01 = sum_r r * I.  PR > 0 fixes the radius at
-// compile time so that all row loads of a lane are independent and in flight together.
-template <int PR>
-__device__ __forceinline__ void patch_moments(const uint8_t* __restrict__ img, int pitch, int x, int y, int pr_rt, int lane,
-                                              int* m10_out, int* m01_out) {
-  const int pr = PR > 0 ? PR : pr_rt;
-  int m10 = 0, m01 = 0;
-  for (int c = lane - pr; c <= pr; c += 32) {
-    const uint8_t* p = img + (size_t)(y - pr) * pitch + x + c;
-    int colsum = 0;
-    if (PR > 0) {
-#pragma unroll (ORIENT_UNROLL)
-      for (int r = -PR; r <= PR; r++) {
-        const int I = p[(size_t)(r + PR) * pitch];
-        colsum += I;
-        m01 += r * I;
-      }
-    } else {
-#pragma unroll 4
-      for (int r = -pr; r <= pr; r++, p += pitch) {
-        const int I = *p;
-        colsum += I;
-        m01 += r * I;
-      }
+// Kernel E: the border-box tables of every level of every frame of the wave (after k_fast has finished the strip
+// tables).  One CTA per (level, frame): ~2 (W + H) line entries spread over the threads, then one warp per corner entry.
+constexpr int E_THREADS = 256;
+__global__ void __launch_bounds__(E_THREADS) k_edges(const OrbPlan P, const Bufs B) {
+  const int l = blockIdx.x, f = blockIdx.y;
+  const OrbLevel& G = P.lv[l];
+  const int W = G.w, H = G.h, ew = G.edge_w, hh = (H + 3) & ~3;
+  const int n_line = 2 * ew + 2 * hh;
+  const uint8_t* img;
+  int pitch;
+  if (l == 0) { img = B.frames + (size_t)f * B.frame_stride; pitch = B.pitch0; }
+  else { img = B.pyr + (size_t)f * P.pyr_frame_bytes + G.lvl_ofs; pitch = G.pitch; }
+  const int* ey = B.cand_count + (size_t)f * B.zero_stride + ORB_MAX_LEVELS + G.edge_ofs;
+  const EdgeSrc E{img, pitch, W, H, ey, ey + ew};
+  int* out = B.edge2 + (size_t)f * P.edge2_frame_elems + G.edge2_ofs;
+  const bool big = W >= 7 && H >= 7;             // smaller levels cannot hold a keypoint (FAST needs a 3-pixel margin)
+  // bottom rows (cy = H-2, H-1; 2 <= cx <= W-3): -(strip above the box), the last row adds the five pixels of row H-4
+  const uint8_t* row = img + (size_t)max(H - 4, 0) * pitch;
+#pragma unroll 2
+  for (int cx = threadIdx.x; cx < ew; cx += E_THREADS) {
+    int v0 = 0, v1 = 0;
+    if (big && cx >= 2 && cx <= W - 3) {
+      const int s = E.ey[cx];
+      v0 = -s;
+      v1 = -(s + row[cx - 2] + row[cx - 1] + row[cx] + row[cx + 1] + row[cx + 2]);
     }
-    m10 += c * colsum;
+    out[cx] = v0;
+    out[ew + cx] = v1;
+  }
+  // right columns (cx = W-2, W-1; 2 <= cy <= H-3): -(strip left of the box); the last column adds column W-4 and the
+  // wrapped column-0 taps (or, when those fall off the integral image, the column-0 strip)
+  const int ey0 = big ? E.ey[0] : 0;
+#pragma unroll 2
+  for (int cy = threadIdx.x; cy < hh; cy += E_THREADS) {
+    int v0 = 0, v1 = 0;
+    if (big && cy >= 2 && cy <= H - 3) {
+      const int s = E.rs[cy - 2] + E.rs[cy - 1] + E.rs[cy] + E.rs[cy + 1] + E.rs[cy + 2];
+      const uint8_t* c = img + (size_t)(cy - 2) * pitch + (W - 4);
+      const int s1 = s + c[0] + c[pitch] + c[2 * pitch] + c[3 * pitch] + c[4 * pitch];
+      int t;
+      if (cy + 4 <= H) { const uint8_t* z = img + (size_t)(cy - 1) * pitch; t = z[0] + z[pitch] + z[2 * pitch] + z[3 * pitch] + z[4 * pitch]; }
+      else t = -ey0;
+      v0 = -s;
+      v1 = t - s1;
+    }
+    out[2 * ew + cy] = v0;
+    out[2 * ew + hh + cy] = v1;
+  }
+  if (threadIdx.x < 4 * 32) {
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;      // corner c: cy = H-2 + (c >> 1), cx = W-2 + (c & 1)
+    const int v = big ? box_corner(E, W - 2 + (c & 1), H - 2 + (c >> 1), lane) : 0;
+    if (lane == 0) out[n_line + c] = v;
+  }
+}
+
+// ---- per-keypoint windows in shared memory -----------------------------------------------------------------------
+// A warp copies what a keypoint needs into its own shared-memory slots with 16-byte cp.async copies, ahead of the
+// keypoint it is working on, so that the global-memory latency is off the critical path and the gathers are shared-
+// memory loads:
+//   orientation : the (2r+1)^2 patch as rows of W_PP bytes (the 16-byte aligned superset of columns kx-r .. kx+r);
+//   BRIEF       : rotated offsets stay within +-19 (pattern radius 18.4), so the 512 box sums of a keypoint lie in the
+//                 39 x 39 window around it: 39 rows x 48 elements of the level's u16 box-sum image.
+// The two uses are in different phases of the kernel and share the warp's buffer.
+constexpr int W_BW = 48, W_BH = 39, W_SLOT = W_BW * W_BH * 2;   // 3744 bytes per box-window slot
+constexpr int W_DEPTH = 2;                                        // box-window slots per warp
+constexpr int W_WARP_BYTES = W_DEPTH * W_SLOT;                    // 7488 bytes per warp
+constexpr int W_PP15 = 48, W_PDEPTH15 = 4;                        // patch 31: 31 rows x 48 bytes, four slots of 1536 bytes
+constexpr int W_PSLOT15 = 1536;
+constexpr int W_PPGEN = 80;                                       // other radii (<= 31): up to 63 rows x 80 bytes, one slot
+static_assert(W_PDEPTH15 * W_PSLOT15 <= W_WARP_BYTES && 63 * W_PPGEN <= W_WARP_BYTES, "patch slots live in the box-window buffer");
+
+__device__ __forceinline__ void cp_async_16(uint32_t sa, const void* g, bool ok, const void* safe) {
+  // rows / columns outside the image are zero-filled (source size 0, address kept valid): they are never used
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(ok ? g : safe), "r"(ok ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+
+// box-sum window of keypoint (kx, ky): lane -> (row lane / 6 of a group of five rows, 16-byte column lane % 6);
+// lanes 30, 31 idle; eight groups = 40 rows
+__device__ __forceinline__ void window_issue(uint32_t slot_sa, const uint16_t* __restrict__ box, int bpitch, int h, int kx, int ky,
+                                             int lane) {
+  const int r0 = lane / 6, c0 = lane - 6 * r0;
+  const int xa = ((kx - 19) & ~7) + 8 * c0, y0 = ky - 19 + r0;
+  if (lane >= 30) return;
+  const bool col_ok = xa >= 0 && xa < bpitch;
+  uint32_t sa = slot_sa + (uint32_t)(r0 * (W_BW * 2) + c0 * 16);
+  if (col_ok && ky - 19 >= 0 && ky + 19 < h) {   // this lane's column and all 39 rows lie inside the level
+    const uint16_t* g = box + (ptrdiff_t)y0 * bpitch + xa;
+    const size_t step = (size_t)(5 * bpitch) * 2;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (j < 7 || r0 < W_BH - 35)               // (the 40th row of the last group is not part of the window)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + j * 5 * (W_BW * 2)), "l"((const char*)g + j * step) : "memory");
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int y = y0 + 5 * j;
+      if (j < 7 || r0 < W_BH - 35) cp_async_16(sa + j * 5 * (W_BW * 2), box + (ptrdiff_t)y * bpitch + xa, col_ok && y >= 0 && y < h, box);
+    }
+  }
+}
+
+// orientation patch of a keypoint whose patch lies inside the level (ref src/orb_cpu.cpp:152-156 sets the angle of the
+// others to 0): rows ky-pr .. ky+pr, bytes from the 16-byte aligned column at or below kx-pr, PP bytes per row.
+// PP == 48 (patch 31): lane -> (row lane / 3 of a group of ten rows, 16-byte column lane % 3), four groups = 40 rows.
+template <int PP>
+__device__ __forceinline__ void patch_issue(uint32_t slot_sa, const uint8_t* __restrict__ img, int pitch, int kx, int ky, int pr, int lane) {
+  constexpr int CPR = PP / 16, ROWS_PER = 30 / CPR;
+  const int r0 = lane / CPR, c0 = lane - CPR * r0;
+  const int xa = ((kx - pr) & ~15) + 16 * c0;
+  if (lane >= 30) return;
+  const bool ok = xa < pitch;
+  const uint8_t* g = ok ? img + (ptrdiff_t)(ky - pr + r0) * pitch + xa : img;
+  const size_t step = ok ? (size_t)ROWS_PER * pitch : 0;
+  const uint32_t sa = slot_sa + (uint32_t)(r0 * PP + c0 * 16), nb = ok ? 16u : 0u;
+  if (PP == W_PP15) {                            // pr == 15: 31 rows
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (j < 3 || r0 == 0)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa + j * ROWS_PER * PP), "l"(g + j * step), "r"(nb) : "memory");
+  } else {
+    for (int r = r0, j = 0; r <= 2 * pr; r += ROWS_PER, j++)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa + j * ROWS_PER * PP), "l"(g + j * step), "r"(nb) : "memory");
+  }
+}
+
+// Intensity-centroid moments of the (2*pr+1)^2 patch, ref src/orb_cpu.cpp:158-176, from the staged patch.  Moments are
+// exact integers (|m| < 2^24), so integer accumulation in any order equals the reference's float accumulation.
+// Lane j owns patch column j - pr (and j + 32 - pr): m10 = sum_c c * colsum(c), m01 = sum_r r * I.  For patch 31 one
+// multiply-add per pixel accumulates both sums: I * (1 + (r' << 13)) with r' = r + 15 keeps the column sum
+// (<= 31 * 255 < 2^13) in the low 13 bits and sum r' * I (<= 465 * 255 < 2^17) above it.
+__device__ __forceinline__ void patch_moments(uint32_t slot_sa, int kx, int pr, int pp, int lane, int* m10_out, int* m01_out) {
+  int m10 = 0, m01 = 0;
+  const uint32_t base = slot_sa + (uint32_t)((kx - pr) & 15);
+  if (pr == 15) {                                                 // patch 31 (include/orb.hpp:12): one column per lane
+    if (lane <= 30) {
+      uint32_t acc = 0;
+#pragma unroll
+      for (int r = 0; r <= 30; r++) acc += lds_u8(base + lane + r * W_PP15) * (1u + ((uint32_t)r << 13));
+      const int colsum = (int)(acc & 0x1fffu);
+      m01 = (int)(acc >> 13) - 15 * colsum;
+      m10 = (lane - 15) * colsum;
+    }
+  } else {
+    for (int c = lane - pr; c <= pr; c += 32) {
+      int colsum = 0;
+      for (int r = -pr; r <= pr; r++) {
+        const int I = (int)lds_u8(base + (uint32_t)((r + pr) * pp + c + pr));
+        colsum += I;
+        m01 += r * I;
+      }
+      m10 += c * colsum;
+    }
   }
   *m10_out = warp_sum(m10);
   *m01_out = warp_sum(m01);
 }
 
-// moments of the orientation patch; returns false (moments untouched) when the patch leaves the level, in which case the
-// reference sets the angle to 0 (src/orb_cpu.cpp:152-156)
-__device__ __forceinline__ bool moments_of(const uint8_t* __restrict__ img, int pitch, int w, int h, int x, int y,
-                                           int pr, int lane, int* m10, int* m01) {
-  if (x - pr < 0 || x + pr >= w || y - pr < 0 || y + pr >= h) return false;
-  if (pr == 15) patch_moments<15>(img, pitch, x, y, pr, lane, m10, m01);      // patch 31 (include/orb.hpp:12)
-  else if (pr == 4) patch_moments<4>(img, pitch, x, y, pr, lane, m10, m01);   // patch 9 (include/orb_cpu.hpp:6)
-  else patch_moments<0>(img, pitch, x, y, pr, lane, m10, m01);
-  return true;
+// rotate one pattern point and round (ref src/orb_cpu.cpp:228-232): (lround(c*x - s*y), lround(s*x + c*y)).  The two
+// products per coordinate pair are packed f32x2 multiplies (each half rounded like the scalar multiply); the sums
+// stay scalar adds so that nothing can contract into an FMA.
+__device__ __forceinline__ void rotate_round(unsigned long long cs, unsigned long long msc, float px, float py, int* dx, int* dy) {
+  unsigned long long a, b;
+  const unsigned long long xx = ((unsigned long long)__float_as_uint(px) << 32) | __float_as_uint(px);
+  const unsigned long long yy = ((unsigned long long)__float_as_uint(py) << 32) | __float_as_uint(py);
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(a) : "l"(cs), "l"(xx));      // (c * x, s * x)
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(b) : "l"(msc), "l"(yy));     // (-s * y, c * y)
+  const float vx = __fadd_rn(__uint_as_float((uint32_t)a), __uint_as_float((uint32_t)b));                // c*x - s*y
+  const float vy = __fadd_rn(__uint_as_float((uint32_t)(a >> 32)), __uint_as_float((uint32_t)(b >> 32)));  // s*x + c*y
+  *dx = orbm::lround_f(vx);
+  *dy = orbm::lround_f(vy);
 }
 
-__device__ __forceinline__ void brief_of(const uint8_t* __restrict__ img, int pitch, const uint16_t* __restrict__ box,
-                                         int bpitch, const EdgeSrc& E, int kx, int ky, float c, float s,
+// wc_sa: shared-memory byte address of the window element that holds the box sum at the keypoint itself, i.e. the box
+// sum at (kx + dx, ky + dy) is the u16 at wc_sa + dy * 96 + dx * 2
+__device__ __forceinline__ void brief_of(uint32_t wc_sa, const EdgeTab& T, int kx, int ky, float c, float s,
                                          const float4* __restrict__ pattern, int lane, uint32_t* out_words) {
-  const int W = E.W, H = E.H;   // c, s = cos / sin of the keypoint angle (ref src/orb_cpu.cpp:217-218)
+  const int W = T.W, H = T.H;   // c, s = cos / sin of the keypoint angle (ref src/orb_cpu.cpp:217-218)
   uint32_t mine = 0;
-  // rotated offsets stay within +-19 (pattern radius 18.4): if every box is interior the bound rule of
-  // src/orb_cpu.cpp:240-245 can never fire and the sums are plain box-sum lookups
+  const unsigned long long cs = ((unsigned long long)__float_as_uint(s) << 32) | __float_as_uint(c);
+  const unsigned long long msc = ((unsigned long long)__float_as_uint(c) << 32) | __float_as_uint(-s);
+  // if every box is interior the bound rule of src/orb_cpu.cpp:240-245 can never fire and the sums are plain lookups
   const bool interior = kx - 19 >= 2 && kx + 19 <= W - 3 && ky - 19 >= 2 && ky + 19 <= H - 3;
   if (interior) {
-    const uint16_t* bc = box + (size_t)ky * bpitch + kx;
 #pragma unroll (BRIEF_UNROLL)
     for (int wd = 0; wd < 8; wd++) {
       const float4 t = __ldg(pattern + wd * 32 + lane);
-      const int dx1 = orbm::lround_f(orbm::fsub(orbm::fmul(c, t.x), orbm::fmul(s, t.y)));   // :228-232
-      const int dy1 = orbm::lround_f(orbm::fadd(orbm::fmul(s, t.x), orbm::fmul(c, t.y)));
-      const int dx2 = orbm::lround_f(orbm::fsub(orbm::fmul(c, t.z), orbm::fmul(s, t.w)));
-      const int dy2 = orbm::lround_f(orbm::fadd(orbm::fmul(s, t.z), orbm::fmul(c, t.w)));
-      const int s1 = bc[dy1 * bpitch + dx1], s2 = bc[dy2 * bpitch + dx2];
+      int dx1, dy1, dx2, dy2;
+      rotate_round(cs, msc, t.x, t.y, &dx1, &dy1);
+      rotate_round(cs, msc, t.z, t.w, &dx2, &dy2);
+      const uint32_t s1 = lds_u16(wc_sa + dy1 * (W_BW * 2) + dx1 * 2), s2 = lds_u16(wc_sa + dy2 * (W_BW * 2) + dx2 * 2);
       const uint32_t word = __ballot_sync(0xffffffffu, s1 < s2);   // bit i of word wd == test 32*wd + i
       if (lane == wd) mine = word;
     }
     *out_words = mine;
     return;
   }
-  // keypoint near a border: only the sides it is close to need the bound rule of :240-245 (against the integral image
-  // dims W+1, H+1), and only right / bottom proximity can produce boxes that leave the image (decision D7)
-  const bool nearL = kx - 19 < 2, nearT = ky - 19 < 2, nearR = kx + 19 > W - 3, nearB = ky + 19 > H - 3;
+  // Keypoint near a border.  The bound rule of :240-245 (against the integral image dims W+1, H+1) skips a test when a
+  // box centre has cx < 2, cy < 2, cx > W-1 or cy > H-1: one unsigned compare per coordinate.  Centres in the last two
+  // columns / rows (decision D7) take their value from the level's border-box tables (k_edges) instead of the window.
+  const uint32_t xlim = (uint32_t)(W - 3), ylim = (uint32_t)(H - 3);
   for (int wd = 0; wd < 8; wd++) {
     const float4 t = __ldg(pattern + wd * 32 + lane);
-    const int cx1 = kx + orbm::lround_f(orbm::fsub(orbm::fmul(c, t.x), orbm::fmul(s, t.y)));
-    const int cy1 = ky + orbm::lround_f(orbm::fadd(orbm::fmul(s, t.x), orbm::fmul(c, t.y)));
-    const int cx2 = kx + orbm::lround_f(orbm::fsub(orbm::fmul(c, t.z), orbm::fmul(s, t.w)));
-    const int cy2 = ky + orbm::lround_f(orbm::fadd(orbm::fmul(s, t.z), orbm::fmul(c, t.w)));
-    bool skip = false;
-    if (nearL) skip |= cx1 < 2 || cx2 < 2;
-    if (nearT) skip |= cy1 < 2 || cy2 < 2;
-    if (nearR) skip |= cx1 > W - 1 || cx2 > W - 1;
-    if (nearB) skip |= cy1 > H - 1 || cy2 > H - 1;
-    int s1 = 0, s2 = 0;
-    if (!(nearR || nearB)) {
-      if (!skip) { s1 = box[(size_t)cy1 * bpitch + cx1]; s2 = box[(size_t)cy2 * bpitch + cx2]; }
-    } else {
-      const bool k1 = !skip && cx1 > W - 3 && cy1 > H - 3, k2 = !skip && cx2 > W - 3 && cy2 > H - 3;   // corner boxes
-      if (!skip) {
-        if (!k1) s1 = (cx1 > W - 3 || cy1 > H - 3) ? box_edge_lane(E, cx1, cy1) : (int)box[(size_t)cy1 * bpitch + cx1];
-        if (!k2) s2 = (cx2 > W - 3 || cy2 > H - 3) ? box_edge_lane(E, cx2, cy2) : (int)box[(size_t)cy2 * bpitch + cx2];
-      }
-      if (nearR && nearB) {
-        unsigned pend = __ballot_sync(0xffffffffu, k1);
-        while (pend) {
-          int src = __ffs(pend) - 1;
-          pend &= pend - 1;
-          int v = box_corner(E, __shfl_sync(0xffffffffu, cx1, src), __shfl_sync(0xffffffffu, cy1, src), lane);
-          if (lane == src) s1 = v;
-        }
-        pend = __ballot_sync(0xffffffffu, k2);
-        while (pend) {
-          int src = __ffs(pend) - 1;
-          pend &= pend - 1;
-          int v = box_corner(E, __shfl_sync(0xffffffffu, cx2, src), __shfl_sync(0xffffffffu, cy2, src), lane);
-          if (lane == src) s2 = v;
-        }
-      }
-    }
+    int dx1, dy1, dx2, dy2;
+    rotate_round(cs, msc, t.x, t.y, &dx1, &dy1);
+    rotate_round(cs, msc, t.z, t.w, &dx2, &dy2);
+    const int cx1 = kx + dx1, cy1 = ky + dy1, cx2 = kx + dx2, cy2 = ky + dy2;
+    const bool skip = (uint32_t)(cx1 - 2) > xlim || (uint32_t)(cy1 - 2) > ylim || (uint32_t)(cx2 - 2) > xlim || (uint32_t)(cy2 - 2) > ylim;
+    const bool e1 = !skip && (cx1 > W - 3 || cy1 > H - 3), e2 = !skip && (cx2 > W - 3 || cy2 > H - 3);
+    int s1 = (int)lds_u16(wc_sa + dy1 * (W_BW * 2) + dx1 * 2), s2 = (int)lds_u16(wc_sa + dy2 * (W_BW * 2) + dx2 * 2);
+    if (e1) s1 = T.at(cx1, cy1);
+    if (e2) s2 = T.at(cx2, cy2);
     uint32_t word = __ballot_sync(0xffffffffu, !skip && s1 < s2);
     if (lane == wd) mine = word;
   }
   *out_words = mine;
 }
 
-// A CTA of K3_WARPS warps owns K3_KPS = 32 consecutive keypoints of one frame and works in three phases so that the scalar
-// libm work (atan2f, cosf, sinf: ~250 instructions that a warp would execute for a single keypoint) runs once per lane
-// for 32 keypoints:  (1) warp per keypoint: integer patch moments -> shared;  (2) warp 0, lane = keypoint: angle, cos,
-// sin, level-0 coordinates, record headers;  (3) warp per keypoint: rotated BRIEF with the shared cos / sin.
+// A CTA of K3_WARPS warps owns K3_KPS = 32 consecutive keypoints of one frame and works in phases so that the scalar
+// work runs once per lane for 32 keypoints instead of once per warp and keypoint:
+//   (0) lane = keypoint: level / position lookup, image and table addresses of its level -> shared memory;
+//   (1) warp per keypoint: integer patch moments out of staged patches (four keypoints ahead);
+//   (2) warp 0, lane = keypoint: angle (libm: ~250 instructions), cos, sin, level-0 coordinates, record headers;
+//   (3) warp per keypoint: rotated BRIEF out of staged box-sum windows (two keypoints ahead; the first two are
+//       requested before phase 2).
 constexpr int K3_KPS = 32;
+
+struct KpSlot {                  // what phase 0 resolves per keypoint
+  const uint8_t* img;            // level image
+  const uint16_t* box;           // level box-sum image
+  const int* tab;                // border-box tables of the level (k_edges)
+  int pitch, bpitch, w, h, edge_w;
+  int x, y, l;                   // level-space position, level (| 0x100: orientation patch leaves the level -> angle 0)
+  union { int m10; float c; };   // moments (phase 1) -> cos / sin of the angle (phase 2)
+  union { int m01; float s; };
+};
 
 __global__ void __launch_bounds__(K3_WARPS * 32, ORB_K3_MINB) k_describe(const OrbPlan P, const Bufs B, const DescribeJob J) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int f = blockIdx.y;
   const int k0 = blockIdx.x * K3_KPS;            // first keypoint (output slot) of this CTA
+  __shared__ __align__(16) uint8_t s_win[K3_WARPS * W_WARP_BYTES];
   __shared__ int s_pref[ORB_MAX_LEVELS + 1];     // exclusive prefix of the frame's kept counts (levels are concatenated)
-  __shared__ int s_x[K3_KPS], s_y[K3_KPS], s_l[K3_KPS], s_m10[K3_KPS], s_m01[K3_KPS];
-  __shared__ float s_c[K3_KPS], s_s[K3_KPS];
+  __shared__ KpSlot s_kp[K3_KPS];
   int total;
   if (J.mode == 0) {
     if (threadIdx.x < 32) {
@@ -1064,42 +1184,89 @@ __global__ void __launch_bounds__(K3_WARPS * 32, ORB_K3_MINB) k_describe(const O
     total = J.list_n;
   }
   if (k0 >= total) return;
+  const int n_cta = min(K3_KPS, total - k0);     // keypoints of this CTA; warp w owns q = w, w + K3_WARPS, ...
+  const int pr = P.patch_radius;
 
-  // ---- phase 1: keypoint lookup + patch moments, one warp per keypoint ----------------------------
-  for (int q = warp; q < K3_KPS; q += K3_WARPS) {
-    const int widx = k0 + q;
-    if (widx >= total) break;
+  // ---- phase 0: lane = keypoint ------------------------------------------------------------------
+  if (threadIdx.x < n_cta) {
+    const int widx = k0 + threadIdx.x;
     int l = 0, x, y;
     if (J.mode == 0) {
-      // level of output slot widx: the number of level starts (levels 1..) at or below it
-      l = __popc(__ballot_sync(0xffffffffu, lane + 1 < P.nlevels && widx >= s_pref[min(lane + 1, ORB_MAX_LEVELS)]));
+      while (l + 1 < P.nlevels && widx >= s_pref[l + 1]) l++;
       const uint32_t xy = B.kept_xy[(size_t)f * P.kept_per_frame + P.lv[l].kept_ofs + (widx - s_pref[l])];
       x = xy & 0xffff; y = xy >> 16;
     } else {
       x = J.list_kps[widx].x; y = J.list_kps[widx].y;
     }
-    int m10 = 0, m01 = 0;
-    bool inside = false;
-    if (J.mode != 2) {
-      const OrbLevel& G = P.lv[l];
-      const uint8_t* img;
-      int pitch;
-      if (l == 0) { img = B.frames + (size_t)f * B.frame_stride; pitch = B.pitch0; }
-      else { img = B.pyr + (size_t)f * P.pyr_frame_bytes + G.lvl_ofs; pitch = G.pitch; }
-      inside = moments_of(img, pitch, G.w, G.h, x, y, P.patch_radius, lane, &m10, &m01);
+    const OrbLevel& G = P.lv[l];
+    KpSlot k;
+    if (l == 0) { k.img = B.frames + (size_t)f * B.frame_stride; k.pitch = B.pitch0; }
+    else { k.img = B.pyr + (size_t)f * P.pyr_frame_bytes + G.lvl_ofs; k.pitch = G.pitch; }
+    k.box = B.box + (size_t)f * P.box_frame_elems + G.box_ofs;
+    k.tab = B.edge2 + (size_t)f * P.edge2_frame_elems + G.edge2_ofs;
+    k.bpitch = G.bpitch; k.w = G.w; k.h = G.h; k.edge_w = G.edge_w;
+    k.x = x; k.y = y;
+    // the reference sets the angle to 0 when the patch leaves the level (src/orb_cpu.cpp:152-156)
+    k.l = (x - pr < 0 || x + pr >= G.w || y - pr < 0 || y + pr >= G.h) ? (l | 0x100) : l;
+    k.m10 = 0; k.m01 = 0;
+    s_kp[threadIdx.x] = k;
+  }
+  __syncthreads();
+  const int n_mine = warp < n_cta ? (n_cta - warp + K3_WARPS - 1) / K3_WARPS : 0;
+  const uint32_t my_sa = smem_u32(s_win) + (uint32_t)(warp * W_WARP_BYTES);
+
+  // ---- phase 1: patch moments, one warp per keypoint, patches staged ahead ---------------------------
+  if (J.mode != 2) {
+    const int pp = pr == 15 ? W_PP15 : W_PPGEN, pdepth = pr == 15 ? W_PDEPTH15 : 1, pslot = pr == 15 ? W_PSLOT15 : 0;
+    auto issue_patch = [&](int i) {
+      if (i < n_mine) {
+        const KpSlot& k = s_kp[warp + K3_WARPS * i];
+        if (!(k.l & 0x100)) {
+          if (pr == 15) patch_issue<W_PP15>(my_sa + (uint32_t)((i % W_PDEPTH15) * W_PSLOT15), k.img, k.pitch, k.x, k.y, 15, lane);
+          else patch_issue<W_PPGEN>(my_sa, k.img, k.pitch, k.x, k.y, pr, lane);
+        }
+      }
+      cp_async_commit();                         // (possibly empty) group i
+    };
+    for (int i = 0; i < pdepth; i++) issue_patch(i);
+    for (int i = 0; i < n_mine; i++) {
+      const int q = warp + K3_WARPS * i;
+      if (pr == 15) cp_async_wait<W_PDEPTH15 - 1>(); else cp_async_wait<0>();
+      __syncwarp();
+      if (!(s_kp[q].l & 0x100)) {
+        int m10, m01;
+        patch_moments(my_sa + (uint32_t)((i % pdepth) * pslot), s_kp[q].x, pr, pp, lane, &m10, &m01);
+        if (lane == 0) { s_kp[q].m10 = m10; s_kp[q].m01 = m01; }
+      }
+      __syncwarp();
+      issue_patch(i + pdepth);
     }
-    if (lane == 0) { s_x[q] = x; s_y[q] = y; s_l[q] = inside ? l : (l | 0x100); s_m10[q] = m10; s_m01[q] = m01; }
+    cp_async_wait<0>();
+  }
+  // the box-sum windows of this warp's first keypoints travel while warp 0 does the libm part
+  auto issue_window = [&](int i) {
+    if (i < n_mine) {
+      const KpSlot& k = s_kp[warp + K3_WARPS * i];
+      window_issue(my_sa + (uint32_t)((i % W_DEPTH) * W_SLOT), k.box, k.bpitch, k.h, k.x, k.y, lane);
+    }
+    cp_async_commit();
+  };
+  if (J.mode != 1) {
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < W_DEPTH; i++) issue_window(i);
   }
   __syncthreads();
 
   // ---- phase 2: lane = keypoint: angle (glibc-exact atan2f), cos / sin, record headers -----------
-  if (warp == 0 && k0 + lane < total) {
-    const int widx = k0 + lane, x = s_x[lane], y = s_y[lane], l = s_l[lane] & 0xff;
+  if (warp == 0 && lane < n_cta) {
+    KpSlot& k = s_kp[lane];
+    const int widx = k0 + lane, x = k.x, y = k.y, l = k.l & 0xff;
     const size_t o = (size_t)f * B.out_cap + widx;
     float angle;
     if (J.mode == 2) angle = J.list_angles[widx];
-    else angle = (s_l[lane] & 0x100) ? 0.0f : orbm::atan2f_glibc((float)s_m01[lane], (float)s_m10[lane]);   // ref src/orb_cpu.cpp:178
-    if (J.mode != 1) { s_c[lane] = orbm::cosf_glibc(angle); s_s[lane] = orbm::sinf_glibc(angle); }      // :217-218
+    else angle = (k.l & 0x100) ? 0.0f : orbm::atan2f_glibc((float)k.m01, (float)k.m10);   // ref src/orb_cpu.cpp:178
+    if (J.mode != 1) { k.c = orbm::cosf_glibc(angle); k.s = orbm::sinf_glibc(angle); }      // :217-218 (overwrites the moments)
     if (J.mode != 2) B.out_angles[o] = angle;
     if (J.mode == 0) {
       // kp.x *= scale (int * float, truncated): ref src/orb.cpp:94-98
@@ -1118,22 +1285,21 @@ __global__ void __launch_bounds__(K3_WARPS * 32, ORB_K3_MINB) k_describe(const O
   if (J.mode == 1) return;
   __syncthreads();
 
-  // ---- phase 3: rotated BRIEF, one warp per keypoint ----------------------------------------------
-  for (int q = warp; q < K3_KPS; q += K3_WARPS) {
-    const int widx = k0 + q;
-    if (widx >= total) break;
-    const int l = s_l[q] & 0xff;
-    const OrbLevel& G = P.lv[l];
-    const uint8_t* img;
-    int pitch;
-    if (l == 0) { img = B.frames + (size_t)f * B.frame_stride; pitch = B.pitch0; }
-    else { img = B.pyr + (size_t)f * P.pyr_frame_bytes + G.lvl_ofs; pitch = G.pitch; }
-    const uint16_t* box = B.box + (size_t)f * P.box_frame_elems + G.box_ofs;
-    const int* ey = B.cand_count + (size_t)f * B.zero_stride + ORB_MAX_LEVELS + G.edge_ofs;
-    const EdgeSrc E{img, pitch, G.w, G.h, ey, ey + G.edge_w};
+  // ---- phase 3: rotated BRIEF, one warp per keypoint, windows W_DEPTH keypoints ahead ----------------
+  uint32_t* out_words = (uint32_t*)B.out_desc + ((size_t)f * B.out_cap + k0) * 8;
+  for (int i = 0; i < n_mine; i++) {
+    const int q = warp + K3_WARPS * i;
+    const KpSlot& k = s_kp[q];
+    const int kx = k.x, ky = k.y;
+    const EdgeTab T{k.tab, k.w, k.h, k.edge_w, (k.h + 3) & ~3};
+    cp_async_wait<W_DEPTH - 1>();                 // group i has landed (this thread's copies) ...
+    __syncwarp();                                 // ... and everybody else's
     uint32_t word;
-    brief_of(img, pitch, box, G.bpitch, E, s_x[q], s_y[q], s_c[q], s_s[q], B.pattern, lane, &word);
-    if (lane < 8) ((uint32_t*)B.out_desc)[((size_t)f * B.out_cap + widx) * 8 + lane] = word;
+    const uint32_t wc_sa = my_sa + (uint32_t)((i % W_DEPTH) * W_SLOT + (19 * W_BW + 19 + ((kx - 19) & 7)) * 2);
+    brief_of(wc_sa, T, kx, ky, k.c, k.s, B.pattern, lane, &word);
+    if (lane < 8) out_words[q * 8 + lane] = word;
+    __syncwarp();                                 // the slot is free again
+    issue_window(i + W_DEPTH);
   }
 }
 

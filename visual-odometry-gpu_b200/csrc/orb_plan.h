@@ -18,6 +18,7 @@ struct OrbLevel {
   int kept_ofs;          // offset of this level's kept list inside a frame's kept arrays
   int xtab_ofs, ytab_ofs;   // offsets into the resize tap tables
   int edge_ofs, edge_w;     // BRIEF border tables of the level: ey[edge_w] column strips, then rs[h] row sums
+  int edge2_ofs;            // border-box value tables of the level (k_edges): bot[2][edge_w], right[2][hh], corner[4]
   float scale;           // (float)pow(f, l): level -> level-0 coordinate scale (ref src/orb.cpp:95)
   unsigned long long lvl_ofs;    // byte offset of the level image inside a frame's pyramid scratch (level 0 unused)
   unsigned long long box_ofs;    // element offset of the box-sum image inside a frame's box scratch
@@ -31,6 +32,7 @@ struct OrbPlan {
   int a_tiles_per_frame;
   int kept_per_frame;        // sum of kept slots over levels
   int edge_frame_elems;      // ints of BRIEF border tables per frame
+  int edge2_frame_elems;     // ints of border-box value tables per frame
   int fast_threshold, fast_n, nms_radius, patch_radius;
   int select_policy, blur_levels;
   float harris_k;
