@@ -855,6 +855,9 @@ constexpr int ORIENT_UNROLL = ORB_ORIENT_UNROLL;
 #ifndef ORB_K3_WARPS
 #define ORB_K3_WARPS 4
 #endif
+#ifndef ORB_K3_WARP_LIBM
+#define ORB_K3_WARP_LIBM 1
+#endif
 #ifndef ORB_K3_MINB
 #define ORB_K3_MINB 7
 #endif
@@ -1075,8 +1078,8 @@ __device__ __forceinline__ void patch_moments(uint32_t slot_sa, int kx, int pr, 
       m10 += c * colsum;
     }
   }
-  *m10_out = warp_sum(m10);
-  *m01_out = warp_sum(m01);
+  *m10_out = __reduce_add_sync(0xffffffffu, m10);   // REDUX.SUM: one instruction per warp sum
+  *m01_out = __reduce_add_sync(0xffffffffu, m01);
 }
 
 // rotate one pattern point and round (ref src/orb_cpu.cpp:228-232): (lround(c*x - s*y), lround(s*x + c*y)).  The two
@@ -1122,6 +1125,7 @@ __device__ __forceinline__ void brief_of(uint32_t wc_sa, const EdgeTab& T, int k
   // box centre has cx < 2, cy < 2, cx > W-1 or cy > H-1: one unsigned compare per coordinate.  Centres in the last two
   // columns / rows (decision D7) take their value from the level's border-box tables (k_edges) instead of the window.
   const uint32_t xlim = (uint32_t)(W - 3), ylim = (uint32_t)(H - 3);
+#pragma unroll 2
   for (int wd = 0; wd < 8; wd++) {
     const float4 t = __ldg(pattern + wd * 32 + lane);
     int dx1, dy1, dx2, dy2;
@@ -1256,12 +1260,23 @@ __global__ void __launch_bounds__(K3_WARPS * 32, ORB_K3_MINB) k_describe(const O
 #pragma unroll
     for (int i = 0; i < W_DEPTH; i++) issue_window(i);
   }
+#if ORB_K3_WARP_LIBM
+  __syncwarp();
+
+  // ---- phase 2: lane = one of the warp's keypoints: angle (glibc-exact atan2f), cos / sin, record headers.  The
+  // ~250 scalar instructions run once per warp for its <= 8 keypoints; in exchange no warp waits at a CTA barrier.
+  if (lane < n_mine) {
+    const int q2 = warp + K3_WARPS * lane;
+    KpSlot& k = s_kp[q2];
+    const int widx = k0 + q2, x = k.x, y = k.y, l = k.l & 0xff;
+#else
   __syncthreads();
 
   // ---- phase 2: lane = keypoint: angle (glibc-exact atan2f), cos / sin, record headers -----------
   if (warp == 0 && lane < n_cta) {
     KpSlot& k = s_kp[lane];
     const int widx = k0 + lane, x = k.x, y = k.y, l = k.l & 0xff;
+#endif
     const size_t o = (size_t)f * B.out_cap + widx;
     float angle;
     if (J.mode == 2) angle = J.list_angles[widx];
@@ -1283,7 +1298,11 @@ __global__ void __launch_bounds__(K3_WARPS * 32, ORB_K3_MINB) k_describe(const O
     }
   }
   if (J.mode == 1) return;
+#if ORB_K3_WARP_LIBM
+  __syncwarp();
+#else
   __syncthreads();
+#endif
 
   // ---- phase 3: rotated BRIEF, one warp per keypoint, windows W_DEPTH keypoints ahead ----------------
   uint32_t* out_words = (uint32_t*)B.out_desc + ((size_t)f * B.out_cap + k0) * 8;
