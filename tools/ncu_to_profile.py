@@ -26,6 +26,10 @@ KEYS = {
     "smsp__thread_inst_executed_per_inst_executed.ratio": "threads_per_inst",
     "l1tex__t_sector_hit_rate.pct": "l1_hit_pct", "lts__t_sector_hit_rate.pct": "l2_hit_pct",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum": "smem_bank_conflicts",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active": "alu_pct",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active": "fma_pct",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active": "xu_pct",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active": "lsu_pct",
 }
 UNIT_SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
 
@@ -61,18 +65,18 @@ def main():
           " (1 B200, one wave of 128 frames per launch). Times are per launch in microseconds, bytes per launch.", ""]
     if os.path.exists(rep):
         ks = read_rep(rep)
-        md.append("| kernel | captures | time us | DRAM read | DRAM write | regs | warps active % | SM thr % | L1/TEX % | L2 % | DRAM % | issue active % | warp inst | L1 hit % | L2 hit % | smem conflicts |")
-        md.append("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
+        md.append("| kernel | captures | time us | DRAM read | DRAM write | regs | warps active % | SM thr % | L1/TEX % | L2 % | DRAM % | issue active % | ALU pipe % | FMA pipe % | warp inst | L1 hit % | L2 hit % | smem conflicts |")
+        md.append("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
         for name, recs in ks.items():
             avg = {k: sum(r.get(k, 0) for r in recs) / len(recs) for k in recs[0]}
             avg["captures"] = len(recs)
             avg["dram_bytes_per_launch"] = avg.get("dram_read", 0) + avg.get("dram_write", 0)
             summary["kernels"][name] = avg
-            md.append("| %s | %d | %.1f | %.2f MB | %.2f MB | %d | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.2f M | %.1f | %.1f | %.0f |" % (
+            md.append("| %s | %d | %.1f | %.2f MB | %.2f MB | %d | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.2f M | %.1f | %.1f | %.0f |" % (
                 name, len(recs), avg.get("time", 0), avg.get("dram_read", 0) / 1e6, avg.get("dram_write", 0) / 1e6, avg.get("regs", 0),
                 avg.get("warps_active_pct", 0), avg.get("sm_throughput_pct", 0), avg.get("l1tex_throughput_pct", 0),
                 avg.get("l2_throughput_pct", 0), avg.get("dram_throughput_pct", 0), avg.get("issue_active_pct", 0),
-                avg.get("warp_inst", 0) / 1e6, avg.get("l1_hit_pct", 0), avg.get("l2_hit_pct", 0), avg.get("smem_bank_conflicts", 0)))
+                avg.get("alu_pct", 0), avg.get("fma_pct", 0), avg.get("warp_inst", 0) / 1e6, avg.get("l1_hit_pct", 0), avg.get("l2_hit_pct", 0), avg.get("smem_bank_conflicts", 0)))
         md.append("")
     if os.path.exists(launches):
         rows = [r for r in csv.reader(open(launches)) if len(r) > 5]
@@ -101,8 +105,13 @@ def main():
             md.append("")
     open(os.path.join(ROOT, "profiles", "%s_ncu_summary.md" % tag), "w").write("\n".join(md) + "\n")
     json.dump(summary, open(os.path.join(ROOT, "profiles", "%s_ncu_summary.json" % tag), "w"), indent=1)
-    latest = {k: {"dram_bytes_per_launch": v["dram_bytes_per_launch"], "time_us": v.get("time")} for k, v in summary["kernels"].items()}
+    latest = {k: {"dram_bytes_per_launch": v["dram_bytes_per_launch"], "time_us": v.get("time"), "warp_inst": v.get("warp_inst"),
+                  "issue_active_pct": v.get("issue_active_pct"), "alu_pct": v.get("alu_pct"), "fma_pct": v.get("fma_pct")}
+              for k, v in summary["kernels"].items()}
     latest["_tag"] = tag
+    latest["_commit"] = sys.argv[sys.argv.index("--commit") + 1] if "--commit" in sys.argv else subprocess.run(
+        ["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], stdout=subprocess.PIPE, text=True).stdout.strip()
+    latest["_config"] = sys.argv[sys.argv.index("--config") + 1] if "--config" in sys.argv else "kitti"
     latest["_frames_per_launch"] = int(sys.argv[sys.argv.index("--frames-per-launch") + 1]) if "--frames-per-launch" in sys.argv else 128
     json.dump(latest, open(os.path.join(ROOT, "profiles", "latest_ncu.json"), "w"), indent=1)
     print("\n".join(md))
