@@ -214,6 +214,12 @@ int  orb_synchronize(orb_ctx* ctx);
 /* libm twins used on the device, evaluated on host arrays (test hook): op 0 atan2f(a,b), 1 cosf(a),
  * 2 sinf(a), 3 lround(a) -- the glibc calls of reference src/orb_cpu.cpp:178,217-218,228-232 */
 int  orb_debug_eval_math(orb_ctx* ctx, int op, const float* a, const float* b, int n, float* out);
+/* Bounds-check builds (-DORB_BOUNDS_CHECK: every shared / global index of the ORB kernels is checked before use; stands in
+ * for compute-sanitizer, which is closed on the B200 pool): *enabled = 1 in such a build, *failures = failed checks since the
+ * library was loaded, *first_line = source line (orb_kernels.cuh) of the first one, *kernels_checked = CTAs that ran checks. */
+int  orb_debug_bounds_check(orb_ctx* ctx, int* enabled, unsigned* failures, unsigned* first_line, unsigned* kernels_checked);
+/* launches a kernel in which exactly one check fails (a bounds-check build then reports one more failure) */
+int  orb_debug_bounds_selftest(orb_ctx* ctx);
 /* per-kernel timing (bench / roofline accounting): when enabled, every kernel launch of the detect calls is
  * bracketed by CUDA events on the context's stream.  orb_get_stage_ms waits for the stream and returns, for the
  * launches since the last call, the summed device time [ms] and launch count of

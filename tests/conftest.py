@@ -15,6 +15,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _bounds_check_report():
+    """On a -DORB_BOUNDS_CHECK build (tests/test_gpu_bounds.py sets ORB_EXPECT_BOUNDS_CHECK) print the device-side counters after
+    the last test of the session."""
+    yield
+    if os.environ.get("ORB_EXPECT_BOUNDS_CHECK"):
+        Vm = importlib.import_module("visual-odometry-gpu_b200")
+        c = Vm.Context(Vm.make_params(max_width=64, max_height=64))
+        print("\norb bounds check: enabled=%d failures=%d first_line=%d ctas_checked=%d" % c.bounds_check())
+        c.close()
+
+
 @pytest.fixture(scope="session")
 def O():
     """The CPU parity oracle (test infrastructure; oracle/pyoracle.py)."""

@@ -35,12 +35,14 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS) or os.path.getmtime(__file__) > t
 
 
-def build(force=False, verbose=False, extra=()):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra=(), out=None):
+    """Compile liborb_b200.so in-tree (or a variant build, e.g. -DORB_BOUNDS_CHECK, to `out`)."""
+    if out is None and not force and not needs_build():
         return LIB
+    out = out or LIB
     extra = list(extra) + os.environ.get("ORB_NVCC_EXTRA", "").split()
     cmd = [nvcc_path()] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     env = dict(os.environ)
     env.pop("CXX", None)
     env.pop("CC", None)
@@ -49,7 +51,7 @@ def build(force=False, verbose=False, extra=()):
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout)
     if verbose:
         print(r.stdout)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

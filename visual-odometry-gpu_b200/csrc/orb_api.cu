@@ -337,6 +337,7 @@ int stage_plan(orb_ctx* ctx, int w, int h, int policy, int quota, OrbPlan* P, Bu
     B->tile_b = ctx->d_tile_b1;
   }
   B->frames = ctx->d_frames; B->frame_stride = ctx->frames_slot_bytes; B->pitch0 = ctx->frames_pitch;
+  B->frames_bytes = ctx->frames_slot_bytes * (size_t)ctx->p.max_batch + 16;
   {
     const int rc = update_tmaps(ctx, *P, ctx->d_frames, (size_t)ctx->frames_pitch, ctx->frames_slot_bytes, ctx->p.max_batch);
     if (rc) return rc;
@@ -691,6 +692,7 @@ int orb_internal_run_batch(orb_ctx* ctx, const uint8_t* frames, int frames_on_de
     Bufs B;
     fill_bufs(ctx, &B);
     B.frames = src + (size_t)c0 * stride; B.frame_stride = stride; B.pitch0 = sp; B.frame0 = c0;
+    B.frames_bytes = direct ? stride * (size_t)(n_frames - c0) : ctx->frames_slot_bytes * (size_t)(ctx->p.max_batch - c0) + 16;
     B.out_kps = o_kps + (size_t)c0 * cap; B.out_angles = o_ang + (size_t)c0 * cap; B.out_desc = o_desc + (size_t)c0 * cap;
     B.out_n = o_n + c0; B.out_cap = cap;
     if (ctx->p.keep_side_arrays) {
@@ -946,6 +948,32 @@ void orb_ratio_test(const orb_match* m, int n, float ratio, uint8_t* keep) {
   // if (m.distance < 0.8 * n.distance), reference src/feature_matching.cpp:178 (float distances, double product)
   for (int i = 0; i < n; i++)
     keep[i] = m[i].idx2 >= 0 && (double)(float)m[i].dist1 < (double)ratio * (double)(float)m[i].dist2;
+}
+
+int orb_debug_bounds_check(orb_ctx* ctx, int* enabled, unsigned* failures, unsigned* first_line, unsigned* kernels_checked) {
+  if (!ctx) return ORB_E_INVALID;
+  CK(cudaSetDevice(ctx->p.device));
+  CK(cudaDeviceSynchronize());
+  unsigned v[4] = {0, 0, 0, 0};
+  CK(cudaMemcpyFromSymbol(v, orbk::g_orb_bounds, sizeof(v)));
+#ifdef ORB_BOUNDS_CHECK
+  if (enabled) *enabled = 1;
+#else
+  if (enabled) *enabled = 0;
+#endif
+  if (failures) *failures = v[0];
+  if (first_line) *first_line = v[1];
+  if (kernels_checked) *kernels_checked = v[2];
+  return ORB_OK;
+}
+
+int orb_debug_bounds_selftest(orb_ctx* ctx) {
+  if (!ctx) return ORB_E_INVALID;
+  CK(cudaSetDevice(ctx->p.device));
+  orbk::k_bounds_selftest<<<1, 32, 0, ctx->stream>>>(31);   // lane 31 fails its check in a bounds-check build
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  return ORB_OK;
 }
 
 int orb_debug_eval_math(orb_ctx* ctx, int op, const float* a, const float* b, int n, float* out) {

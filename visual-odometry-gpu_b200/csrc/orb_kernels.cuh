@@ -27,6 +27,23 @@
 
 namespace orbk {
 
+// -DORB_BOUNDS_CHECK: every shared / global index the ORB kernels compute is checked against its buffer before use
+// (compute-sanitizer is closed on the B200 pool; tests/test_gpu_bounds.py runs the parity suite on such a build).  A
+// failing check is counted, with the source line of the first one, in g_orb_bounds; the access still happens.
+__device__ unsigned int g_orb_bounds[4];   // [0] failed checks, [1] first failing line, [2] checks executed (low 32 bits)
+#ifdef ORB_BOUNDS_CHECK
+__device__ __noinline__ void orb_bounds_fail(int line) {
+  if (atomicAdd(&g_orb_bounds[0], 1u) == 0) g_orb_bounds[1] = (unsigned)line;
+}
+#define ORB_CHECK(cond) do { if (!(cond)) orb_bounds_fail(__LINE__); } while (0)
+#define ORB_CHECK_COUNT() do { if (threadIdx.x == 0) atomicAdd(&g_orb_bounds[2], 1u); } while (0)
+#else
+#define ORB_CHECK(cond) ((void)0)
+#define ORB_CHECK_COUNT() ((void)0)
+#endif
+// byte range [p, p + n) inside [base, base + size)
+#define ORB_CHECK_RANGE(p, n, base, size) ORB_CHECK((const char*)(p) >= (const char*)(base) && (const char*)(p) + (n) <= (const char*)(base) + (size))
+
 struct Bufs {
   const uint8_t* frames;         // level 0 of the chunk's first frame
   unsigned long long frame_stride;
@@ -54,6 +71,7 @@ struct Bufs {
   orb_keypoint* side_xy;         // nullable side arrays, [chunk][out_cap]
   int* side_level;
   float* side_resp;
+  unsigned long long frames_bytes;   // bytes addressable from `frames` (bounds-check builds)
   const CUtensorMap* tmaps;      // TMA tensor maps, [3][ORB_MAX_LEVELS]: TM_PIX, TM_BOXW, TM_PATCH per level
   int frame0;                    // index of the wave's first frame inside the level-0 tensor (the whole source batch)
 };
@@ -224,6 +242,7 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
   const int rw = A_TW + 2 * halo, rh = A_TH + 2 * halo;
   const uint8_t* __restrict__ src = B.frames + (size_t)f * B.frame_stride;
   const uint32_t sp = (uint32_t)B.pitch0;
+  ORB_CHECK_COUNT();
 
   for (int i = tid; i < rw + rh; i += A_THREADS) {
     if (i < rw) {
@@ -250,9 +269,12 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
     r1 = min(r1, h + halo - (y0 - halo));
 #pragma unroll 3
     for (int ry = r0; ry < r1; ry++) {
+      ORB_CHECK(ry >= 0 && ry < A_RH && col >= 0 && col < A_RW);
       const uint4 ty = s_yt[ry];
       const uint8_t* q0 = p0 + ty.x;
       const uint8_t* q1 = p0 + ty.y;
+      ORB_CHECK_RANGE(q0, 2, B.frames, B.frames_bytes);      // the second tap may be the byte after the row's last pixel
+      ORB_CHECK_RANGE(q1, 2, B.frames, B.frames_bytes);
       const int h0 = __ldg(q0) * a0 + __ldg(q0 + 1) * a1;
       const int h1 = __ldg(q1) * a0 + __ldg(q1 + 1) * a1;
       const int v = ((((int)ty.z * (h0 >> 4)) >> 16) + (((int)ty.w * (h1 >> 4)) >> 16) + 2) >> 2;
@@ -274,9 +296,13 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
     r1 = min(r1, h + halo - (y0 - halo));
 #pragma unroll (A_UNROLL)
     for (int ry = r0; ry < r1; ry++) {
+      ORB_CHECK(ry >= 0 && ry < A_RH && col >= 0 && col + 1 < A_RP);
       const uint4 ty = s_yt[ry];
       const uint32_t* q0 = (const uint32_t*)(p0 + ty.x);
       const uint32_t* q1 = (const uint32_t*)(p0 + ty.y);
+      ORB_CHECK_RANGE(q0, 8, B.frames, B.frames_bytes);
+      ORB_CHECK_RANGE(q1, 8, B.frames, B.frames_bytes);
+      ORB_CHECK(((uintptr_t)q0 & 3) == 0 && (uint32_t)(base + 8) <= sp);          // both words inside the row
       const uint32_t t0 = prmt(__ldg(q0), __ldg(q0 + 1), sel), t1 = prmt(__ldg(q1), __ldg(q1 + 1), sel);
       const int h0a = (int)__dp2a_lo(xa0, t0, 0u), h0b = (int)__dp2a_hi(xa1, t0, 0u);
       const int h1a = (int)__dp2a_lo(xa0, t1, 0u), h1b = (int)__dp2a_hi(xa1, t1, 0u);
@@ -320,6 +346,8 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
       const uint32_t M = 0x00ff00ffu, R = 0x00800080u;
       const uint8_t* r = s_res + oy0 * A_RP + 8 * g;
       uint8_t* d = dst + (size_t)(y0 + oy0) * G.pitch + x0 + 8 * g;
+      ORB_CHECK(oy0 + A_SEG + 4 <= A_RH && 8 * g + 12 <= A_RP);
+      ORB_CHECK_RANGE(d, 8, dst, (size_t)G.h * G.pitch);                // (later rows of the segment are guarded by y < h)
       uint4 hs[5];
 #pragma unroll
       for (int k = 0; k < A_SEG + 4; k++) {
@@ -396,6 +424,7 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
   const OrbLevel& G = P.lv[l];
   const int x0 = ((tt >> 4) & 0x3fff) * B_TW, y0 = (tt >> 18) * B_TH;
   const int w = G.w, h = G.h;
+  ORB_CHECK_COUNT();
 
   // ---- phase 0/1: stage the tile with one TMA load (box 160 x 72 at (x0 - 16, y0 - 4); everything outside the level
   // reads as 0 -- no valid output depends on it: FAST centres stay >= 3 pixels inside, the 5x5 sums that BRIEF may read
@@ -450,6 +479,7 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
       uint32_t flags = 0;
       if (vmask && sy < B_SH && y >= 3 && y < h - 3) {      // 3 <= y < h-3 (ref src/orb_cpu.cpp:34)
         const uint8_t* rc = s_pix + (sy + 3) * B_SP + pc;
+        ORB_CHECK(rc - 3 * B_SP - 4 >= s_pix && rc + 3 * B_SP + 12 <= s_pix + B_PIX_BYTES);
         const uint32_t m = *(const uint32_t*)(rc - 4), p = *(const uint32_t*)(rc + 8);
         const uint2 cc = *(const uint2*)rc, tt = *(const uint2*)(rc - 3 * B_SP), bb = *(const uint2*)(rc + 3 * B_SP);
         const uint32_t C[4] = {prmt(cc.x, K, 0x4140), prmt(cc.x, K, 0x4342), prmt(cc.y, K, 0x4140), prmt(cc.y, K, 0x4342)};
@@ -525,6 +555,8 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
     for (int j = tid; j < n1; j += B_THREADS) {
       const int idx = s_list[j];
       const int sy = idx / B_SP, pcx = idx - sy * B_SP;
+      ORB_CHECK(j < B_LIST && sy >= 0 && sy < B_SH && pcx >= 15 && pcx <= 16 + B_TW);     // ring reach 3: rows sy .. sy+6, columns pcx-3 .. pcx+3
+      ORB_CHECK(sy * B_SCP + pcx - 12 >= 0 && sy * B_SCP + pcx - 12 < B_SH * B_SCP);
       const int sc = fast_ring_score<B_SP>(s_pix + (sy + 3) * B_SP + pcx, thr, fn);
       if (sc) s_score[sy * B_SCP + pcx - 12] = (uint16_t)sc;
     }
@@ -552,12 +584,14 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
   auto emit = [&](int idx, int slot) {   // key = raster position; k_harris adds the response in the high word
     const int sy = idx / B_SP, pcx = idx - sy * B_SP;
     const int lx = x0 + pcx - 16, ly = y0 - 1 + sy;
+    ORB_CHECK(lx >= 3 && lx < w - 3 && ly >= 3 && ly < h - 3 && slot >= 0);
     if (slot < G.cand_cap) cand[slot] = (unsigned long long)(unsigned)((ly << 16) | lx);
   };
   auto nms_one = [&](int idx) {
     const int sy = idx / B_SP, pcx = idx - sy * B_SP;
     if (sy < 1 || sy > B_TH || pcx < 16 || pcx >= 16 + B_TW) return;   // halo positions belong to neighbours
     const uint16_t* s = s_score + sy * B_SCP + pcx - 12;
+    ORB_CHECK(s - B_SCP - 1 >= s_score && s + B_SCP + 1 < s_score + B_SH * B_SCP);
     const int v = s[0];
     if (v == 0) return;
     if (nmsr) {   // ties keep both (ref src/orb_cpu.cpp:126)
@@ -600,6 +634,9 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
     if (yb < h && x0 + 8 * g < G.bpitch) {
       uint16_t* box = B.box + (size_t)f * P.box_frame_elems + G.box_ofs + (size_t)yb * G.bpitch + x0 + 8 * g;
       const uint8_t* rc = s_pix + (8 * seg + 2) * B_SP + 16 + 8 * g;   // input row yb - 2
+      ORB_CHECK(rc - 4 >= s_pix && rc + 11 * B_SP + 12 <= s_pix + B_PIX_BYTES);
+      ORB_CHECK_RANGE(box, 16, B.box + (size_t)f * P.box_frame_elems + G.box_ofs, (size_t)(G.h + 1) * G.bpitch * 2);
+      ORB_CHECK(G.edge_ofs + G.edge_w + ((h + 3) & ~3) <= P.edge_frame_elems);
       const int nstrip = min(8, h - 4 - yb);                         // owned rows that lie above row h-4
       uint4 hs[5];
       uint4 strip = make_uint4(0, 0, 0, 0), acc = make_uint4(0, 0, 0, 0);
@@ -656,6 +693,7 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
           if (nb > 0) acc = __dp4a(nb >= 4 ? wd[k] : (wd[k] & ((1u << (8 * nb)) - 1u)), 0x01010101u, acc);
         }
       }
+      ORB_CHECK(y >= 0 && y < h && (iy + 4) * B_SP + 16 + ((ncol + 15) & ~15) <= B_PIX_BYTES);
       if (ncol > 0) atomicAdd(rs + y, (int)acc);
       if (x0 == 0 && y < h - 4) atomicAdd(ey, (int)r[0]);
     }
@@ -663,6 +701,7 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
   __syncthreads();
   if (tid < B_TW) {
     const int x = x0 + tid, v = s_ey[16 * (tid & 7) + (tid >> 3)];
+    ORB_CHECK(!(v && x >= 2 && x <= w - 3) || x < G.edge_w);
     if (v && x >= 2 && x <= w - 3) atomicAdd(ey + x, v);
   }
 }
@@ -689,6 +728,7 @@ __global__ void __launch_bounds__(C_THREADS, ORB_C_MINB) k_harris(const OrbPlan 
     unsigned long long* slot = B.cand + (size_t)f * P.cand_frame_elems + G.cand_ofs + j;
     const uint32_t xy = (uint32_t)*slot;
     const int x = xy & 0xffff, y = xy >> 16, w = G.w, h = G.h;
+    ORB_CHECK(j < G.cand_cap && x >= 3 && x < w - 3 && y >= 3 && y < h - 3);
     const uint8_t* img;
     int pitch;
     if (l == 0) { img = B.frames + (size_t)f * B.frame_stride; pitch = B.pitch0; }
@@ -707,6 +747,7 @@ __global__ void __launch_bounds__(C_THREADS, ORB_C_MINB) k_harris(const OrbPlan 
       r = harris_at([&](int dy, int (&v)[9]) {
         const int oy = dy == -4 ? dyt : (dy == 4 ? dyb : dy);
         const uint32_t* q = (const uint32_t*)(base + oy * pitch);
+        ORB_CHECK(((uintptr_t)q & 3) == 0 && (const uint8_t*)q >= img && (const uint8_t*)q + 12 <= img + (size_t)h * pitch && y + oy >= 0 && y + oy < h);
         const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
         const uint32_t a = __funnelshift_r(w0, w1, sh), b = __funnelshift_r(w1, w2, sh), c = w2 >> sh;
         v[0] = a & 0xff; v[1] = (a >> 8) & 0xff; v[2] = (a >> 16) & 0xff; v[3] = a >> 24;
@@ -717,6 +758,7 @@ __global__ void __launch_bounds__(C_THREADS, ORB_C_MINB) k_harris(const OrbPlan 
       r = harris_at([&](int dy, int (&v)[9]) {
         const int oy = dy == -4 ? dyt : (dy == 4 ? dyb : dy);
         const uint8_t* q = ctr + oy * pitch;
+        ORB_CHECK(y + oy >= 0 && y + oy < h && x + dxl >= 0 && x + dxr < w && x - 3 >= 0 && x + 3 < w);
         v[0] = q[dxl];
 #pragma unroll
         for (int c = 1; c < 8; c++) v[c] = q[c - 4];
@@ -817,6 +859,7 @@ __global__ void __launch_bounds__(K2_THREADS) k_select(const OrbPlan P, const Bu
       unsigned long long k = keys[i];
       if (k <= T) {
         int pos = atomicAdd(&s_n, 1);
+        ORB_CHECK(pos < m && npow2 <= npow2_max);
         if (pos < npow2) s_sort[pos] = (k << 32) | (k >> 32);
       }
     }
@@ -834,6 +877,7 @@ __global__ void __launch_bounds__(K2_THREADS) k_select(const OrbPlan P, const Bu
     }
   uint32_t* kxy = B.kept_xy + (size_t)f * P.kept_per_frame + G.kept_ofs;
   float* kr = B.kept_r + (size_t)f * P.kept_per_frame + G.kept_ofs;
+  ORB_CHECK(G.kept_ofs + m <= P.kept_per_frame && n <= G.cand_cap && (n <= K2_SMEM_KEYS || keys == gkeys));
   for (int i = tid; i < m; i += K2_THREADS) {
     unsigned long long v = s_sort[i];
     kxy[i] = (uint32_t)(v >> 32);
@@ -874,15 +918,17 @@ struct EdgeSrc {
 // k_edges from the strip tables: what the reference's four wrapped integral taps add up to.
 //   bot[a * edge_w + cx]  : cy = H-2+a, 2 <= cx <= W-3      right[b * hh + cy] : cx = W-2+b, 2 <= cy <= H-3
 //   corner[a * 2 + b]     : cy = H-2+a, cx = W-2+b          (hh = h rounded up to a multiple of 4)
+__host__ __device__ inline int edge2_level_elems(int edge_w, int h) { return 2 * edge_w + 2 * ((h + 3) & ~3) + 4; }
 struct EdgeTab {
   const int* __restrict__ tab; int W, H, edge_w, hh;
   __device__ __forceinline__ int at(int cx, int cy) const {
     const int a = cy - (H - 2), b = cx - (W - 2);
     const int idx = a >= 0 ? (b >= 0 ? 2 * edge_w + 2 * hh + 2 * a + b : a * edge_w + cx) : 2 * edge_w + b * hh + cy;
+    ORB_CHECK(idx >= 0 && idx < edge2_level_elems(edge_w, H) && cx >= 2 && cx <= W - 1 && cy >= 2 && cy <= H - 1);
     return __ldg(tab + idx);
   }
 };
-__host__ __device__ inline int edge2_level_elems(int edge_w, int h) { return 2 * edge_w + 2 * ((h + 3) & ~3) + 4; }
+
 
 // ---- BRIEF boxes that leave the image on the right / bottom ---------------------------------------
 // The reference's sum5x5 (src/orb_cpu.cpp:190-201) indexes its (H+1)x(W+1) integral image flat, so for centres
@@ -935,6 +981,8 @@ __global__ void __launch_bounds__(E_THREADS) k_edges(const OrbPlan P, const Bufs
   const EdgeSrc E{img, pitch, W, H, ey, ey + ew};
   int* out = B.edge2 + (size_t)f * P.edge2_frame_elems + G.edge2_ofs;
   const bool big = W >= 7 && H >= 7;             // smaller levels cannot hold a keypoint (FAST needs a 3-pixel margin)
+  ORB_CHECK_COUNT();
+  ORB_CHECK(G.edge2_ofs + n_line + 4 <= P.edge2_frame_elems && G.edge_ofs + ew + hh <= P.edge_frame_elems && W <= ew);
   // bottom rows (cy = H-2, H-1; 2 <= cx <= W-3): -(strip above the box), the last row adds the five pixels of row H-4
   const uint8_t* row = img + (size_t)max(H - 4, 0) * pitch;
 #pragma unroll 2
@@ -1009,9 +1057,12 @@ __device__ __forceinline__ void window_issue(uint32_t slot_sa, const uint16_t* _
   if (lane >= 30) return;
   const bool col_ok = xa >= 0 && xa < bpitch;
   uint32_t sa = slot_sa + (uint32_t)(r0 * (W_BW * 2) + c0 * 16);
+  ORB_CHECK(r0 * (W_BW * 2) + c0 * 16 + 7 * 5 * (W_BW * 2) + 16 <= W_SLOT + (r0 < W_BH - 35 ? 0 : 5 * (W_BW * 2)));
   if (col_ok && ky - 19 >= 0 && ky + 19 < h) {   // this lane's column and all 39 rows lie inside the level
     const uint16_t* g = box + (ptrdiff_t)y0 * bpitch + xa;
     const size_t step = (size_t)(5 * bpitch) * 2;
+    ORB_CHECK_RANGE(g, 16, box, (size_t)h * bpitch * 2);
+    ORB_CHECK_RANGE((const char*)g + (r0 < W_BH - 35 ? 7 : 6) * step, 16, box, (size_t)h * bpitch * 2);
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       if (j < 7 || r0 < W_BH - 35)               // (the 40th row of the last group is not part of the window)
@@ -1021,6 +1072,7 @@ __device__ __forceinline__ void window_issue(uint32_t slot_sa, const uint16_t* _
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       const int y = y0 + 5 * j;
+      ORB_CHECK(!(col_ok && y >= 0 && y < h) || (xa + 8 <= bpitch && (size_t)y * bpitch + xa + 8 <= (size_t)h * bpitch));
       if (j < 7 || r0 < W_BH - 35) cp_async_16(sa + j * 5 * (W_BW * 2), box + (ptrdiff_t)y * bpitch + xa, col_ok && y >= 0 && y < h, box);
     }
   }
@@ -1039,6 +1091,7 @@ __device__ __forceinline__ void patch_issue(uint32_t slot_sa, const uint8_t* __r
   const uint8_t* g = ok ? img + (ptrdiff_t)(ky - pr + r0) * pitch + xa : img;
   const size_t step = ok ? (size_t)ROWS_PER * pitch : 0;
   const uint32_t sa = slot_sa + (uint32_t)(r0 * PP + c0 * 16), nb = ok ? 16u : 0u;
+  ORB_CHECK(ky - pr >= 0 && kx - pr >= 0 && ((kx - pr) & 15) + 2 * pr + 1 <= PP && (!ok || xa + 16 <= pitch));
   if (PP == W_PP15) {                            // pr == 15: 31 rows
 #pragma unroll
     for (int j = 0; j < 4; j++)
@@ -1058,6 +1111,7 @@ __device__ __forceinline__ void patch_issue(uint32_t slot_sa, const uint8_t* __r
 __device__ __forceinline__ void patch_moments(uint32_t slot_sa, int kx, int pr, int pp, int lane, int* m10_out, int* m01_out) {
   int m10 = 0, m01 = 0;
   const uint32_t base = slot_sa + (uint32_t)((kx - pr) & 15);
+  ORB_CHECK(((kx - pr) & 15) + 2 * pr + 1 <= pp && (2 * pr + 1) * pp <= W_WARP_BYTES);
   if (pr == 15) {                                                 // patch 31 (include/orb.hpp:12): one column per lane
     if (lane <= 30) {
       uint32_t acc = 0;
@@ -1114,6 +1168,7 @@ __device__ __forceinline__ void brief_of(uint32_t wc_sa, const EdgeTab& T, int k
       int dx1, dy1, dx2, dy2;
       rotate_round(cs, msc, t.x, t.y, &dx1, &dy1);
       rotate_round(cs, msc, t.z, t.w, &dx2, &dy2);
+      ORB_CHECK(abs(dx1) <= 19 && abs(dy1) <= 19 && abs(dx2) <= 19 && abs(dy2) <= 19);      // the window holds offsets -19 .. 19
       const uint32_t s1 = lds_u16(wc_sa + dy1 * (W_BW * 2) + dx1 * 2), s2 = lds_u16(wc_sa + dy2 * (W_BW * 2) + dx2 * 2);
       const uint32_t word = __ballot_sync(0xffffffffu, s1 < s2);   // bit i of word wd == test 32*wd + i
       if (lane == wd) mine = word;
@@ -1134,6 +1189,7 @@ __device__ __forceinline__ void brief_of(uint32_t wc_sa, const EdgeTab& T, int k
     const int cx1 = kx + dx1, cy1 = ky + dy1, cx2 = kx + dx2, cy2 = ky + dy2;
     const bool skip = (uint32_t)(cx1 - 2) > xlim || (uint32_t)(cy1 - 2) > ylim || (uint32_t)(cx2 - 2) > xlim || (uint32_t)(cy2 - 2) > ylim;
     const bool e1 = !skip && (cx1 > W - 3 || cy1 > H - 3), e2 = !skip && (cx2 > W - 3 || cy2 > H - 3);
+    ORB_CHECK(abs(dx1) <= 19 && abs(dy1) <= 19 && abs(dx2) <= 19 && abs(dy2) <= 19);
     int s1 = (int)lds_u16(wc_sa + dy1 * (W_BW * 2) + dx1 * 2), s2 = (int)lds_u16(wc_sa + dy2 * (W_BW * 2) + dx2 * 2);
     if (e1) s1 = T.at(cx1, cy1);
     if (e2) s2 = T.at(cx2, cy2);
@@ -1189,6 +1245,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32, ORB_K3_MINB) k_describe(const O
   }
   if (k0 >= total) return;
   const int n_cta = min(K3_KPS, total - k0);     // keypoints of this CTA; warp w owns q = w, w + K3_WARPS, ...
+  ORB_CHECK_COUNT();
   const int pr = P.patch_radius;
 
   // ---- phase 0: lane = keypoint ------------------------------------------------------------------
@@ -1210,6 +1267,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32, ORB_K3_MINB) k_describe(const O
     k.tab = B.edge2 + (size_t)f * P.edge2_frame_elems + G.edge2_ofs;
     k.bpitch = G.bpitch; k.w = G.w; k.h = G.h; k.edge_w = G.edge_w;
     k.x = x; k.y = y;
+    ORB_CHECK(x >= 0 && x < G.w && y >= 0 && y < G.h && G.edge2_ofs + edge2_level_elems(G.edge_w, G.h) <= P.edge2_frame_elems);
     // the reference sets the angle to 0 when the patch leaves the level (src/orb_cpu.cpp:152-156)
     k.l = (x - pr < 0 || x + pr >= G.w || y - pr < 0 || y + pr >= G.h) ? (l | 0x100) : l;
     k.m10 = 0; k.m01 = 0;
@@ -1315,6 +1373,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32, ORB_K3_MINB) k_describe(const O
     __syncwarp();                                 // ... and everybody else's
     uint32_t word;
     const uint32_t wc_sa = my_sa + (uint32_t)((i % W_DEPTH) * W_SLOT + (19 * W_BW + 19 + ((kx - 19) & 7)) * 2);
+    ORB_CHECK(k0 + q < total && total <= B.out_cap && 19 + 19 + ((kx - 19) & 7) < W_BW);
     brief_of(wc_sa, T, kx, ky, k.c, k.s, B.pattern, lane, &word);
     if (lane < 8) out_words[q * 8 + lane] = word;
     __syncwarp();                                 // the slot is free again
@@ -1393,6 +1452,9 @@ __global__ void __launch_bounds__(M_THREADS) k_match(const orb_descriptor* __res
     out[(size_t)p * out_stride + qi] = m;
   }
 }
+
+// trips one check on purpose (tests/test_gpu_bounds.py: the counters of a bounds-check build do count)
+__global__ void k_bounds_selftest(int n) { ORB_CHECK((int)threadIdx.x < n); }
 
 // libm twins evaluated on arrays (tests/test_gpu_math.py): op 0 atan2f(a,b), 1 cosf(a), 2 sinf(a), 3 lround(a)
 __global__ void k_eval_math(int op, const float* a, const float* b, int n, float* out) {

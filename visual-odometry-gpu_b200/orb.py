@@ -49,7 +49,7 @@ EXPORTS = [
     "orb_abi_version", "orb_default_params", "orb_create", "orb_destroy", "orb_last_error", "orb_set_stream", "orb_use_own_stream",
     "orb_synchronize", "orb_detect_and_compute", "orb_detect_and_compute_batch", "orb_get_level", "orb_level_size",
     "orb_level_quota", "orb_fast_detect", "orb_harris", "orb_orientations", "orb_brief", "orb_get_side_arrays",
-    "orb_get_candidates", "orb_get_harris_weights", "orb_last_launch_count", "orb_set_profiling", "orb_get_stage_ms", "orb_match_knn2", "orb_match_knn2_batch", "orb_ratio_test", "orb_debug_eval_math", "bit_pattern_31_",
+    "orb_get_candidates", "orb_get_harris_weights", "orb_last_launch_count", "orb_set_profiling", "orb_get_stage_ms", "orb_match_knn2", "orb_match_knn2_batch", "orb_ratio_test", "orb_debug_eval_math", "orb_debug_bounds_check", "orb_debug_bounds_selftest", "bit_pattern_31_",
     "orb_png_info", "orb_png_decode_gray8", "orb_imread_gray8", "orb_detect_and_compute_files", "orb_get_ingested_frame", "orb_debug_inflate", "orb_lk_track", "orb_lk_levels", "orb_lk_get_level",
 ]
 
@@ -57,7 +57,8 @@ _lib = None
 
 
 def lib_path():
-    return _build.LIB
+    """The library in use: in-tree liborb_b200.so, or the variant build named by ORB_B200_LIB (tests/test_gpu_bounds.py)."""
+    return os.environ.get("ORB_B200_LIB") or _build.LIB
 
 
 def load_library():
@@ -65,7 +66,7 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    path = os.environ.get("ORB_B200_LIB") or _build.build()
     L = C.CDLL(path)
     vp, i, sz = C.c_void_p, C.c_int, C.c_size_t
     L.orb_abi_version.restype = i
@@ -93,6 +94,8 @@ def load_library():
     L.orb_get_harris_weights.argtypes = [vp, vp]
     L.orb_last_launch_count.argtypes = [vp]
     L.orb_debug_eval_math.argtypes = [vp, i, vp, vp, i, vp]
+    L.orb_debug_bounds_check.argtypes = [vp, vp, vp, vp, vp]
+    L.orb_debug_bounds_selftest.argtypes = [vp]
     L.orb_match_knn2.argtypes = [vp, vp, i, vp, i, i, vp]
     L.orb_match_knn2_batch.argtypes = [vp, vp, vp, i, i, i, vp]
     L.orb_ratio_test.argtypes = [vp, i, C.c_float, vp]
@@ -398,6 +401,15 @@ class Context:
         keep = np.zeros(len(m), np.uint8)
         self.lib.orb_ratio_test(_p(m), len(m), ratio, _p(keep))
         return keep.astype(bool).reshape(np.shape(matches))
+
+    def bounds_check(self):
+        """(enabled, failures, first_line, ctas_checked) of a -DORB_BOUNDS_CHECK build (enabled = 0 in a normal build)."""
+        en, fl, ln, kc = C.c_int(), C.c_uint(), C.c_uint(), C.c_uint()
+        self._ck(self.lib.orb_debug_bounds_check(self.h, C.byref(en), C.byref(fl), C.byref(ln), C.byref(kc)))
+        return en.value, fl.value, ln.value, kc.value
+
+    def bounds_selftest(self):
+        self._ck(self.lib.orb_debug_bounds_selftest(self.h))
 
     def eval_math(self, op, a, b=None):
         a = np.ascontiguousarray(a, np.float32)
