@@ -109,7 +109,8 @@ public:
     std::vector<Keypoint> detect(const cv::Mat& image, int nfeatures) {
         orb_b200_detail::check_image(image);
         this->nfeatures = nfeatures;
-        std::vector<Keypoint> kps(nfeatures > 0 ? nfeatures : 0);
+        if (nfeatures <= 0) return std::vector<Keypoint>();      // detect(pyr, 2 * quota) with quota 0: the reference returns an empty vector
+        std::vector<Keypoint> kps(nfeatures);
         int count = 0;
         h_->check(orb_fast_detect(h_->get(image.cols, image.rows), image.data, image.cols, image.rows, image.step, nfeatures,
                                   reinterpret_cast<orb_keypoint*>(kps.data()), &count));

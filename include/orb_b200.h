@@ -125,6 +125,13 @@ int  orb_level_quota(const orb_ctx* ctx, int level);
  * FAST-n segment test, SAD score, 3x3 NMS; first `nfeatures` survivors in raster order. */
 int  orb_fast_detect(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch,
                      int nfeatures, orb_keypoint* kps, int* n_out);
+/* replaces: NMS() over a caller's score map (reference include/NMS.cuh:5, src/cuda/NMS.cu:21-164): `scores` is a host
+ * float map (w x h, pitch_bytes between rows).  A pixel at least nms_window/2 inside the map is kept iff its score
+ * exceeds `threshold` and no score of its window is strictly greater (ties keep both).  The reference appends survivors
+ * in the arrival order of a global atomic and drops what exceeds nfeatures; here the first `nfeatures` survivors in
+ * raster order are returned (deterministic). */
+int  orb_nms_scores(orb_ctx* ctx, const float* scores, int w, int h, size_t pitch_bytes, int nms_window, int nfeatures,
+                    float threshold, orb_keypoint* kps, int* n_out);
 /* replaces: HarrisScore() (reference include/HarrisScore.cuh:5, src/cuda/HarrisScore.cu:42-89) */
 int  orb_harris(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch,
                 const orb_keypoint* kps, int n, float* response);

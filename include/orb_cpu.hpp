@@ -24,6 +24,15 @@ private:
 class RotatedBRIEFCPU {
 public:
     RotatedBRIEFCPU() {}
+    // 5x5 box sum around (x, y) from an integral image (reference include/orb_cpu.hpp:21, src/orb_cpu.cpp:190-201): four taps
+    // of the caller's CV_32S matrix, addressed through its own row step like cv::Mat::at<int> (`width` is unused there too).
+    // Host arithmetic on caller data -- the descriptors themselves come from compute(), i.e. from the GPU.
+    int sum5x5(const cv::Mat& integral, int x, int y, int /*width*/) {
+        const int x0 = x - 2, y0 = y - 2, x1 = x + 3, y1 = y + 3;
+        const unsigned char* base = integral.data;
+        auto at = [&](int r, int c) { return reinterpret_cast<const int*>(base + (size_t)r * integral.step)[c]; };
+        return at(y1, x1) + at(y0, x0) - at(y0, x1) - at(y1, x0);
+    }
     std::vector<ORBDescriptor> compute(const cv::Mat& image, const std::vector<Keypoint>& keypoints, const std::vector<float>& orientations) {
         return brief.compute(image, keypoints, orientations);
     }

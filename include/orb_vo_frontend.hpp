@@ -73,9 +73,10 @@ inline void calcOpticalFlowPyrLK(const cv::Mat& prevImg, const cv::Mat& nextImg,
   const int n = (int)prevPts.size();
   nextPts.resize(n); status.resize(n); err.resize(n);
   if (!n) return;
-  // cv::TermCriteria: a missing COUNT means 30 iterations, a missing EPS means 0.001 (lkpyramid.cpp)
+  // cv::TermCriteria: a missing COUNT means 30 iterations, a missing EPS means 0.01 (lkpyramid.cpp; tests/test_lk.py pins
+  // the latter against cv2: COUNT-only criteria give exactly the tracks of COUNT+EPS with epsilon 0.01)
   const int max_iter = (criteria.type & cv::TermCriteria::COUNT) ? criteria.maxCount : 30;
-  const double eps = (criteria.type & cv::TermCriteria::EPS) ? criteria.epsilon : 0.001;
+  const double eps = (criteria.type & cv::TermCriteria::EPS) ? criteria.epsilon : 0.01;
   static thread_local detail::TrackerContext holder;
   orb_ctx* ctx = holder.get(prevImg.cols, prevImg.rows);
   const int rc = orb_lk_track(ctx, prevImg.ptr<unsigned char>(0), nextImg.ptr<unsigned char>(0), prevImg.cols, prevImg.rows, prevImg.step,

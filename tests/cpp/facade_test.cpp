@@ -53,6 +53,28 @@ int main(int argc, char** argv) {
         Orientations(image, kf, af, 31);
         Brief(image, kf, af, df, 256, 31);
         HarrisScore(image, kf, hf, 7, 0.04f);
+        // the reference's call site passes a double literal (src/orb.cpp:65): resolves to the floating-point overload, k = 0.04
+        std::vector<float> hd; HarrisScore(image, kf, hd, 7, 0.04);
+        if (hd != hf) { fprintf(stderr, "HarrisScore(double) differs from HarrisScore(float)\n"); return 6; }
+        // the reference's exact signature, through a pointer of that type (include/HarrisScore.cuh:5): integer k
+        void (*harris_ref)(const cv::Mat&, std::vector<Keypoint>&, std::vector<float>&, int, int) = &HarrisScore;
+        std::vector<float> h0; harris_ref(image, kf, h0, 7, 0);
+        dump(out + ".free.harris_k0", h0);
+        // NMS() over a caller's score map (include/NMS.cuh:5): a synthetic float map with plateaus
+        std::vector<float> smap((size_t)w * h);
+        for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) smap[(size_t)y * w + x] = (float)(((x * 7 + y * 13) % 31) * ((x ^ y) & 1));
+        cv::Mat score(h, w, CV_32FC1, smap.data());
+        std::vector<Keypoint> kn; NMS(score, kn, 3, 5000, 10.0f);
+        dump(out + ".free.nms", kn);
+        // RotatedBRIEFCPU::sum5x5 (include/orb_cpu.hpp:21): four taps of a caller's integral image
+        std::vector<int> integ((size_t)(w + 1) * (h + 1), 0);
+        for (int y = 0; y < h; y++) { int run = 0; for (int x = 0; x < w; x++) { run += pix[(size_t)y * w + x]; integ[(size_t)(y + 1) * (w + 1) + x + 1] = integ[(size_t)y * (w + 1) + x + 1] + run; } }
+        cv::Mat imat(h + 1, w + 1, CV_32SC1, integ.data());
+        RotatedBRIEFCPU bcpu;
+        long box = 0; for (int dy = -2; dy <= 2; dy++) for (int dx = -2; dx <= 2; dx++) box += pix[(size_t)(100 + dy) * w + 200 + dx];
+        if (bcpu.sum5x5(imat, 200, 100, w + 1) != box) { fprintf(stderr, "sum5x5\n"); return 7; }
+        // detect(image, 0): the reference returns an empty vector (quota 0 levels)
+        if (!fast.detect(image, 0).empty()) { fprintf(stderr, "detect(0)\n"); return 8; }
         if (kp_count != (int)kf.size() || kf.size() != ks.size()) { fprintf(stderr, "Fast() count\n"); return 5; }
         dump(out + ".free.kps", kf); dump(out + ".free.ang", af); dump(out + ".free.desc", df); dump(out + ".free.harris", hf);
         long s = 0; for (int i = 0; i < 1024; i++) s += bit_pattern_31_[i];

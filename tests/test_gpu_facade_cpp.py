@@ -63,6 +63,20 @@ def test_facade_matches_oracle(tmp_path, V, O, kitti0):
     assert np.array_equal(k, kr) and np.array_equal(a.view(np.uint32), ar.view(np.uint32)) and np.array_equal(d, O.brief(kitti0, kr, ar))
     hs = np.fromfile(out + ".free.harris", dtype=np.float32)
     assert np.array_equal(hs.view(np.uint32), O.harris(kitti0, kr, 0.04).view(np.uint32))
+    h0 = np.fromfile(out + ".free.harris_k0", dtype=np.float32)                     # the reference's `int k` signature: k = 0
+    assert np.array_equal(h0.view(np.uint32), O.harris(kitti0, kr, 0.0).view(np.uint32))
+    # NMS() over the synthetic score map of facade_test.cpp
+    ys, xs = np.mgrid[0:376, 0:1241]
+    m = (((xs * 7 + ys * 13) % 31) * ((xs ^ ys) & 1)).astype(np.float32)
+    pad = np.zeros((378, 1243), np.float32)
+    pad[1:-1, 1:-1] = m
+    best = np.max([pad[1 + dy:377 + dy, 1 + dx:1242 + dx] for dy in (-1, 0, 1) for dx in (-1, 0, 1)], axis=0)
+    keep = (m > 10) & (m >= best)
+    keep[0, :] = keep[-1, :] = False
+    keep[:, 0] = keep[:, -1] = False
+    ky, kx = np.nonzero(keep)
+    kn = np.fromfile(out + ".free.nms", dtype=V.KP)
+    assert np.array_equal(kn["x"], kx[:5000]) and np.array_equal(kn["y"], ky[:5000])
 
 
 def _build_feature2d(tmp_path, V):

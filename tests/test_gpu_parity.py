@@ -118,6 +118,30 @@ def test_fast_nms_keypoint_sets(V, O, kitti0, thr, n, nms):
     c.close()
 
 
+def test_nms_over_a_callers_score_map(V, O, kitti0):
+    """NMS() of the reference's stage seam (include/NMS.cuh:5, src/cuda/NMS.cu:95-127): score > threshold, no strictly greater
+    score in the window (ties keep both), centres at least window/2 inside the map; survivors in raster order."""
+    c = V.Context(V.make_params(nfeatures=3000, nlevels=1, select_policy=V.SELECT_RASTER_FIRST_N, max_width=1241, max_height=376))
+    sc = O.fast_scores(kitti0, 20).astype(np.float32)
+    assert np.array_equal(c.nms_scores(sc, 3, 8192), O.nms(sc, 3))                 # FAST scores: the FAST + NMS stage itself
+    assert np.array_equal(c.nms_scores(sc, 3, 100), O.nms(sc, 3)[:100])
+    rng = np.random.default_rng(11)
+    for (h, w), win, thr in (((60, 90), 3, 0.5), ((47, 131), 5, 0.25), ((33, 40), 1, 0.9), ((20, 300), 7, 0.0)):
+        m = rng.random((h, w), dtype=np.float32)
+        m[rng.random((h, w)) < 0.3] = np.float32(0.75)                                 # plateaus: exact ties
+        r = win // 2
+        pad = np.zeros((h + 2 * r, w + 2 * r), np.float32)
+        pad[r:h + r, r:w + r] = m
+        best = np.max([pad[r + dy:r + dy + h, r + dx:r + dx + w] for dy in range(-r, r + 1) for dx in range(-r, r + 1)], axis=0)
+        keep = (m > thr) & (m >= best)
+        keep[:r, :] = keep[h - r:, :] = False
+        keep[:, :r] = keep[:, w - r:] = False
+        ys, xs = np.nonzero(keep)
+        got = c.nms_scores(np.ascontiguousarray(np.pad(m, ((0, 0), (0, 5)))[:, :w]), win, 8192, thr)     # padded rows (pitch > w)
+        assert len(got) == len(xs) > 0 and np.array_equal(got["x"], xs) and np.array_equal(got["y"], ys)
+    c.close()
+
+
 def test_reference_single_level_mode_golden(V, golden, kitti0, kitti1):
     """ORBCPU as shipped (D3) -- compared with the outputs of the reference's own compiled code."""
     orb = V.ORBCPU(max_width=1241, max_height=376)

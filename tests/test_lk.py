@@ -71,6 +71,22 @@ def test_oracle_pinned_against_cv2(O, cfg):
     assert np.abs(er1 - er2)[ok].max() < 0.1
 
 
+def test_count_only_criteria_mean_epsilon_001():
+    """What include/orb_vo_frontend.hpp substitutes when TermCriteria has no EPS flag: OpenCV then uses epsilon 0.01, whatever
+    the epsilon field says (the adapter used 0.001)."""
+    import cv2
+    a, b = kitti_pair()
+    pts = fast_points(a, 800).reshape(-1, 1, 2)
+
+    def run(crit):
+        return cv2.calcOpticalFlowPyrLK(a, b, pts.copy(), None, winSize=(21, 21), maxLevel=3, criteria=crit, flags=0, minEigThreshold=0.001)[0]
+    count_only = run((cv2.TERM_CRITERIA_COUNT, 30, 0.5))
+    assert np.array_equal(count_only, run((cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)))
+    assert not np.array_equal(count_only, run((cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.001)))
+    src = open(os.path.join(os.path.dirname(GOLDEN), "..", "include", "orb_vo_frontend.hpp")).read()
+    assert "criteria.epsilon : 0.01;" in src
+
+
 def test_oracle_recovers_a_known_shift(O):
     a, _ = kitti_pair()
     b = np.roll(a, (3, -5), (0, 1))                   # content moves by (+3 rows, -5 columns)

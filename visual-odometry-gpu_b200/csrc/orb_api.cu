@@ -29,7 +29,7 @@ struct PatternInit {
   PatternInit() { for (int i = 0; i < 1024; i++) bit_pattern_31_[i] = ORB_BRIEF_PATTERN_31[i]; }
 } g_pattern_init;
 }  // namespace
-char g_orb_create_error[512] = "";
+thread_local char g_orb_create_error[512] = "";   // errors without a context (orb_create, PNG helpers): per thread
 #define g_create_error g_orb_create_error
 
 namespace {
@@ -378,6 +378,8 @@ void orb_destroy(orb_ctx* ctx) {
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   if (ctx->h_ingest) cudaFreeHost(ctx->h_ingest);
   if (ctx->d_lk) cudaFree(ctx->d_lk);
+  if (ctx->d_scores) cudaFree(ctx->d_scores);
+  for (void* q : ctx->d_scratch) if (q) cudaFree(q);
   if (ctx->h_comp) cudaFreeHost(ctx->h_comp);
   if (ctx->h_descs) cudaFreeHost(ctx->h_descs);
   if (ctx->h_inf_status) cudaFreeHost(ctx->h_inf_status);
@@ -420,6 +422,9 @@ int orb_create(const orb_params* p, orb_ctx** out) {
   if (p->nfeatures < 1) return fail(ctx, ORB_E_INVALID, "nfeatures must be >= 1");
   if (p->max_width < 1 || p->max_height < 1 || p->max_width > 65535 || p->max_height > 65535 || p->max_batch < 1)
     return fail(ctx, ORB_E_INVALID, "bad capacity fields");
+  // per-level pixel counts and offsets are 32-bit in the plan: 2^28 pixels per frame keep every product below 2^31
+  if ((long long)p->max_width * p->max_height > (1ll << 28))
+    return fail(ctx, ORB_E_CAPACITY, "frame capacity %dx%d exceeds 2^28 pixels", p->max_width, p->max_height);
   if ((p->select_policy == ORB_SELECT_RASTER_FIRST_N ? p->nfeatures : level_quota(p->nfeatures, p->scale_factor, p->nlevels, 0)) > ORB_SORT_CAP)
     return fail(ctx, ORB_E_INVALID, "per-level keypoint budget exceeds %d", ORB_SORT_CAP);
 
@@ -596,7 +601,27 @@ int orb_get_stage_ms(orb_ctx* ctx, float ms[5], int launches[5]) {
 
 }  // extern "C"
 
+static int run_batch_body(orb_ctx* ctx, const uint8_t* frames, int frames_on_device, int n_frames, int w, int h,
+                     size_t pitch, size_t frame_stride, int cap, orb_keypoint* kps, float* angles,
+                     orb_descriptor* desc, int* n_out, int outputs_on_device, WaveSource* source);
+
 int orb_internal_run_batch(orb_ctx* ctx, const uint8_t* frames, int frames_on_device, int n_frames, int w, int h,
+                     size_t pitch, size_t frame_stride, int cap, orb_keypoint* kps, float* angles,
+                     orb_descriptor* desc, int* n_out, int outputs_on_device, WaveSource* source) {
+  const int rc = run_batch_body(ctx, frames, frames_on_device, n_frames, w, h, pitch, frame_stride, cap, kps, angles, desc, n_out,
+                                outputs_on_device, source);
+  if (rc != ORB_OK && ctx && ctx->s_h2d) {
+    // a failure in the middle of the wave pipeline: copies into / out of the caller's host buffers may still be in flight on
+    // the copy streams -- drain them before the buffers go back to the caller (the error text is already in ctx->err)
+    cudaStreamSynchronize(ctx->s_h2d);
+    cudaStreamSynchronize(ctx->s_d2h);
+    cudaStreamSynchronize(ctx->s_side);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  return rc;
+}
+
+static int run_batch_body(orb_ctx* ctx, const uint8_t* frames, int frames_on_device, int n_frames, int w, int h,
                      size_t pitch, size_t frame_stride, int cap, orb_keypoint* kps, float* angles,
                      orb_descriptor* desc, int* n_out, int outputs_on_device, WaveSource* source) {
   if (!ctx) return ORB_E_INVALID;
@@ -886,6 +911,56 @@ int orb_brief(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch, cons
   return describe_list(ctx, img, w, h, pitch, kps, angles, n, nullptr, desc);
 }
 
+int orb_nms_scores(orb_ctx* ctx, const float* scores, int w, int h, size_t pitch_bytes, int nms_window, int nfeatures, float threshold,
+                   orb_keypoint* kps, int* n_out) {
+  if (!ctx || !scores || !kps || !n_out) return ORB_E_INVALID;
+  if (w < 1 || h < 1 || pitch_bytes < (size_t)w * 4 || pitch_bytes % 4) return fail(ctx, ORB_E_INVALID, "bad score map geometry");
+  if (w > ctx->p.max_width || h > ctx->p.max_height)
+    return fail(ctx, ORB_E_CAPACITY, "score map %dx%d exceeds context capacity %dx%d", w, h, ctx->p.max_width, ctx->p.max_height);
+  if (nfeatures < 0 || nfeatures > ORB_SORT_CAP) return fail(ctx, ORB_E_CAPACITY, "nfeatures must be 0..%d", ORB_SORT_CAP);
+  if (nms_window < 1 || nms_window > 7) return fail(ctx, ORB_E_INVALID, "nms_window must be 1..7");
+  CK(cudaSetDevice(ctx->p.device));
+  const size_t need = (size_t)w * h * sizeof(float);
+  if (need > ctx->d_scores_bytes) {             // grow-only scratch for the uploaded map
+    if (ctx->d_scores) CK(cudaFree(ctx->d_scores));
+    ctx->d_scores = nullptr; ctx->d_scores_bytes = 0;
+    CK(cudaMalloc(&ctx->d_scores, need));
+    ctx->d_scores_bytes = need;
+  }
+  CK(cudaMemcpy2DAsync(ctx->d_scores, (size_t)w * 4, scores, pitch_bytes, (size_t)w * 4, h, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->last_n = 0;
+  OrbPlan P; Bufs B;
+  int rc;
+  if ((rc = stage_plan(ctx, w, h, ORB_SELECT_RASTER_FIRST_N, nfeatures, &P, &B))) return rc;
+  CK(cudaMemsetAsync(ctx->d_cand_count, 0, ctx->zero_bytes_per_frame, ctx->stream));
+  orbk::k_nms_scores<<<dim3((w + 127) / 128, h), 128, 0, ctx->stream>>>(ctx->d_scores, w, w, h, nms_window / 2, threshold, ctx->d_cand,
+                                                                      ctx->d_cand_count, P.lv[0].cand_cap);
+  CK(cudaGetLastError());
+  ctx->launches = 1;
+  if ((rc = launch_select(ctx, P, B, 1))) return rc;
+  int m = 0;
+  CK(cudaMemcpyAsync(&m, ctx->d_kept_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if ((rc = check_flags(ctx))) return rc;
+  std::vector<uint32_t> xy(std::max(m, 1));
+  CK(cudaMemcpy(xy.data(), ctx->d_kept_xy, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < m; i++) kps[i] = orb_keypoint{(int)(xy[i] & 0xffff), (int)(xy[i] >> 16)};
+  *n_out = m;
+  return ORB_OK;
+}
+
+// grow-only device scratch of the context for the host-buffer paths of the matcher / debug calls (nothing is allocated
+// per call once it is large enough; freed in orb_destroy)
+static int scratch(orb_ctx* ctx, int slot, size_t bytes, void** out) {
+  if (bytes > ctx->scratch_bytes[slot]) {
+    if (ctx->d_scratch[slot]) CK(cudaFree(ctx->d_scratch[slot]));
+    ctx->d_scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0;
+    CK(cudaMalloc(&ctx->d_scratch[slot], bytes));
+    ctx->scratch_bytes[slot] = bytes;
+  }
+  *out = ctx->d_scratch[slot];
+  return ORB_OK;
+}
+
 // ---- descriptor matching -------------------------------------------------------------------------
 static int match_launch(orb_ctx* ctx, const orb_descriptor* dq, const orb_descriptor* dt, const int* dn, int nq, int nt, int npairs,
                         long long sq, long long st, long long so, orb_match* dout) {
@@ -905,18 +980,16 @@ int orb_match_knn2(orb_ctx* ctx, const orb_descriptor* query, int nq, const orb_
   CK(cudaSetDevice(ctx->p.device));
   if (on_device) return match_launch(ctx, query, train, nullptr, nq, nt, 1, 0, 0, 0, out);
   orb_descriptor *dq = nullptr, *dt = nullptr; orb_match* dm = nullptr;
-  CK(cudaMalloc(&dq, sizeof(orb_descriptor) * (size_t)nq));
-  CK(cudaMalloc(&dt, sizeof(orb_descriptor) * (size_t)std::max(nt, 1)));
-  CK(cudaMalloc(&dm, sizeof(orb_match) * (size_t)nq));
+  int rc;
+  if ((rc = scratch(ctx, 0, sizeof(orb_descriptor) * (size_t)nq, (void**)&dq))) return rc;
+  if ((rc = scratch(ctx, 1, sizeof(orb_descriptor) * (size_t)std::max(nt, 1), (void**)&dt))) return rc;
+  if ((rc = scratch(ctx, 2, sizeof(orb_match) * (size_t)nq, (void**)&dm))) return rc;
   CK(cudaMemcpyAsync(dq, query, sizeof(orb_descriptor) * (size_t)nq, cudaMemcpyHostToDevice, ctx->stream));
   if (nt) CK(cudaMemcpyAsync(dt, train, sizeof(orb_descriptor) * (size_t)nt, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = match_launch(ctx, dq, dt, nullptr, nq, nt, 1, 0, 0, 0, dm);
-  if (!rc) {
-    CK(cudaMemcpyAsync(out, dm, sizeof(orb_match) * (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-  }
-  cudaFree(dq); cudaFree(dt); cudaFree(dm);
-  return rc;
+  if ((rc = match_launch(ctx, dq, dt, nullptr, nq, nt, 1, 0, 0, 0, dm))) return rc;
+  CK(cudaMemcpyAsync(out, dm, sizeof(orb_match) * (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return ORB_OK;
 }
 
 int orb_match_knn2_batch(orb_ctx* ctx, const orb_descriptor* desc, const int* n, int n_frames, int cap, int on_device,
@@ -929,19 +1002,17 @@ int orb_match_knn2_batch(orb_ctx* ctx, const orb_descriptor* desc, const int* n,
   if (on_device) return match_launch(ctx, desc, desc + cap, n, cap, cap, n_frames - 1, s, s, s, out);
   orb_descriptor* dd = nullptr; int* dn = nullptr; orb_match* dm = nullptr;
   const size_t nd = (size_t)n_frames * cap, nm = (size_t)(n_frames - 1) * cap;
-  CK(cudaMalloc(&dd, sizeof(orb_descriptor) * nd));
-  CK(cudaMalloc(&dn, sizeof(int) * n_frames));
-  CK(cudaMalloc(&dm, sizeof(orb_match) * nm));
+  int rc;
+  if ((rc = scratch(ctx, 0, sizeof(orb_descriptor) * nd, (void**)&dd))) return rc;
+  if ((rc = scratch(ctx, 1, sizeof(int) * n_frames, (void**)&dn))) return rc;
+  if ((rc = scratch(ctx, 2, sizeof(orb_match) * nm, (void**)&dm))) return rc;
   CK(cudaMemcpyAsync(dd, desc, sizeof(orb_descriptor) * nd, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(dn, n, sizeof(int) * n_frames, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(dm, out, sizeof(orb_match) * nm, cudaMemcpyHostToDevice, ctx->stream));   // entries >= n[p] stay as they were
-  int rc = match_launch(ctx, dd, dd + cap, dn, cap, cap, n_frames - 1, s, s, s, dm);
-  if (!rc) {
-    CK(cudaMemcpyAsync(out, dm, sizeof(orb_match) * nm, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-  }
-  cudaFree(dd); cudaFree(dn); cudaFree(dm);
-  return rc;
+  if ((rc = match_launch(ctx, dd, dd + cap, dn, cap, cap, n_frames - 1, s, s, s, dm))) return rc;
+  CK(cudaMemcpyAsync(out, dm, sizeof(orb_match) * nm, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return ORB_OK;
 }
 
 void orb_ratio_test(const orb_match* m, int n, float ratio, uint8_t* keep) {
@@ -980,16 +1051,15 @@ int orb_debug_eval_math(orb_ctx* ctx, int op, const float* a, const float* b, in
   if (!ctx || !a || !out || n < 0 || op < 0 || op > 3 || (op == 0 && !b)) return ORB_E_INVALID;
   CK(cudaSetDevice(ctx->p.device));
   float *da = nullptr, *db = nullptr, *dout = nullptr;
-  CK(cudaMalloc(&da, sizeof(float) * std::max(n, 1)));
-  CK(cudaMalloc(&db, sizeof(float) * std::max(n, 1)));
-  CK(cudaMalloc(&dout, sizeof(float) * std::max(n, 1)));
-  CK(cudaMemcpy(da, a, sizeof(float) * n, cudaMemcpyHostToDevice));
-  if (b) CK(cudaMemcpy(db, b, sizeof(float) * n, cudaMemcpyHostToDevice));
+  int rc;
+  const size_t nb = sizeof(float) * (size_t)std::max(n, 1);
+  if ((rc = scratch(ctx, 0, nb, (void**)&da)) || (rc = scratch(ctx, 1, nb, (void**)&db)) || (rc = scratch(ctx, 2, nb, (void**)&dout))) return rc;
+  CK(cudaMemcpyAsync(da, a, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+  if (b) CK(cudaMemcpyAsync(db, b, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
   if (n > 0) orbk::k_eval_math<<<(n + 255) / 256, 256, 0, ctx->stream>>>(op, da, db, n, dout);
   CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, dout, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  CK(cudaMemcpy(out, dout, sizeof(float) * n, cudaMemcpyDeviceToHost));
-  cudaFree(da); cudaFree(db); cudaFree(dout);
   return ORB_OK;
 }
 

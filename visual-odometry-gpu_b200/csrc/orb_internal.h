@@ -30,6 +30,8 @@ struct orb_ctx {
   uint8_t* d_frames = nullptr; size_t frames_slot_bytes = 0; int frames_pitch = 0;
   uint8_t* d_pyr = nullptr; uint16_t* d_box = nullptr; unsigned long long* d_cand = nullptr;
   int* d_edge2 = nullptr;
+  void* d_scratch[3] = {nullptr, nullptr, nullptr}; size_t scratch_bytes[3] = {0, 0, 0};   // host-buffer matcher / debug calls (grow-only)
+  float* d_scores = nullptr; size_t d_scores_bytes = 0;   // orb_nms_scores: the caller's score map (grow-only)
   int* d_cand_count = nullptr; size_t zero_bytes_per_frame = 0; uint32_t* d_kept_xy = nullptr; float* d_kept_r = nullptr; int* d_kept_count = nullptr;
   OrbTap *d_xtab = nullptr, *d_ytab = nullptr;
   uint32_t *d_tile_a = nullptr, *d_tile_b = nullptr, *d_tile_b1 = nullptr; int tile_a_cap = 0, tile_b_cap = 0;
@@ -71,7 +73,7 @@ struct orb_ctx {
   std::vector<Span> spans; size_t spans_used = 0;
 };
 
-extern char g_orb_create_error[512];
+extern thread_local char g_orb_create_error[512];
 
 inline int orb_fail(orb_ctx* c, int code, const char* fmt, ...) {
   char* dst = c ? c->err : g_orb_create_error;

@@ -1453,6 +1453,23 @@ __global__ void __launch_bounds__(M_THREADS) k_match(const orb_descriptor* __res
   }
 }
 
+// NMS over a caller's float score map (stage entry point orb_nms_scores; ref d_NMS, src/cuda/NMS.cu:21-128): a pixel at
+// least `r` inside the map is kept iff its score exceeds `threshold` and no score in its (2r+1)^2 window is strictly
+// greater (ties keep both; outside the map reads 0).  Survivors go to the level-0 candidate list as raster keys; k_select
+// (raster policy) then keeps the first nfeatures of them in raster order.
+__global__ void k_nms_scores(const float* __restrict__ sc, int pitch, int w, int h, int r, float threshold, unsigned long long* cand,
+                             int* count, int cap) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x < r || y < r || x >= w - r || y >= h - r) return;
+  const float v = sc[(size_t)y * pitch + x];
+  if (!(v > threshold)) return;
+  for (int dy = -r; dy <= r; dy++)
+    for (int dx = -r; dx <= r; dx++)
+      if (sc[(size_t)(y + dy) * pitch + x + dx] > v) return;
+  const int slot = atomicAdd(count, 1);
+  if (slot < cap) cand[slot] = (unsigned long long)(unsigned)((y << 16) | x);
+}
+
 // trips one check on purpose (tests/test_gpu_bounds.py: the counters of a bounds-check build do count)
 __global__ void k_bounds_selftest(int n) { ORB_CHECK((int)threadIdx.x < n); }
 

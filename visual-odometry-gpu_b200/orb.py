@@ -48,7 +48,7 @@ class ImageInfo(C.Structure):
 EXPORTS = [
     "orb_abi_version", "orb_default_params", "orb_create", "orb_destroy", "orb_last_error", "orb_set_stream", "orb_use_own_stream",
     "orb_synchronize", "orb_detect_and_compute", "orb_detect_and_compute_batch", "orb_get_level", "orb_level_size",
-    "orb_level_quota", "orb_fast_detect", "orb_harris", "orb_orientations", "orb_brief", "orb_get_side_arrays",
+    "orb_level_quota", "orb_fast_detect", "orb_nms_scores", "orb_harris", "orb_orientations", "orb_brief", "orb_get_side_arrays",
     "orb_get_candidates", "orb_get_harris_weights", "orb_last_launch_count", "orb_set_profiling", "orb_get_stage_ms", "orb_match_knn2", "orb_match_knn2_batch", "orb_ratio_test", "orb_debug_eval_math", "orb_debug_bounds_check", "orb_debug_bounds_selftest", "bit_pattern_31_",
     "orb_png_info", "orb_png_decode_gray8", "orb_imread_gray8", "orb_detect_and_compute_files", "orb_get_ingested_frame", "orb_debug_inflate", "orb_lk_track", "orb_lk_levels", "orb_lk_get_level",
 ]
@@ -347,6 +347,17 @@ class Context:
         self._ck(self.lib.orb_fast_detect(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], nfeatures,
                                           _p(kps), C.byref(n)))
         return kps[:n.value].copy()
+
+    def nms_scores(self, scores, nms_window, nfeatures, threshold=0.0):
+        """NMS over a float score map (reference NMS(), include/NMS.cuh:5): first `nfeatures` survivors in raster order."""
+        sc = np.asarray(scores)
+        if sc.dtype != np.float32 or sc.ndim != 2 or sc.strides[1] != 4:
+            raise ValueError("scores must be a 2-D float32 array with contiguous rows")
+        kps = np.zeros(max(nfeatures, 1), KP)
+        n = C.c_int()
+        self._ck(self.lib.orb_nms_scores(self.h, _p(sc), sc.shape[1], sc.shape[0], C.c_size_t(sc.strides[0]), int(nms_window), int(nfeatures),
+                                         C.c_float(threshold), _p(kps), C.byref(n)))
+        return kps[:n.value]
 
     def harris(self, image, kps):
         img = _img(image)
