@@ -126,34 +126,43 @@ __device__ __forceinline__ float ord2f(uint32_t k) {
 // columns give Ix = V[c+1] - V[c-1], the horizontal [1 2 1] sums of the rows above / below give Iy.
 __constant__ float c_harris_w[49];   // createGaussianKernel(7), ref src/GaussianBlur.cpp:7-37 (uploaded at orb_create)
 
-__device__ __forceinline__ float int2float_exact(int v) {   // |v| < 2^22: exact, two full-rate instructions
-  return __fsub_rn(__int_as_float(0x4B400000 + v), 12582912.0f);
+// byte `sel` (0..3 of a, 4..7 of b) of the word pair as an exact float: 2^23 + byte assembled by one byte permute
+// (0x4B0000xx), minus 2^23
+__device__ __forceinline__ float byte2float(uint32_t a, uint32_t b, uint32_t sel) {
+  // the constant 0x4B000000 supplies bytes 1..3; selector picks the pixel byte into byte 0
+  return __fsub_rn(__uint_as_float(__byte_perm(a, b, sel)), 8388608.0f);
 }
 
+// All Sobel arithmetic is done in float on small integers (|values| <= 4 * 255, products < 2^24), i.e. exactly: the
+// results equal the integer Sobel sums and products the oracle converts to float, so only the 147 weighted
+// accumulations round -- in the reference order.
 template <typename ROW>
 __device__ __forceinline__ float harris_at(ROW row, float k) {
   float A = 0.f, B = 0.f, C = 0.f;
-  int pm[9], pc[9], pp[9], hm[7], hc[7], hp[7];
+  float pm[9], pc[9], pp[9], hm[7], hc[7], hp[7];
   row(-4, pm);
   row(-3, pc);
 #pragma unroll
-  for (int j = 0; j < 7; j++) { hm[j] = pm[j] + 2 * pm[j + 1] + pm[j + 2]; hc[j] = pc[j] + 2 * pc[j + 1] + pc[j + 2]; }
+  for (int j = 0; j < 7; j++) {
+    hm[j] = __fadd_rn(__fmaf_rn(pm[j + 1], 2.0f, pm[j]), pm[j + 2]);
+    hc[j] = __fadd_rn(__fmaf_rn(pc[j + 1], 2.0f, pc[j]), pc[j + 2]);
+  }
 #pragma unroll
   for (int dy = -3; dy <= 3; dy++) {
     row(dy + 1, pp);
 #pragma unroll
-    for (int j = 0; j < 7; j++) hp[j] = pp[j] + 2 * pp[j + 1] + pp[j + 2];
-    int V[9];
+    for (int j = 0; j < 7; j++) hp[j] = __fadd_rn(__fmaf_rn(pp[j + 1], 2.0f, pp[j]), pp[j + 2]);
+    float V[9];
 #pragma unroll
-    for (int c = 0; c < 9; c++) V[c] = pm[c] + 2 * pc[c] + pp[c];
+    for (int c = 0; c < 9; c++) V[c] = __fadd_rn(__fmaf_rn(pc[c], 2.0f, pm[c]), pp[c]);
 #pragma unroll
     for (int j = 0; j < 7; j++) {
-      const int ix = V[j + 2] - V[j];          // Sobel x at (dy, j-3)
-      const int iy = hp[j] - hm[j];            // Sobel y at (dy, j-3)
+      const float ix = __fsub_rn(V[j + 2], V[j]);          // Sobel x at (dy, j-3)
+      const float iy = __fsub_rn(hp[j], hm[j]);            // Sobel y at (dy, j-3)
       const float g = c_harris_w[(dy + 3) * 7 + j];
-      A = orbm::fadd(A, orbm::fmul(int2float_exact(ix * ix), g));
-      B = orbm::fadd(B, orbm::fmul(int2float_exact(ix * iy), g));
-      C = orbm::fadd(C, orbm::fmul(int2float_exact(iy * iy), g));
+      A = orbm::fadd(A, orbm::fmul(__fmul_rn(ix, ix), g));
+      B = orbm::fadd(B, orbm::fmul(__fmul_rn(ix, iy), g));
+      C = orbm::fadd(C, orbm::fmul(__fmul_rn(iy, iy), g));
     }
 #pragma unroll
     for (int c = 0; c < 9; c++) { pm[c] = pc[c]; pc[c] = pp[c]; }
@@ -744,25 +753,26 @@ __global__ void __launch_bounds__(C_THREADS, ORB_C_MINB) k_harris(const OrbPlan 
       // word, which holds column x+4 < w, is inside the row): 3 loads + 3 funnel shifts per row instead of 9 byte loads
       const int sh = 8 * ((x - 4) & 3);
       const uint8_t* base = ctr - 4 - ((x - 4) & 3);
-      r = harris_at([&](int dy, int (&v)[9]) {
+      r = harris_at([&](int dy, float (&v)[9]) {
         const int oy = dy == -4 ? dyt : (dy == 4 ? dyb : dy);
         const uint32_t* q = (const uint32_t*)(base + oy * pitch);
         ORB_CHECK(((uintptr_t)q & 3) == 0 && (const uint8_t*)q >= img && (const uint8_t*)q + 12 <= img + (size_t)h * pitch && y + oy >= 0 && y + oy < h);
         const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
         const uint32_t a = __funnelshift_r(w0, w1, sh), b = __funnelshift_r(w1, w2, sh), c = w2 >> sh;
-        v[0] = a & 0xff; v[1] = (a >> 8) & 0xff; v[2] = (a >> 16) & 0xff; v[3] = a >> 24;
-        v[4] = b & 0xff; v[5] = (b >> 8) & 0xff; v[6] = (b >> 16) & 0xff; v[7] = b >> 24;
-        v[8] = c & 0xff;
+        const uint32_t F = 0x4B000000u;              // byte permutes below: (pixel byte, 0x00, 0x00, 0x4B)
+        v[0] = byte2float(a, F, 0x7440); v[1] = byte2float(a, F, 0x7441); v[2] = byte2float(a, F, 0x7442); v[3] = byte2float(a, F, 0x7443);
+        v[4] = byte2float(b, F, 0x7440); v[5] = byte2float(b, F, 0x7441); v[6] = byte2float(b, F, 0x7442); v[7] = byte2float(b, F, 0x7443);
+        v[8] = byte2float(c, F, 0x7440);
       }, P.harris_k);
     } else {
-      r = harris_at([&](int dy, int (&v)[9]) {
+      r = harris_at([&](int dy, float (&v)[9]) {
         const int oy = dy == -4 ? dyt : (dy == 4 ? dyb : dy);
         const uint8_t* q = ctr + oy * pitch;
         ORB_CHECK(y + oy >= 0 && y + oy < h && x + dxl >= 0 && x + dxr < w && x - 3 >= 0 && x + 3 < w);
-        v[0] = q[dxl];
+        v[0] = (float)q[dxl];
 #pragma unroll
-        for (int c = 1; c < 8; c++) v[c] = q[c - 4];
-        v[8] = q[dxr];
+        for (int c = 1; c < 8; c++) v[c] = (float)q[c - 4];
+        v[8] = (float)q[dxr];
       }, P.harris_k);
     }
     *slot = ((unsigned long long)(~f2ord(r)) << 32) | xy;
@@ -1387,10 +1397,10 @@ __global__ void k_harris_list(const uint8_t* __restrict__ img, int pitch, int w,
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int ky = kps[i].y, kx = kps[i].x;
-  out[i] = harris_at([&](int dy, int (&v)[9]) {
+  out[i] = harris_at([&](int dy, float (&v)[9]) {
     const uint8_t* q = img + (size_t)reflect101(ky + dy, h) * pitch;
 #pragma unroll
-    for (int c = 0; c < 9; c++) v[c] = q[reflect101(kx + c - 4, w)];
+    for (int c = 0; c < 9; c++) v[c] = (float)q[reflect101(kx + c - 4, w)];
   }, k);
 }
 
