@@ -402,7 +402,7 @@ constexpr int B_PH = B_TH + 8;         // rows y0-4 .. y0+B_TH+3
 constexpr int B_SCP = 136;             // score pitch (u16); pixel x sits at column x - x0 + 4
 constexpr int B_SH = B_TH + 2;         // rows y0-1 .. y0+B_TH
 #ifndef ORB_B_LIST
-#define ORB_B_LIST 2816
+#define ORB_B_LIST 2704
 #endif
 #ifndef ORB_B_MINB
 #define ORB_B_MINB 6
@@ -410,11 +410,14 @@ constexpr int B_SH = B_TH + 2;         // rows y0-1 .. y0+B_TH
 #ifndef ORB_PRETEST_SPLIT
 #define ORB_PRETEST_SPLIT 2
 #endif
+#ifndef ORB_B_PREFILTER
+#define ORB_B_PREFILTER 1
+#endif
 constexpr int B_LIST = ORB_B_LIST;     // pretest passers kept in the list; denser tiles take the dense fallback
 constexpr int B_SURV = 1024;
 constexpr int B_PIX_BYTES = B_PH * B_SP, B_SCORE_BYTES = B_SH * B_SCP * 2;
 constexpr int B_LIST_BYTES = B_LIST * 2;
-constexpr int B_SMEM = B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES + B_SURV * 2 + 16 + B_TW * 4 + 64 + 16;   // 37.7 KB and 40 registers -> 6 CTAs / SM
+constexpr int B_SMEM = B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES + B_SURV * 2 + 16 + B_TW * 4 + 64 + 56 * 4 + 16;   // 37.7 KB and 40 registers -> 6 CTAs / SM
 
 __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P, const Bufs B) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -422,10 +425,13 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
   uint16_t* s_score = (uint16_t*)(smem + B_PIX_BYTES);
   uint16_t* s_list = (uint16_t*)(smem + B_PIX_BYTES + B_SCORE_BYTES);
   uint16_t* s_surv = (uint16_t*)(smem + B_PIX_BYTES + B_SCORE_BYTES + B_LIST_BYTES);
-  int* s_ctr = (int*)(s_surv + B_SURV);   // [0] pretest list, [1] survivor list, [2] global base
-  int* s_ey = s_ctr + 4;                  // [B_TW] column-strip sums of this tile (phase 5/6)
-  uint16_t* s_tab = (uint16_t*)(s_ey + B_TW);   // [32] passer bit -> tile offset (phase 2)
-  uint64_t* s_bar = (uint64_t*)(s_tab + 32);    // mbarrier of the tile load
+  int* s_ey = (int*)(s_surv + B_SURV);    // [B_TW] column-strip sums of this tile (phase 5/6)
+  int* s_ctr = s_ey + B_TW;               // [0] pretest list, [1] survivor list, [2] global base, [3] item list
+  uint16_t* s_tab = (uint16_t*)(s_ctr + 4);     // [32] passer bit -> tile offset (phase 2, list variant)
+  uint32_t* s_vm = (uint32_t*)(s_tab + 32);     // [18][3] per column group: pair-lane validity mask, byte validity masks (phase 2)
+  uint64_t* s_bar = (uint64_t*)(s_vm + 54 + 2); // mbarrier of the tile load
+  uint16_t* s_items = s_surv;             // [<= 18 * 66] row items that survive the prefilter: lives in s_surv + the head of
+                                          // s_ey until phase 2 is over (s_ey is cleared after that)
 
   const int tid = threadIdx.x, lane = tid & 31, f = blockIdx.y;
   const uint32_t tt = __ldg(B.tile_b + blockIdx.x);
@@ -445,13 +451,154 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
     tma_load_3d(s_pix, B.tmaps + TM_PIX + l, s_bar, x0 - 16, y0 - 4, l == 0 ? f + B.frame0 : f);
   }
   for (int i = tid; i < B_SCORE_BYTES / 16; i += B_THREADS) ((uint4*)s_score)[i] = make_uint4(0, 0, 0, 0);
-  if (tid < 3) s_ctr[tid] = 0;
+  if (tid < 4) s_ctr[tid] = 0;
+#if !ORB_B_PREFILTER
   if (tid < B_TW) s_ey[tid] = 0;
+#endif
   // passer bit b of a thread's mask word: row item b >> 3 (rows 14 apart), pixel 0,2,4,6,1,3,5,7 for b & 7 = 0..7
   if (tid < 32) s_tab[tid] = (uint16_t)((tid >> 3) * (14 * B_SP) + ((tid & 3) << 1) + ((tid >> 2) & 1));
   __syncthreads();          // the mbarrier is initialised for everybody
   mbar_wait(s_bar, 0);
 
+#if ORB_B_PREFILTER
+  // ---- phase 2: compass pretest (ref src/orb_cpu.cpp:39-58), 8 pixels per row item, in two steps -----------------
+  // (a) prefilter, byte SIMD (4 pixels / instruction): a pixel can only have >= 3 of its 4 compass pixels brighter (or
+  //     darker) by thr if at least one of top / bottom AND at least one of left / right differs from it by >= thr.  With
+  //     d = |a - b| per byte (VABSDIFF4), (dT | dB) >= max(dT, dB), so "(dT | dB) >= thr and (dL | dR) >= thr" is a
+  //     necessary condition; the byte compare is one add whose carry lands in bit 7.  About two thirds of the row items of
+  //     a KITTI-like frame have no such pixel and are dropped here, at ~40 instructions per item.
+  // (b) the exact test on packed half2 (2 pixels / instruction) only for the surviving items, compacted into a list so
+  //     that every lane of a warp has an item.
+  const int thr = P.fast_threshold, fn = P.fast_n;
+  constexpr int NG = 18, NRT = 14, NK = (B_SH + NRT - 1) / NRT;
+  if (tid < NG) {   // per column group: which of its 8 pixels are valid centres
+    const int xs = x0 - 8 + 8 * tid;
+    // valid centres: 3 <= x < w-3 (ref src/orb_cpu.cpp:35), inside tile + 1 halo column on each side
+    const int lo = max(max(0, 3 - xs), x0 - 1 - xs), hi = min(min(8, w - 3 - xs), x0 + B_TW + 1 - xs);
+    uint32_t vmask = 0, vb0 = 0, vb1 = 0;
+    if (lo < hi) {
+      const uint32_t v8m = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {                        // pixel 2q -> bit 10+q, pixel 2q+1 -> bit 26+q (see below)
+        vmask |= (((v8m >> (2 * q)) & 1u) << (10 + q)) | (((v8m >> (2 * q + 1)) & 1u) << (26 + q));
+        vb0 |= ((v8m >> q) & 1u) << (8 * q + 7);
+        vb1 |= ((v8m >> (4 + q)) & 1u) << (8 * q + 7);
+      }
+    }
+    s_vm[3 * tid] = vmask; s_vm[3 * tid + 1] = vb0; s_vm[3 * tid + 2] = vb1;
+  }
+  __syncthreads();
+  {
+    const int g = tid % NG, rt = tid / NG;
+    const int pc = 8 + 8 * g;
+    const uint32_t vb0 = rt < NRT ? s_vm[3 * g + 1] : 0u, vb1 = rt < NRT ? s_vm[3 * g + 2] : 0u;
+    const uint32_t K7 = (uint32_t)(0x80 - min(thr, 128)) * 0x01010101u;
+    const bool wide = thr > 128;               // then bit 7 of d itself (d >= 128) is the (weaker, still necessary) test
+    uint32_t sb = 0;                           // bit k: row item k survives
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+      const int sy = rt + NRT * k, y = y0 - 1 + sy;
+      if ((vb0 | vb1) && sy < B_SH && y >= 3 && y < h - 3) {      // 3 <= y < h-3 (ref src/orb_cpu.cpp:34)
+        const uint8_t* rc = s_pix + (sy + 3) * B_SP + pc;
+        ORB_CHECK(rc - 3 * B_SP - 4 >= s_pix && rc + 3 * B_SP + 12 <= s_pix + B_PIX_BYTES);
+        const uint32_t m = *(const uint32_t*)(rc - 4), p = *(const uint32_t*)(rc + 8);
+        const uint2 cc = *(const uint2*)rc, tt = *(const uint2*)(rc - 3 * B_SP), bb = *(const uint2*)(rc + 3 * B_SP);
+        const uint32_t v0 = __vabsdiffu4(tt.x, cc.x) | __vabsdiffu4(bb.x, cc.x), v1 = __vabsdiffu4(tt.y, cc.y) | __vabsdiffu4(bb.y, cc.y);
+        const uint32_t h0 = __vabsdiffu4(prmt(m, cc.x, 0x4321), cc.x) | __vabsdiffu4(prmt(cc.x, cc.y, 0x6543), cc.x);
+        const uint32_t h1 = __vabsdiffu4(prmt(cc.x, cc.y, 0x4321), cc.y) | __vabsdiffu4(prmt(cc.y, p, 0x6543), cc.y);
+        uint32_t f0, f1;
+        if (!wide) {
+          f0 = (((v0 & 0x7f7f7f7fu) + K7) | v0) & (((h0 & 0x7f7f7f7fu) + K7) | h0);
+          f1 = (((v1 & 0x7f7f7f7fu) + K7) | v1) & (((h1 & 0x7f7f7f7fu) + K7) | h1);
+        } else {
+          f0 = v0 & h0; f1 = v1 & h1;
+        }
+        if ((f0 & vb0) | (f1 & vb1)) sb |= 1u << k;
+      }
+    }
+    // compact the surviving items of the warp into the item list (ballot ranks; one shared atomic per warp)
+    unsigned bal[NK];
+    int tot = 0;
+#pragma unroll
+    for (int k = 0; k < NK; k++) { bal[k] = __ballot_sync(0xffffffffu, (sb >> k) & 1u); tot += __popc(bal[k]); }
+    if (tot) {
+      int o = 0;
+      if (lane == 0) o = atomicAdd(&s_ctr[3], tot);
+      o = __shfl_sync(0xffffffffu, o, 0);
+      const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+      for (int k = 0; k < NK; k++) {
+        if ((sb >> k) & 1u) s_items[o + __popc(bal[k] & lt)] = (uint16_t)(((rt + NRT * k) << 5) | g);
+        o += __popc(bal[k]);
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const uint32_t K = 0x64646464u;   // half(1024 + p) = 0x6400 | p
+    // Two equivalent formulations share the work between the ALU pipe (HMNMX2 / HSET2) and the half-precision adder:
+    // (a) ">= 3 of 4 have v >= Ip + thr" <=> the second smallest of the four >= Ip + thr (min/max network);
+    // (b) the count of such pixels is a sum of saturated differences, sat(v - Ip - thr + 1) in {0, 1} (small integers,
+    //     exact in half precision), and ">= 3" is sat(count - 2): HADD2(.SAT) only.
+    // The first ORB_PRETEST_SPLIT pixel pairs of an item use (a), the rest (b).
+    // The darker side uses max(thr, 1) so that a pixel is never counted on both sides (ref src/orb_cpu.cpp:44-57).
+    const __half2 one_m_thr = __float2half2_rn((float)(1 - thr)), one_m_dthr = __float2half2_rn((float)(1 - max(thr, 1)));
+    const __half2 minus2 = __float2half2_rn(-2.0f);
+    const __half2 thr2 = __float2half2_rn((float)thr), dthr2 = __float2half2_rn((float)max(thr, 1));
+    const int n_items = s_ctr[3];
+    for (int it = tid; it < n_items; it += B_THREADS) {
+      const int code = s_items[it], sy = code >> 5, g = code & 31, pc = 8 + 8 * g;
+      const uint32_t vmask = s_vm[3 * g];
+      const uint8_t* rc = s_pix + (sy + 3) * B_SP + pc;
+      ORB_CHECK(sy < B_SH && g < NG && rc - 3 * B_SP - 4 >= s_pix && rc + 3 * B_SP + 12 <= s_pix + B_PIX_BYTES);
+      const uint32_t m = *(const uint32_t*)(rc - 4), p = *(const uint32_t*)(rc + 8);
+      const uint2 cc = *(const uint2*)rc, tt = *(const uint2*)(rc - 3 * B_SP), bb = *(const uint2*)(rc + 3 * B_SP);
+      const uint32_t C[4] = {prmt(cc.x, K, 0x4140), prmt(cc.x, K, 0x4342), prmt(cc.y, K, 0x4140), prmt(cc.y, K, 0x4342)};
+      const uint32_t T[4] = {prmt(tt.x, K, 0x4140), prmt(tt.x, K, 0x4342), prmt(tt.y, K, 0x4140), prmt(tt.y, K, 0x4342)};
+      const uint32_t Bm[4] = {prmt(bb.x, K, 0x4140), prmt(bb.x, K, 0x4342), prmt(bb.y, K, 0x4140), prmt(bb.y, K, 0x4342)};
+      // pixel pairs three to the left / right of each centre pair
+      const uint32_t p34 = prmt(prmt(cc.x, cc.y, 0x0043), K, 0x4140);
+      const uint32_t Lf[4] = {prmt(m, K, 0x4241), prmt(prmt(m, cc.x, 0x0043), K, 0x4140), prmt(cc.x, K, 0x4241), p34};
+      const uint32_t Rt[4] = {p34, prmt(cc.y, K, 0x4241), prmt(prmt(cc.y, p, 0x0043), K, 0x4140), prmt(p, K, 0x4241)};
+      uint32_t flags = 0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const __half2 v0 = as_h2(T[q]), v4 = as_h2(Rt[q]), v8 = as_h2(Bm[q]), v12 = as_h2(Lf[q]), c2 = as_h2(C[q]);
+        if (q < ORB_PRETEST_SPLIT) {   // min/max network (ALU pipe): 2nd smallest / 2nd largest of the four against Ip +- thr
+          const __half2 a = __hmin2(v0, v4), b = __hmax2(v0, v4), c = __hmin2(v8, v12), d = __hmax2(v8, v12);
+          const __half2 m1 = __hmax2(a, c), m2 = __hmin2(b, d);
+          const __half2 s2 = __hmin2(m1, m2), l2 = __hmax2(m1, m2);
+          const uint32_t fb = __hge2_mask(__hsub2(s2, c2), thr2);
+          const uint32_t fd = __hge2_mask(__hsub2(c2, l2), dthr2);
+          flags |= (fb | fd) & (0x04000400u << q);
+        } else {                       // saturated counts (half-precision adds)
+          const __half2 nhi = __hsub2(one_m_thr, c2), plo = __hadd2(c2, one_m_dthr);
+          const __half2 nb = __hadd2(__hadd2(__hadd2_sat(v0, nhi), __hadd2_sat(v4, nhi)),
+                                     __hadd2(__hadd2_sat(v8, nhi), __hadd2_sat(v12, nhi)));
+          const __half2 nd = __hadd2(__hadd2(__hadd2_sat(plo, __hneg2(v0)), __hadd2_sat(plo, __hneg2(v4))),
+                                     __hadd2(__hadd2_sat(plo, __hneg2(v8)), __hadd2_sat(plo, __hneg2(v12))));
+          const __half2 pass = __hadd2(__hadd2_sat(nb, minus2), __hadd2_sat(nd, minus2));   // 0 or 1.0 (0x3c00) per pixel
+          flags |= (*reinterpret_cast<const uint32_t*>(&pass)) & (0x04000400u << q);
+        }
+      }
+      flags &= vmask;
+      uint32_t m8 = ((flags >> 10) & 0xfu) | ((flags >> 22) & 0xf0u);   // bits 0-3: pixels 0,2,4,6; bits 4-7: pixels 1,3,5,7
+      if (m8) {
+        int off = atomicAdd(&s_ctr[0], __popc(m8));
+        const int e0 = sy * B_SP + pc;
+        do {
+          const int b = __ffs(m8) - 1;
+          m8 &= m8 - 1;
+          if (off < B_LIST) s_list[off] = (uint16_t)(e0 + ((b & 3) << 1) + (b >> 2));
+          off++;
+        } while (m8);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < B_TW) s_ey[tid] = 0;        // (the item list used this space; the strip sums start at phase 5)
+
+#else
   // ---- phase 2: compass pretest, 8 pixels per item -------------------------------------------
   // Thread (g, rt) owns column group g (8 pixels from x0 - 8 + 8g) on rows rt, rt+14, ...; the column validity mask
   // is loop invariant.  Passers of all its rows are appended with one warp scan + one shared atomic per warp.
@@ -556,6 +703,7 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
   }
   __syncthreads();
 
+#endif
   // ---- phase 3: ring test + SAD score for the passers, one pixel per thread --------------------
   // (a tile with more than B_LIST passers -- synthetic worst cases only -- is rescanned densely instead)
   const int n1 = s_ctr[0];
