@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liborb_b200.so")
 SOURCES = ["orb_api.cu", "orb_ingest.cu", "orb_lk.cu", "orb_png.cpp"]
-DEPS = ["orb_api.cu", "orb_ingest.cu", "orb_lk.cu", "orb_internal.h", "orb_png.cpp", "orb_png.h", "orb_kernels.cuh", "orb_ingest_kernels.cuh", "orb_lk_kernels.cuh", "orb_math.cuh", "orb_plan.h",
+DEPS = ["orb_api.cu", "orb_ingest.cu", "orb_lk.cu", "orb_internal.h", "orb_png.cpp", "orb_png.h", "orb_kernels.cuh", "orb_match_tc.cuh", "orb_ingest_kernels.cuh", "orb_lk_kernels.cuh", "orb_math.cuh", "orb_plan.h",
         os.path.join("..", "..", "include", "orb_b200.h"), os.path.join("..", "..", "include", "orb_brief_pattern.h")]
 
 NVCC_FLAGS = [

@@ -17,6 +17,7 @@
 #include "../../include/orb_brief_pattern.h"
 #include "orb_internal.h"
 #include "orb_kernels.cuh"
+#include "orb_match_tc.cuh"
 
 using orbk::Bufs;
 using orbk::DescribeJob;
@@ -180,7 +181,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 // 3-D map (x, y, frame) over `n` images of w x h elements; out-of-range elements read as zero
 int encode_map(orb_ctx* ctx, CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, int w, int h, int n,
-               size_t pitch_bytes, size_t frame_bytes, int box_w, int box_h) {
+               size_t pitch_bytes, size_t frame_bytes, int box_w, int box_h, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_NONE) {
   if ((uintptr_t)base % 16 || pitch_bytes % 16 || frame_bytes % 16 || (size_t)box_w * esize % 16 || box_w > 256 || box_h > 256)
     return fail(ctx, ORB_E_INVALID, "tensor map geometry not TMA-compatible (base %p pitch %zu stride %zu box %dx%d)", base, pitch_bytes,
                 frame_bytes, box_w, box_h);
@@ -189,7 +190,7 @@ int encode_map(orb_ctx* ctx, CUtensorMap* m, CUtensorMapDataType dt, int esize, 
   cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = ((EncodeTiledFn)ctx->tmap_encode)(m, dt, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                                swizzle, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(ctx, ORB_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return ORB_OK;
 }
@@ -380,6 +381,8 @@ void orb_destroy(orb_ctx* ctx) {
   if (ctx->d_lk) cudaFree(ctx->d_lk);
   if (ctx->d_scores) cudaFree(ctx->d_scores);
   for (void* q : ctx->d_scratch) if (q) cudaFree(q);
+  if (ctx->d_match_exp) cudaFree(ctx->d_match_exp);
+  if (ctx->d_match_maps) cudaFree(ctx->d_match_maps);
   if (ctx->h_comp) cudaFreeHost(ctx->h_comp);
   if (ctx->h_descs) cudaFreeHost(ctx->h_descs);
   if (ctx->h_inf_status) cudaFreeHost(ctx->h_inf_status);
@@ -529,6 +532,7 @@ int orb_create(const orb_params* p, orb_ctx** out) {
     }
     CK(cudaMemset(ctx->d_flags, 0, sizeof(int)));
     CK(cudaFuncSetAttribute(orbk::k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, orbk::B_SMEM));
+    CK(cudaFuncSetAttribute(orbk::k_match_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, orbk::MT_SMEM));
     CK(cudaFuncSetAttribute(orbk::k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (ORB_SORT_CAP + orbk::K2_SMEM_KEYS) * 8));
     return ORB_OK;
   };
@@ -962,13 +966,41 @@ static int scratch(orb_ctx* ctx, int slot, size_t bytes, void** out) {
 }
 
 // ---- descriptor matching -------------------------------------------------------------------------
-static int match_launch(orb_ctx* ctx, const orb_descriptor* dq, const orb_descriptor* dt, const int* dn, int nq, int nt, int npairs,
-                        long long sq, long long st, long long so, orb_match* dout) {
+// Tensor-core path (orb_match_tc.cuh): descriptors are expanded to +-1 int8 rows in a grow-only device buffer, two tensor
+// maps (query rows, train rows; 128-byte swizzle) are encoded for the call, one CTA per 128 queries of a pair.
+static int match_tc(orb_ctx* ctx, const orb_descriptor* dq, int rows_q, long long stride_q, const orb_descriptor* dt, int rows_t,
+                    long long stride_t, bool same_buffer, const int* dn, int nq, int nt, int npairs, long long out_stride, orb_match* dout) {
   if (npairs <= 0 || nq <= 0) return ORB_OK;
-  dim3 grid((nq + orbk::M_THREADS - 1) / orbk::M_THREADS, npairs);
-  orbk::k_match<<<grid, orbk::M_THREADS, 0, ctx->stream>>>(dq, dt, dn, nq, nt, sq, st, so, dout);
+  if (rows_t > orbk::MT_MAX_INDEX) return fail(ctx, ORB_E_CAPACITY, "matcher: at most %d train descriptors per set", orbk::MT_MAX_INDEX);
+  // expanded rows: [sets_q][rows_q][256] then (unless the train sets are the query sets shifted by one) [sets_t][rows_t][256]
+  const int sets_q = same_buffer ? npairs + 1 : npairs, sets_t = same_buffer ? 0 : npairs;
+  const size_t bytes_q = (size_t)sets_q * rows_q * orbk::MT_KB, bytes_t = (size_t)sets_t * std::max(rows_t, 1) * orbk::MT_KB;
+  if (bytes_q + bytes_t > ctx->match_exp_bytes) {
+    if (ctx->d_match_exp) CK(cudaFree(ctx->d_match_exp));
+    ctx->d_match_exp = nullptr; ctx->match_exp_bytes = 0;
+    CK(cudaMalloc(&ctx->d_match_exp, bytes_q + bytes_t + 1024));
+    ctx->match_exp_bytes = bytes_q + bytes_t;
+  }
+  if (!ctx->d_match_maps) CK(cudaMalloc(&ctx->d_match_maps, 2 * sizeof(CUtensorMap)));
+  int8_t* eq = ctx->d_match_exp;
+  int8_t* et = same_buffer ? eq + (size_t)rows_q * orbk::MT_KB : eq + bytes_q;
+  orbk::k_match_expand<<<dim3((rows_q * 16 + 255) / 256, sets_q), 256, 0, ctx->stream>>>(dq, same_buffer ? dn : nullptr, rows_q, stride_q, rows_q, eq);
+  if (!same_buffer && rows_t > 0)
+    orbk::k_match_expand<<<dim3((rows_t * 16 + 255) / 256, sets_t), 256, 0, ctx->stream>>>(dt, nullptr, rows_t, stride_t, rows_t, et);
   CK(cudaGetLastError());
-  ctx->launches += 1;
+  CUtensorMap maps[2];
+  int rc;
+  if ((rc = encode_map(ctx, &maps[0], CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, eq, orbk::MT_KB, rows_q, npairs, orbk::MT_KB, (size_t)rows_q * orbk::MT_KB,
+                       128, 128, CU_TENSOR_MAP_SWIZZLE_128B)))
+    return rc;
+  if ((rc = encode_map(ctx, &maps[1], CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, et, orbk::MT_KB, std::max(rows_t, 1), npairs, orbk::MT_KB,
+                       (size_t)std::max(same_buffer ? rows_q : rows_t, 1) * orbk::MT_KB, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B)))
+    return rc;
+  CK(cudaMemcpyAsync(ctx->d_match_maps, maps, sizeof(maps), cudaMemcpyHostToDevice, ctx->stream));
+  dim3 grid((nq + orbk::MT_M - 1) / orbk::MT_M, npairs);
+  orbk::k_match_tc<<<grid, orbk::MT_THREADS, orbk::MT_SMEM, ctx->stream>>>(ctx->d_match_maps, dn, nq, nt, out_stride, dout);
+  CK(cudaGetLastError());
+  ctx->launches += same_buffer ? 2 : 3;
   return ORB_OK;
 }
 
@@ -978,7 +1010,7 @@ int orb_match_knn2(orb_ctx* ctx, const orb_descriptor* query, int nq, const orb_
   if (nq < 0 || nt < 0 || (nq > 0 && (!query || !out)) || (nt > 0 && !train)) return fail(ctx, ORB_E_INVALID, "bad match arguments");
   if (nq == 0) return ORB_OK;
   CK(cudaSetDevice(ctx->p.device));
-  if (on_device) return match_launch(ctx, query, train, nullptr, nq, nt, 1, 0, 0, 0, out);
+  if (on_device) return match_tc(ctx, query, nq, 0, train, nt, 0, false, nullptr, nq, nt, 1, 0, out);
   orb_descriptor *dq = nullptr, *dt = nullptr; orb_match* dm = nullptr;
   int rc;
   if ((rc = scratch(ctx, 0, sizeof(orb_descriptor) * (size_t)nq, (void**)&dq))) return rc;
@@ -986,7 +1018,7 @@ int orb_match_knn2(orb_ctx* ctx, const orb_descriptor* query, int nq, const orb_
   if ((rc = scratch(ctx, 2, sizeof(orb_match) * (size_t)nq, (void**)&dm))) return rc;
   CK(cudaMemcpyAsync(dq, query, sizeof(orb_descriptor) * (size_t)nq, cudaMemcpyHostToDevice, ctx->stream));
   if (nt) CK(cudaMemcpyAsync(dt, train, sizeof(orb_descriptor) * (size_t)nt, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = match_launch(ctx, dq, dt, nullptr, nq, nt, 1, 0, 0, 0, dm))) return rc;
+  if ((rc = match_tc(ctx, dq, nq, 0, dt, nt, 0, false, nullptr, nq, nt, 1, 0, dm))) return rc;
   CK(cudaMemcpyAsync(out, dm, sizeof(orb_match) * (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return ORB_OK;
@@ -999,7 +1031,7 @@ int orb_match_knn2_batch(orb_ctx* ctx, const orb_descriptor* desc, const int* n,
   if (n_frames < 2) return ORB_OK;
   CK(cudaSetDevice(ctx->p.device));
   const long long s = cap;
-  if (on_device) return match_launch(ctx, desc, desc + cap, n, cap, cap, n_frames - 1, s, s, s, out);
+  if (on_device) return match_tc(ctx, desc, cap, s, desc + cap, cap, s, true, n, cap, cap, n_frames - 1, s, out);
   orb_descriptor* dd = nullptr; int* dn = nullptr; orb_match* dm = nullptr;
   const size_t nd = (size_t)n_frames * cap, nm = (size_t)(n_frames - 1) * cap;
   int rc;
@@ -1009,7 +1041,7 @@ int orb_match_knn2_batch(orb_ctx* ctx, const orb_descriptor* desc, const int* n,
   CK(cudaMemcpyAsync(dd, desc, sizeof(orb_descriptor) * nd, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(dn, n, sizeof(int) * n_frames, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(dm, out, sizeof(orb_match) * nm, cudaMemcpyHostToDevice, ctx->stream));   // entries >= n[p] stay as they were
-  if ((rc = match_launch(ctx, dd, dd + cap, dn, cap, cap, n_frames - 1, s, s, s, dm))) return rc;
+  if ((rc = match_tc(ctx, dd, cap, s, dd + cap, cap, s, true, dn, cap, cap, n_frames - 1, s, dm))) return rc;
   CK(cudaMemcpyAsync(out, dm, sizeof(orb_match) * nm, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return ORB_OK;
