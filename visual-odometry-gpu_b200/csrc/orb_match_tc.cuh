@@ -25,8 +25,9 @@ constexpr int MT_M = 128, MT_N = 256, MT_KB = 256;          // queries per CTA, 
 constexpr int MT_STAGES = 2;
 constexpr int MT_SLAB_A = MT_M * 128, MT_SLAB_B = MT_N * 128;   // one 128-byte K slab of a tile (SWIZZLE_128B atom rows)
 constexpr int MT_A_BYTES = 2 * MT_SLAB_A, MT_B_BYTES = 2 * MT_SLAB_B;
-constexpr int MT_SMEM = MT_A_BYTES + MT_STAGES * MT_B_BYTES + 256 + 1024;   // + barriers + slack for the 1024-byte alignment
-constexpr int MT_THREADS = 192;                              // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-5: epilogue
+constexpr int MT_SMEM = MT_A_BYTES + MT_STAGES * MT_B_BYTES + 128 + 1024 + 1024;   // + barriers + merge area + slack for the 1024-byte alignment
+constexpr int MT_EPI_WARPS = 8;                              // two warps per TMEM lane quarter, 128 columns of a tile each
+constexpr int MT_THREADS = 64 + 32 * MT_EPI_WARPS;            // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-9: epilogue
 constexpr int MT_MAX_INDEX = 1 << 14;                        // train indices must fit the key's low 14 bits
 
 // ---- descriptors -> +-1 int8 rows -----------------------------------------------------------------------------------
@@ -90,8 +91,15 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, int (&v)[32]) {
         "=r"(v[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// 32 lanes x 64 consecutive 32-bit columns -> 64 registers per thread
+__device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, int (&v)[64]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // grid (ceil(max queries / 128), pairs).  maps[0]: query rows, maps[1]: train rows (3-D: 256 bytes, rows, pairs; box 128 x 128).
 // n_arr != nullptr: pair p matches the n_arr[p] descriptors of frame p against the n_arr[p + 1] of frame p + 1.
@@ -112,7 +120,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* _
   const int ntiles = (nt + MT_N - 1) / MT_N;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+    for (int i = 0; i < 2; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(tfull + i, 1); mbar_init(tempty + i, MT_EPI_WARPS); }
     mbar_init(afull, 1);
     mbar_fence_init();
   }
@@ -159,44 +167,63 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* _
         umma_commit(tfull + st);                          // accumulator ready
       }
     }
-  } else {                                                // ===== epilogue: warps 2..5 own TMEM lanes 32 * (warp % 4) .. + 31 =====
-    const int quarter = warp & 3, row = m0 + quarter * 32 + lane;
+  } else {
+    // ===== epilogue: warp w owns TMEM lanes 32 * (w % 4) .. + 31 (its query rows) and columns 128 * half .. + 127 of every
+    // tile; chunks of 32 columns, the next chunk's tcgen05.ld in flight while the current one is folded into the keys =====
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
     int k1 = 0x7fffffff, k2 = 0x7fffffff;                 // two smallest keys: distance << 14 | train index
+    auto fold = [&](const int (&v)[64], int kb, int nvalid) {   // key = (256 - dot) / 2 * 2^14 + j = (256 - dot) * 2^13 + j
+      if (nvalid >= 64) {
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+          const int key = kb + i - v[i] * 8192;
+          k2 = min(k2, max(k1, key));
+          k1 = min(k1, key);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+          const int key = i < nvalid ? kb + i - v[i] * 8192 : 0x7fffffff;
+          k2 = min(k2, max(k1, key));
+          k1 = min(k1, key);
+        }
+      }
+    };
     for (int t = 0; t < ntiles; t++) {
       const int st = t & 1;
       mbar_wait(tfull + st, (t >> 1) & 1);
       tc_fence_after();
-      const int jn = min(MT_N, nt - t * MT_N);            // valid train columns of this tile
-#pragma unroll 1
-      for (int c = 0; c < MT_N / 32 && c * 32 < jn; c++) {
-        int v[32];
-        tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + st * MT_N + c * 32, v);
-        const int kb = (256 << 13) + t * MT_N + c * 32;   // key = (256 - dot) / 2 * 2^14 + j = (256 - dot) * 2^13 + j
-        if ((c + 1) * 32 <= jn) {
-#pragma unroll
-          for (int i = 0; i < 32; i++) {
-            const int key = kb + i - v[i] * 8192;
-            k2 = min(k2, max(k1, key));
-            k1 = min(k1, key);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i++) {
-            const int key = c * 32 + i < jn ? kb + i - v[i] * 8192 : 0x7fffffff;
-            k2 = min(k2, max(k1, key));
-            k1 = min(k1, key);
-          }
+      const int c0 = half * 128;                          // first column of this warp inside the tile
+      const int jn = min(MT_N, nt - t * MT_N) - c0;       // valid train columns from c0 on (<= 0: nothing for this warp)
+      const uint32_t ta = tmem + ((uint32_t)(quarter * 32) << 16) + st * MT_N + c0;
+      const int kb = (256 << 13) + t * MT_N + c0;
+      int va[64], vb[64];
+      if (jn > 0) {
+        tmem_ld_32x64(ta, va);
+        tmem_ld_wait();
+        if (jn > 64) tmem_ld_32x64(ta + 64, vb);          // in flight while the first 64 columns are folded
+        fold(va, kb, jn);
+        if (jn > 64) {
+          tmem_ld_wait();
+          fold(vb, kb + 64, jn - 64);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + st);
     }
-    if (row < nq) {
+    // the two column halves of a row meet in shared memory
+    int* s_merge = (int*)(bars + 16);
+    const int r = quarter * 32 + lane;
+    if (half == 1) { s_merge[2 * r] = k1; s_merge[2 * r + 1] = k2; }
+    asm volatile("bar.sync 1, %0;" ::"r"(32 * MT_EPI_WARPS) : "memory");
+    if (half == 0 && m0 + r < nq) {
+      const int b1 = s_merge[2 * r], b2 = s_merge[2 * r + 1];
+      const int m1 = min(k1, b1), m2 = min(max(k1, b1), min(k2, b2));
       orb_match m;
-      m.idx1 = k1 == 0x7fffffff ? -1 : (k1 & (MT_MAX_INDEX - 1)); m.dist1 = k1 == 0x7fffffff ? 0x7fffffff : (k1 >> 14);
-      m.idx2 = k2 == 0x7fffffff ? -1 : (k2 & (MT_MAX_INDEX - 1)); m.dist2 = k2 == 0x7fffffff ? 0x7fffffff : (k2 >> 14);
-      out[(size_t)p * out_stride + row] = m;
+      m.idx1 = m1 == 0x7fffffff ? -1 : (m1 & (MT_MAX_INDEX - 1)); m.dist1 = m1 == 0x7fffffff ? 0x7fffffff : (m1 >> 14);
+      m.idx2 = m2 == 0x7fffffff ? -1 : (m2 & (MT_MAX_INDEX - 1)); m.dist2 = m2 == 0x7fffffff ? 0x7fffffff : (m2 >> 14);
+      out[(size_t)p * out_stride + m0 + r] = m;
     }
   }
   tc_fence_before();
