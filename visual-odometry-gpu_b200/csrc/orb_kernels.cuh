@@ -13,7 +13,8 @@
 //   k_describe : CTA per 32 kept keypoints (warp per keypoint; lane per keypoint for the libm part):
 //                intensity-centroid orientation (ref d_Orientations, src/cuda/Orientations.cu:22-63 == src/orb_cpu.cpp:139-183) and rotated BRIEF with ballot-packed words
 //                (ref d_Brief, src/cuda/Brief.cu:40-95 == src/orb_cpu.cpp:203-258).
-// plus k_match (exact Hamming 2-NN, the step after the descriptors: ref flann->knnMatch, src/feature_matching.cpp:168)
+// plus k_edges (border-box value tables for BRIEF), k_nms_scores (NMS over a caller's score map); the descriptor matcher
+// lives in orb_match_tc.cuh (tensor cores)
 // and two helpers for the single-image stage entry points (k_harris_list, k_eval_math).
 #pragma once
 #include <cuda.h>
@@ -1550,65 +1551,6 @@ __global__ void k_harris_list(const uint8_t* __restrict__ img, int pitch, int w,
 #pragma unroll
     for (int c = 0; c < 9; c++) v[c] = (float)q[reflect101(kx + c - 4, w)];
   }, k);
-}
-
-// =============================================================================================
-// Kernel M: exact brute-force Hamming 2-NN (replaces flann->knnMatch(des1, des2, matches, 2), reference
-// src/feature_matching.cpp:168 / src/feature_tracking.cpp:205).  One thread per query descriptor (8 registers), train
-// descriptors staged 64 at a time in shared memory and broadcast; the eight XOR words go through a carry-save adder
-// tree so that four POPCs replace eight (POPC is the slow pipe).  Ties go to the lower train index (ascending scan,
-// strict comparisons).
-constexpr int M_THREADS = 128, M_TILE = 64;
-
-__device__ __forceinline__ void csa(uint32_t& hi, uint32_t& lo, uint32_t a, uint32_t b, uint32_t c) {
-  const uint32_t u = a ^ b;
-  hi = (a & b) | (u & c);
-  lo = u ^ c;
-}
-
-__global__ void __launch_bounds__(M_THREADS) k_match(const orb_descriptor* __restrict__ desc_q, const orb_descriptor* __restrict__ desc_t,
-                                                     const int* __restrict__ n_arr, int nq_fixed, int nt_fixed,
-                                                     long long pair_stride_q, long long pair_stride_t, long long out_stride,
-                                                     orb_match* __restrict__ out) {
-  __shared__ __align__(16) uint32_t s_t[M_TILE * 8];
-  const int p = blockIdx.y;
-  const int nq = n_arr ? n_arr[p] : nq_fixed, nt = n_arr ? n_arr[p + 1] : nt_fixed;
-  const uint4* q4 = (const uint4*)(desc_q + (size_t)p * pair_stride_q);
-  const uint4* t4 = (const uint4*)(desc_t + (size_t)p * pair_stride_t);
-  const int qi = blockIdx.x * M_THREADS + threadIdx.x;
-  if (blockIdx.x * M_THREADS >= nq) return;
-  uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
-  if (qi < nq) { qa = q4[2 * (size_t)qi]; qb = q4[2 * (size_t)qi + 1]; }
-  int d1 = 0x7fffffff, d2 = 0x7fffffff, i1 = -1, i2 = -1;
-  for (int j0 = 0; j0 < nt; j0 += M_TILE) {
-    const int nj = min(M_TILE, nt - j0);
-    __syncthreads();
-    for (int k = threadIdx.x; k < nj * 2; k += M_THREADS) ((uint4*)s_t)[k] = t4[2 * (size_t)j0 + k];
-    __syncthreads();
-#pragma unroll 2
-    for (int j = 0; j < nj; j++) {
-      const uint4 ta = ((const uint4*)s_t)[2 * j], tb = ((const uint4*)s_t)[2 * j + 1];
-      const uint32_t x0 = qa.x ^ ta.x, x1 = qa.y ^ ta.y, x2 = qa.z ^ ta.z, x3 = qa.w ^ ta.w;
-      const uint32_t x4 = qb.x ^ tb.x, x5 = qb.y ^ tb.y, x6 = qb.z ^ tb.z, x7 = qb.w ^ tb.w;
-      // Harley-Seal: eight words -> ones, twos (x2), fours (x1)
-      uint32_t twoA, onesA, twoB, onesB, twoC, ones, four, two;
-      csa(twoA, onesA, x0, x1, x2);
-      csa(twoB, onesB, x3, x4, x5);
-      csa(twoC, ones, onesA, onesB, x6);
-      const uint32_t ones2 = ones ^ x7, twoD = ones & x7;
-      csa(four, two, twoA, twoB, twoC);
-      const uint32_t two2 = two ^ twoD, four2 = two & twoD;
-      const int d = __popc(ones2) + 2 * __popc(two2) + 4 * (__popc(four) + __popc(four2));
-      const int jj = j0 + j;
-      if (d < d1) { d2 = d1; i2 = i1; d1 = d; i1 = jj; }
-      else if (d < d2) { d2 = d; i2 = jj; }
-    }
-  }
-  if (qi < nq) {
-    orb_match m;
-    m.idx1 = i1; m.dist1 = d1; m.idx2 = i2; m.dist2 = d2;
-    out[(size_t)p * out_stride + qi] = m;
-  }
 }
 
 // NMS over a caller's float score map (stage entry point orb_nms_scores; ref d_NMS, src/cuda/NMS.cu:21-128): a pixel at

@@ -1,7 +1,7 @@
 // orb_match_tc.cuh -- exact Hamming 2-NN on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), sm_100a.
 //
 // Replaces flann->knnMatch(des1, des2, matches, 2) of the reference's VO loops (src/feature_matching.cpp:168,174-182;
-// src/feature_tracking.cpp:205-219) like k_match does, but as a contraction: with descriptor bits mapped to +-1,
+// src/feature_tracking.cpp:205-219) by an exact brute-force search, written as a contraction: with descriptor bits mapped to +-1,
 //     <a, b> = 256 - 2 * hamming(a, b),   i.e.   hamming = (256 - <a, b>) / 2,
 // and an INT8 x INT8 -> INT32 product of +-1 vectors of length 256 is exact (|sum| <= 256).  One CTA owns 128 query
 // descriptors of a frame pair and walks over the train descriptors in tiles of 256:
@@ -10,7 +10,7 @@
 //                    warp 1 (one lane) issues tcgen05.mma.kind::i8 (M 128 x N 256 x K 32, eight per tile) into one of two
 //                    TMEM accumulators (2 x 256 columns), warps 2-5 read the finished accumulator with tcgen05.ld and keep
 //                    the two smallest (distance, index) keys per query row while the next tile is being multiplied.
-// Ties go to the lower train index (key = distance * 2^14 + index), exactly as k_match / the CPU oracle.
+// Ties go to the lower train index (key = distance * 2^14 + index), exactly as the CPU oracle (orc_match_knn2).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
