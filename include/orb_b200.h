@@ -132,6 +132,16 @@ int  orb_fast_detect(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitc
  * raster order are returned (deterministic). */
 int  orb_nms_scores(orb_ctx* ctx, const float* scores, int w, int h, size_t pitch_bytes, int nms_window, int nfeatures,
                     float threshold, orb_keypoint* kps, int* n_out);
+/* replaces: conv2d() (reference include/Convolution.cuh:5, src/cuda/Convolution.cu:57-103) and, with it, what GaussianBlurCUDA
+ * (src/GaussianBlur.cpp:39-49), SobelCUDA (src/Sobel.cpp:18-31) and GaussianBlur (src/cuda/GaussianBlur.cu:73-130) do around
+ * it: K x K correlation of the u8 image promoted to float (one FMA per tap, row by row), optionally after extending the image
+ * by K/2 with BORDER_REFLECT_101 (output then has the input's size, else valid mode: (w-K+1) x (h-K+1)), optionally divided by
+ * `divisor` (0 = no division), converted like cv::Mat::convertTo(CV_8U).  `kernel` is a host array of ksize*ksize floats. */
+int  orb_conv2d_u8(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch, const float* kernel, int ksize,
+                   int border_reflect101, float divisor, uint8_t* out, size_t out_pitch);
+/* replaces: GaussianBlur1D() (reference include/GaussianBlur.cuh:4, src/cuda/GaussianBlur1D.cu:108-166): separable [1 4 6 4 1]/16,
+ * BORDER_REFLECT_101, float, convertTo(CV_8U) */
+int  orb_gaussian_blur_1d(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch, uint8_t* out, size_t out_pitch);
 /* replaces: HarrisScore() (reference include/HarrisScore.cuh:5, src/cuda/HarrisScore.cu:42-89) */
 int  orb_harris(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch,
                 const orb_keypoint* kps, int n, float* response);

@@ -4,6 +4,10 @@
 //   void Brief(image, keypoints, orientations, descriptors, n_bits, patch_size)      reference include/Brief.cuh:5
 //   void HarrisScore(image, keypoints, harris_scores, corner_window, k)              reference include/HarrisScore.cuh:5
 //   void NMS(score_map, keypoints, nms_window, nfeatures, threshold)                 reference include/NMS.cuh:5
+//   int  conv2d(image, dst, kernel, kernel_size)                                     reference include/Convolution.cuh:5
+//   void GaussianBlur(image, dst), GaussianBlur1D(image, dst)                        reference include/GaussianBlur.cuh:3-4
+//   void GaussianBlurCUDA(image, dst, kernel_size)                                   reference include/GaussianBlur.hpp:6
+//   void SobelCUDA(image, dst, dir)                                                  reference include/Sobel.hpp:6
 // Same names and argument lists, so a translation unit that includes the reference's Fast.cuh / Brief.cuh / HarrisScore.cuh
 // (src/orb.cpp:24,31,42,65) includes this header instead.  Each call forwards to one C-ABI stage entry point
 // (orb_fast_detect / orb_orientations / orb_brief / orb_harris); contexts are per thread and per parameter set and grow
@@ -16,11 +20,13 @@
 // floating-point overload WINS overload resolution (exact match for the double literal), so k = 0.04 as the call site means;
 // the reference's own declaration would truncate it to 0 -- recorded deviation, DESIGN.md D5.  NMS() returns the first
 // `nfeatures` survivors in raster order, like Fast().
-// conv2d(), GaussianBlur*(), SobelCUDA() are internal steps of HarrisScore in this implementation and have no stand-alone
-// entry point.
+// conv2d(), GaussianBlur*(), SobelCUDA() keep the reference's arithmetic (u8 promoted to float, one FMA per tap row by row,
+// cv::Mat::convertTo(CV_8U) at the end, BORDER_REFLECT_101 where the reference pads); the Harris response itself does not go
+// through them (k_harris evaluates Sobel and the 7x7 window at the candidates only).
 #ifndef ORB_STAGES_HPP
 #define ORB_STAGES_HPP
 
+#include <cmath>
 #include <map>
 #include <memory>
 #include <tuple>
@@ -99,6 +105,64 @@ inline void orb_b200_detail::harris_score(const cv::Mat& image, std::vector<Keyp
                        reinterpret_cast<const orb_keypoint*>(keypoints.data()), (int)keypoints.size(), harris_scores.data()));
 }
 
+
+// ---- the reference's stand-alone filters ---------------------------------------------------------------------------------
+namespace orb_b200_detail {
+inline void filter_u8(const cv::Mat& image, cv::Mat& dst, const float* kernel, int ksize, bool reflect, float divisor) {
+    check_image(image);
+    const int ow = reflect ? image.cols : image.cols - ksize + 1, oh = reflect ? image.rows : image.rows - ksize + 1;
+    if (ow < 1 || oh < 1) throw std::runtime_error("orb_b200: image smaller than the kernel");
+    Handle& h = stage_handle(20, 9, 3, 31);
+    cv::Mat out;
+    out.create(oh, ow, CV_8UC1);                        // (dst may alias image)
+    h.check(orb_conv2d_u8(h.get(image.cols, image.rows), image.data, image.cols, image.rows, image.step, kernel, ksize, reflect ? 1 : 0,
+                          divisor, out.data, out.step));
+    dst = out;
+}
+}  // namespace orb_b200_detail
+
+// valid-mode K x K correlation of a (pre-padded) image -> CV_8U (reference src/cuda/Convolution.cu:57-103; its header declares
+// `int`, its definition `void`: 0 is returned)
+inline int conv2d(const cv::Mat& image, cv::Mat& dst, float* kernel, int kernel_size) {
+    orb_b200_detail::filter_u8(image, dst, kernel, kernel_size, false, 0.0f);
+    return 0;
+}
+// 5x5 Gaussian {1 4 7 4 1; 4 16 26 16 4; 7 26 41 26 7; ...} / 273, BORDER_REFLECT_101 (reference src/cuda/GaussianBlur.cu:21-130)
+inline void GaussianBlur(const cv::Mat& image, cv::Mat& dst) {
+    static const float k[25] = {1, 4, 7, 4, 1, 4, 16, 26, 16, 4, 7, 26, 41, 26, 7, 4, 16, 26, 16, 4, 1, 4, 7, 4, 1};
+    orb_b200_detail::filter_u8(image, dst, k, 5, true, 273.0f);
+}
+// separable [1 4 6 4 1] / 16, BORDER_REFLECT_101 (reference src/cuda/GaussianBlur1D.cu:108-166)
+inline void GaussianBlur1D(const cv::Mat& image, cv::Mat& dst) {
+    orb_b200_detail::check_image(image);
+    orb_b200_detail::Handle& h = orb_b200_detail::stage_handle(20, 9, 3, 31);
+    cv::Mat out;
+    out.create(image.rows, image.cols, CV_8UC1);
+    h.check(orb_gaussian_blur_1d(h.get(image.cols, image.rows), image.data, image.cols, image.rows, image.step, out.data, out.step));
+    dst = out;
+}
+// createGaussianKernel(kernel_size) + BORDER_REFLECT_101 + conv2d (reference src/GaussianBlur.cpp:7-49)
+inline void GaussianBlurCUDA(const cv::Mat& image, cv::Mat& dst, int kernel_size) {
+    if (kernel_size < 1 || kernel_size % 2 == 0) throw std::runtime_error("orb_b200: kernel size must be odd");
+    std::vector<float> kernel((size_t)kernel_size * kernel_size);
+    const float sigma = 0.3f * ((kernel_size - 1) * 0.5f) + 0.8f;       // the reference's heuristic (src/GaussianBlur.cpp:15-16)
+    const int half = kernel_size / 2;
+    float sum = 0.0f;
+    for (int y = -half; y <= half; ++y)
+        for (int x = -half; x <= half; ++x) {
+            const float value = std::exp(-(x * x + y * y) / (2 * sigma * sigma));
+            kernel[(size_t)(y + half) * kernel_size + (x + half)] = value;
+            sum += value;
+        }
+    for (float& v : kernel) v /= sum;
+    orb_b200_detail::filter_u8(image, dst, kernel.data(), kernel_size, true, 0.0f);
+}
+// 3x3 Sobel, dir 0 = x, else y, BORDER_REFLECT_101, result CV_8U (negative responses saturate to 0, as in the reference:
+// src/Sobel.cpp:6-31 -> conv2d's convertTo(CV_8U))
+inline void SobelCUDA(const cv::Mat& image, cv::Mat& dst, int dir) {
+    static const float sx[9] = {-1.f, 0.f, 1.f, -2.f, 0.f, 2.f, -1.f, 0.f, 1.f}, sy[9] = {-1.f, -2.f, -1.f, 0.f, 0.f, 0.f, 1.f, 2.f, 1.f};
+    orb_b200_detail::filter_u8(image, dst, dir == 0 ? sx : sy, 3, true, 0.0f);
+}
 
 // NMS over a caller's CV_32F score map (reference include/NMS.cuh:5; src/cuda/NMS.cu:130-164)
 inline void NMS(const cv::Mat& input, std::vector<Keypoint>& keypoints, int nms_window, int nfeatures, float threshold) {

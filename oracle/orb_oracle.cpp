@@ -258,6 +258,68 @@ void orc_harris(const uint8_t* data, int w, int h, size_t pitch, const orc_keypo
   }
 }
 
+// ---- the reference's filter wrappers ----------------------------------------------------------------------------
+// createGaussianKernel(k), src/GaussianBlur.cpp:7-37 (float arithmetic, sigma heuristic)
+void orc_gaussian_kernel(int kernelSize, float* kernel) {
+  float sigma = 0.3f * ((kernelSize - 1) * 0.5f) + 0.8f;
+  int halfSize = kernelSize / 2;
+  float sum = 0.0f;
+  for (int y = -halfSize; y <= halfSize; ++y)
+    for (int x = -halfSize; x <= halfSize; ++x) {
+      float value = std::exp(-(x * x + y * y) / (2 * sigma * sigma));
+      kernel[(y + halfSize) * kernelSize + (x + halfSize)] = value;
+      sum += value;
+    }
+  for (int i = 0; i < kernelSize * kernelSize; ++i) kernel[i] /= sum;
+}
+
+// cv::Mat::convertTo(CV_8U) of a float: saturate_cast<uchar>(cvRound(v)), round half to even
+static inline uint8_t to_u8(float v) {
+  long r = std::lrint(v);
+  return (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+}
+
+// conv2d (src/cuda/Convolution.cu:20-103): valid-mode K x K correlation of the u8 image promoted to float, accumulated row
+// by row as `sum += tile * kernel` -- an FMA in the reference's default nvcc build --, result convertTo(CV_8U).
+// reflect != 0: the image is first extended by K/2 with BORDER_REFLECT_101 (GaussianBlurCUDA src/GaussianBlur.cpp:39-49,
+// SobelCUDA src/Sobel.cpp:18-31, GaussianBlur src/cuda/GaussianBlur.cu:73-77), so the output has the input's size.
+// divisor != 0: the sum is divided by it before the conversion (d_GaussianBlur: sum / 273.0f, src/cuda/GaussianBlur.cu:67).
+void orc_conv2d_u8(const uint8_t* data, int w, int h, size_t pitch, const float* kernel, int K, int reflect, float divisor, uint8_t* out) {
+  Img im{data, w, h, pitch};
+  const int r = K / 2, ow = reflect ? w : w - K + 1, oh = reflect ? h : h - K + 1;
+  for (int y = 0; y < oh; y++)
+    for (int x = 0; x < ow; x++) {
+      float sum = 0;
+      for (int i = 0; i < K; i++)
+        for (int j = 0; j < K; j++) {
+          int yy = reflect ? reflect101(y + i - r, h) : y + i, xx = reflect ? reflect101(x + j - r, w) : x + j;
+          sum = std::fmaf((float)im.at(yy, xx), kernel[i * K + j], sum);
+        }
+      if (divisor != 0.0f) sum = sum / divisor;
+      out[(size_t)y * ow + x] = to_u8(sum);
+    }
+}
+
+// GaussianBlur1D (src/cuda/GaussianBlur1D.cu:34-166): [1 4 6 4 1] / 16 along x, then along y, float, reflect-101 (the
+// intent of its halo code), convertTo(CV_8U)
+void orc_gaussian_blur_1d(const uint8_t* data, int w, int h, size_t pitch, uint8_t* out) {
+  Img im{data, w, h, pitch};
+  const float k[5] = {1, 4, 6, 4, 1};
+  std::vector<float> tmp((size_t)w * h);
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      float sum = 0.0f;
+      for (int t = 0; t < 5; t++) sum += k[t] * (float)im.at(y, reflect101(x - 2 + t, w));
+      tmp[(size_t)y * w + x] = sum / 16.0f;
+    }
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      float sum = 0.0f;
+      for (int t = 0; t < 5; t++) sum += k[t] * tmp[(size_t)reflect101(y - 2 + t, h) * w + x];
+      out[(size_t)y * w + x] = to_u8(sum / 16.0f);
+    }
+}
+
 // ---- orientation: src/orb_cpu.cpp:139-183 --------------------------------------------------
 void orc_orientations(const uint8_t* data, int w, int h, size_t pitch, const orc_keypoint* kps, int n, int patch, float* out) {
   Img im{data, w, h, pitch};

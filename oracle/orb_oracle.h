@@ -55,6 +55,10 @@ void orc_build_level(const uint8_t* img, int W, int H, size_t pitch, const orc_p
 void orc_fast_scores(const uint8_t* img, int w, int h, size_t pitch, int thr, int n, float* scores /* w*h */);
 int  orc_nms(const float* scores, int w, int h, int nms_window, int cap, orc_keypoint* kps);
 void orc_harris_weights(float* w49);  /* createGaussianKernel(7): reference src/GaussianBlur.cpp:7-37 */
+/* the reference's filter wrappers (src/cuda/Convolution.cu, src/cuda/GaussianBlur.cu, src/cuda/GaussianBlur1D.cu, src/GaussianBlur.cpp, src/Sobel.cpp) */
+void orc_gaussian_kernel(int ksize, float* kernel);
+void orc_conv2d_u8(const uint8_t* img, int w, int h, size_t pitch, const float* kernel, int ksize, int reflect, float divisor, uint8_t* out);
+void orc_gaussian_blur_1d(const uint8_t* img, int w, int h, size_t pitch, uint8_t* out);
 void orc_harris(const uint8_t* img, int w, int h, size_t pitch, const orc_keypoint* kps, int n, float k, float* out);
 void orc_orientations(const uint8_t* img, int w, int h, size_t pitch, const orc_keypoint* kps, int n, int patch, float* out);
 void orc_brief(const uint8_t* img, int w, int h, size_t pitch, const orc_keypoint* kps, const float* angles, int n,

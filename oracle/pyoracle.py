@@ -83,6 +83,9 @@ def lib():
         L.orc_fast_scores.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
         L.orc_nms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orc_harris_weights.argtypes = [C.c_void_p]
+        L.orc_gaussian_kernel.argtypes = [C.c_int, C.c_void_p]
+        L.orc_conv2d_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
+        L.orc_gaussian_blur_1d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p]
         L.orc_orientations.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orc_brief.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.orc_brief_flags.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -202,6 +205,32 @@ def harris_weights():
     w = np.empty(49, np.float32)
     lib().orc_harris_weights(_ptr(w))
     return w
+
+
+def gaussian_kernel(ksize):
+    """createGaussianKernel(ksize) of the reference (src/GaussianBlur.cpp:7-37)."""
+    k = np.empty(ksize * ksize, np.float32)
+    lib().orc_gaussian_kernel(ksize, _ptr(k))
+    return k
+
+
+def conv2d_u8(img, kernel, reflect=False, divisor=0.0):
+    """conv2d() of the reference (src/cuda/Convolution.cu): valid-mode correlation -> CV_8U; reflect: BORDER_REFLECT_101 first."""
+    img = _img(img)
+    kernel = np.ascontiguousarray(kernel, np.float32).ravel()
+    K = int(round(len(kernel) ** 0.5))
+    h, w = img.shape
+    oh, ow = (h, w) if reflect else (h - K + 1, w - K + 1)
+    out = np.empty((oh, ow), np.uint8)
+    lib().orc_conv2d_u8(_ptr(img), w, h, img.strides[0], _ptr(kernel), K, int(reflect), float(divisor), _ptr(out))
+    return out
+
+
+def gaussian_blur_1d(img):
+    img = _img(img)
+    out = np.empty(img.shape, np.uint8)
+    lib().orc_gaussian_blur_1d(_ptr(img), img.shape[1], img.shape[0], img.strides[0], _ptr(out))
+    return out
 
 
 def harris(img, kps, k=0.04):

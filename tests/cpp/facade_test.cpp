@@ -73,6 +73,19 @@ int main(int argc, char** argv) {
         RotatedBRIEFCPU bcpu;
         long box = 0; for (int dy = -2; dy <= 2; dy++) for (int dx = -2; dx <= 2; dx++) box += pix[(size_t)(100 + dy) * w + 200 + dx];
         if (bcpu.sum5x5(imat, 200, 100, w + 1) != box) { fprintf(stderr, "sum5x5\n"); return 7; }
+        // the reference's stand-alone filters (include/Convolution.cuh, GaussianBlur.cuh, GaussianBlur.hpp, Sobel.hpp)
+        {
+            cv::Mat g5, g1d, g7, sbx, sby, cv3;
+            GaussianBlur(image, g5); GaussianBlur1D(image, g1d); GaussianBlurCUDA(image, g7, 7); SobelCUDA(image, sbx, 0); SobelCUDA(image, sby, 1);
+            float box3[9] = {0.111f, 0.111f, 0.111f, 0.111f, 0.112f, 0.111f, 0.111f, 0.111f, 0.111f};
+            if (conv2d(image, cv3, box3, 3) != 0 || cv3.rows != h - 2 || cv3.cols != w - 2) { fprintf(stderr, "conv2d shape\n"); return 9; }
+            auto dump_mat = [&](const std::string& tag, const cv::Mat& m) {
+                std::vector<unsigned char> v((size_t)m.rows * m.cols);
+                for (int y = 0; y < m.rows; y++) for (int x = 0; x < m.cols; x++) v[(size_t)y * m.cols + x] = m.ptr<unsigned char>(y)[x];
+                dump(out + ".filt." + tag, v);
+            };
+            dump_mat("g5", g5); dump_mat("g1d", g1d); dump_mat("g7", g7); dump_mat("sx", sbx); dump_mat("sy", sby); dump_mat("c3", cv3);
+        }
         // detect(image, 0): the reference returns an empty vector (quota 0 levels)
         if (!fast.detect(image, 0).empty()) { fprintf(stderr, "detect(0)\n"); return 8; }
         if (kp_count != (int)kf.size() || kf.size() != ks.size()) { fprintf(stderr, "Fast() count\n"); return 5; }

@@ -65,6 +65,17 @@ def test_facade_matches_oracle(tmp_path, V, O, kitti0):
     assert np.array_equal(hs.view(np.uint32), O.harris(kitti0, kr, 0.04).view(np.uint32))
     h0 = np.fromfile(out + ".free.harris_k0", dtype=np.float32)                     # the reference's `int k` signature: k = 0
     assert np.array_equal(h0.view(np.uint32), O.harris(kitti0, kr, 0.0).view(np.uint32))
+    # the reference's stand-alone filters through the facade
+    G5 = np.float32([1, 4, 7, 4, 1, 4, 16, 26, 16, 4, 7, 26, 41, 26, 7, 4, 16, 26, 16, 4, 1, 4, 7, 4, 1])
+
+    def filt(tag, shape=(376, 1241)):
+        return np.fromfile(out + ".filt." + tag, dtype=np.uint8).reshape(shape)
+    assert np.array_equal(filt("g5"), O.conv2d_u8(kitti0, G5, True, 273.0))
+    assert np.array_equal(filt("g1d"), O.gaussian_blur_1d(kitti0))
+    assert np.array_equal(filt("g7"), O.conv2d_u8(kitti0, O.gaussian_kernel(7), True))
+    assert np.array_equal(filt("sx"), O.conv2d_u8(kitti0, np.float32([-1, 0, 1, -2, 0, 2, -1, 0, 1]), True))
+    assert np.array_equal(filt("sy"), O.conv2d_u8(kitti0, np.float32([-1, -2, -1, 0, 0, 0, 1, 2, 1]), True))
+    assert np.array_equal(filt("c3", (374, 1239)), O.conv2d_u8(kitti0, np.float32([0.111, 0.111, 0.111, 0.111, 0.112, 0.111, 0.111, 0.111, 0.111])))
     # NMS() over the synthetic score map of facade_test.cpp
     ys, xs = np.mgrid[0:376, 0:1241]
     m = (((xs * 7 + ys * 13) % 31) * ((xs ^ ys) & 1)).astype(np.float32)

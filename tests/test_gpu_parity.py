@@ -142,6 +142,30 @@ def test_nms_over_a_callers_score_map(V, O, kitti0):
     c.close()
 
 
+def test_reference_filter_wrappers(V, O, kitti0):
+    """conv2d / GaussianBlur / GaussianBlur1D / GaussianBlurCUDA / SobelCUDA of the reference's stage seam (include/Convolution.cuh:5,
+    GaussianBlur.cuh:3-4, GaussianBlur.hpp:6, Sobel.hpp:6): float accumulation with one FMA per tap, convertTo(CV_8U); byte-exact
+    against the oracle's restatement, which is itself tied to cv2 where OpenCV has the same operator."""
+    import cv2
+    c = V.Context(V.make_params(nlevels=1, max_width=1241, max_height=376))
+    rng = np.random.default_rng(3)
+    G5 = np.float32([1, 4, 7, 4, 1, 4, 16, 26, 16, 4, 7, 26, 41, 26, 7, 4, 16, 26, 16, 4, 1, 4, 7, 4, 1])
+    for img in (kitti0, noise_image(37, 53, 2), noise_image(5, 7, 3)):
+        assert np.array_equal(c.conv2d_u8(img, G5, True, 273.0), O.conv2d_u8(img, G5, True, 273.0))              # GaussianBlur
+        assert np.array_equal(c.gaussian_blur_1d(img), O.gaussian_blur_1d(img))                                      # GaussianBlur1D
+        for ks in (3, 5, 7):
+            assert np.array_equal(c.conv2d_u8(img, O.gaussian_kernel(ks), True), O.conv2d_u8(img, O.gaussian_kernel(ks), True))   # GaussianBlurCUDA
+        for k in (np.float32([-1, 0, 1, -2, 0, 2, -1, 0, 1]), np.float32([-1, -2, -1, 0, 0, 0, 1, 2, 1])):           # SobelCUDA
+            got = c.conv2d_u8(img, k, True)
+            assert np.array_equal(got, O.conv2d_u8(img, k, True))
+            ref = cv2.Sobel(img, cv2.CV_32F, int(k[2] == 1), int(k[2] != 1), ksize=3, borderType=cv2.BORDER_REFLECT_101)
+            assert np.array_equal(got, np.clip(ref, 0, 255).astype(np.uint8))
+        kr = rng.normal(0, 0.3, 25).astype(np.float32)                                                                # conv2d, valid mode
+        if img.shape[0] >= 5:
+            assert np.array_equal(c.conv2d_u8(img, kr), O.conv2d_u8(img, kr))
+    c.close()
+
+
 def test_reference_single_level_mode_golden(V, golden, kitti0, kitti1):
     """ORBCPU as shipped (D3) -- compared with the outputs of the reference's own compiled code."""
     orb = V.ORBCPU(max_width=1241, max_height=376)

@@ -19,6 +19,10 @@
 #include "orb_kernels.cuh"
 #include "orb_match_tc.cuh"
 
+#ifndef ORB_E2E_RAMP_DOWN
+#define ORB_E2E_RAMP_DOWN 1
+#endif
+
 using orbk::Bufs;
 using orbk::DescribeJob;
 
@@ -668,10 +672,20 @@ static int run_batch_body(orb_ctx* ctx, const uint8_t* frames, int frames_on_dev
     int wave = (direct && outputs_on_device) ? ctx->chunk : ctx->chunk_staged;
     if (source && source->preferred_wave(ctx) > 0) wave = std::min(ctx->chunk, source->preferred_wave(ctx));
     int c0 = 0, ramp = (!direct && n_frames > wave) ? std::max(1, wave / 8) : wave;
-    while (c0 < n_frames) {
+    // ... and (ORB_E2E_RAMP_DOWN) the last waves shrink again (wave/2, wave/4, wave/8): what is left after the last frame
+    // has arrived is the computation and the result copy of the last wave only
+    int tail = 0;
+#if ORB_E2E_RAMP_DOWN
+    if (!direct && !outputs_on_device && !source && n_frames >= 4 * wave) tail = wave / 2 + wave / 4 + wave / 8;
+#endif
+    while (c0 < n_frames - tail) {
       wave_begin.push_back(c0);
-      c0 += std::min(ramp, wave);
+      c0 += std::min(std::min(ramp, wave), n_frames - tail - c0);
       if (ramp < wave) ramp *= 2;
+    }
+    for (int d = wave / 2; tail > 0 && c0 < n_frames; d = std::max(1, d / 2)) {
+      wave_begin.push_back(c0);
+      c0 += std::min(d <= wave / 8 ? n_frames - c0 : d, n_frames - c0);
     }
     wave_begin.push_back(n_frames);
   }
@@ -949,6 +963,44 @@ int orb_nms_scores(orb_ctx* ctx, const float* scores, int w, int h, size_t pitch
   CK(cudaMemcpy(xy.data(), ctx->d_kept_xy, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost));
   for (int i = 0; i < m; i++) kps[i] = orb_keypoint{(int)(xy[i] & 0xffff), (int)(xy[i] >> 16)};
   *n_out = m;
+  return ORB_OK;
+}
+
+// ---- the reference's stand-alone filter wrappers ------------------------------------------------------------
+static int scratch(orb_ctx* ctx, int slot, size_t bytes, void** out);
+
+int orb_conv2d_u8(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch, const float* kernel, int ksize, int border_reflect101,
+                  float divisor, uint8_t* out, size_t out_pitch) {
+  if (!ctx || !kernel || !out) return ORB_E_INVALID;
+  if (ksize < 1 || ksize > 31 || !(ksize & 1)) return fail(ctx, ORB_E_INVALID, "kernel size must be odd, 1..31");
+  const int ow = border_reflect101 ? w : w - ksize + 1, oh = border_reflect101 ? h : h - ksize + 1;
+  if (ow < 1 || oh < 1 || out_pitch < (size_t)ow) return fail(ctx, ORB_E_INVALID, "image smaller than the kernel / bad output pitch");
+  CK(cudaSetDevice(ctx->p.device));
+  int rc = stage_image(ctx, img, w, h, pitch);
+  if (rc) return rc;
+  uint8_t* d_out = nullptr; float* d_k = nullptr;
+  if ((rc = scratch(ctx, 0, (size_t)ow * oh, (void**)&d_out)) || (rc = scratch(ctx, 1, sizeof(float) * ksize * ksize, (void**)&d_k))) return rc;
+  CK(cudaMemcpyAsync(d_k, kernel, sizeof(float) * ksize * ksize, cudaMemcpyHostToDevice, ctx->stream));
+  orbk::k_conv2d_u8<<<dim3((ow + 127) / 128, oh), 128, sizeof(float) * ksize * ksize, ctx->stream>>>(
+      ctx->d_frames, ctx->frames_pitch, w, h, d_k, ksize, border_reflect101, divisor, d_out, ow, ow, oh);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy2DAsync(out, out_pitch, d_out, ow, ow, oh, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return ORB_OK;
+}
+
+int orb_gaussian_blur_1d(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch, uint8_t* out, size_t out_pitch) {
+  if (!ctx || !out) return ORB_E_INVALID;
+  if (out_pitch < (size_t)w) return fail(ctx, ORB_E_INVALID, "bad output pitch");
+  CK(cudaSetDevice(ctx->p.device));
+  int rc = stage_image(ctx, img, w, h, pitch);
+  if (rc) return rc;
+  uint8_t* d_out = nullptr;
+  if ((rc = scratch(ctx, 0, (size_t)w * h, (void**)&d_out))) return rc;
+  orbk::k_gauss1d_u8<<<dim3((w + 127) / 128, h), 128, 0, ctx->stream>>>(ctx->d_frames, ctx->frames_pitch, w, h, d_out, w);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy2DAsync(out, out_pitch, d_out, w, w, h, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return ORB_OK;
 }
 

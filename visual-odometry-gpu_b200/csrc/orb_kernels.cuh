@@ -1,21 +1,25 @@
-// orb_kernels.cuh -- sm_100a kernels of the ORB hot path (u8 end to end; no tensor cores: nothing in the extractor is
-// a dense contraction).  Per wave of frames one small memset and five launches:
+// orb_kernels.cuh -- sm_100a kernels of the ORB hot path (u8 end to end; the extractor uses no tensor cores: nothing in it
+// is a dense contraction -- the matcher in orb_match_tc.cuh is, and runs on them).  Per wave of frames one small memset
+// and six launches:
 //   k_pyramid  : per (frame, level >= 1, 128x64 tile): bilinear resize from level 0 + 5x5 Gaussian in shared memory,
 //                level pixels written once.  Replaces ORB::buildPyramid (ref src/orb.cpp:111-120 / src/orb_cpu.cpp:278-290).
-//   k_fast     : per (frame, level, 128x64 tile): FAST-n segment test + SAD score + 3x3 NMS -> candidate positions;
-//                5x5 box-sum image and border strip tables for BRIEF.  Replaces d_Fast (ref src/cuda/Fast.cu:30-209),
-//                d_NMS (src/cuda/NMS.cu:21-128) and the host cv::integral (src/cuda/Brief.cu:101-105).
+//   k_fast     : per (frame, level, 128x64 tile), tile staged by one TMA load: byte-SIMD prefilter + exact compass pretest,
+//                FAST-n segment test + SAD score + 3x3 NMS -> candidate positions; 5x5 box-sum image and border strip
+//                tables for BRIEF.  Replaces d_Fast (ref src/cuda/Fast.cu:30-209), d_NMS (src/cuda/NMS.cu:21-128) and the
+//                host cv::integral (src/cuda/Brief.cu:101-105).
+//   k_edges    : per (frame, level): the values of BRIEF boxes whose centre lies in the last two columns / rows
+//                (decision D7) as tables, from k_fast's strip tables (side stream, next to k_harris / k_select).
 //   k_harris   : one thread per candidate: Harris response into the candidate key.  Replaces HarrisScore
 //                (ref src/cuda/HarrisScore.cu:23-89 + src/Sobel.cpp + src/GaussianBlur.cpp).
 //   k_select   : per (frame, level): exact top-quota selection under the total order (response desc, y asc, x asc) by
 //                64-bit radix select, then raster sort (ref std::nth_element at src/orb.cpp:73-86; raster cap at
 //                src/orb_cpu.cpp:110).
-//   k_describe : CTA per 32 kept keypoints (warp per keypoint; lane per keypoint for the libm part):
-//                intensity-centroid orientation (ref d_Orientations, src/cuda/Orientations.cu:22-63 == src/orb_cpu.cpp:139-183) and rotated BRIEF with ballot-packed words
+//   k_describe : CTA per 32 kept keypoints (warp per keypoint; lane per keypoint for the libm part); patches and box-sum
+//                windows staged per keypoint by cp.async rings: intensity-centroid orientation (ref d_Orientations,
+//                src/cuda/Orientations.cu:22-63 == src/orb_cpu.cpp:139-183) and rotated BRIEF with ballot-packed words
 //                (ref d_Brief, src/cuda/Brief.cu:40-95 == src/orb_cpu.cpp:203-258).
-// plus k_edges (border-box value tables for BRIEF), k_nms_scores (NMS over a caller's score map); the descriptor matcher
-// lives in orb_match_tc.cuh (tensor cores)
-// and two helpers for the single-image stage entry points (k_harris_list, k_eval_math).
+// plus k_nms_scores (NMS over a caller's score map, ref NMS() include/NMS.cuh:5) and two helpers for the single-image
+// stage entry points (k_harris_list, k_eval_math).
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -390,9 +394,12 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
 }
 
 // =============================================================================================
-// Kernel B: FAST-n + SAD score + 3x3 NMS + 5x5 box sums on one 128x64 tile of one level (tile staged by cp.async).
-//   pretest  : the >=3-of-4 compass test (ref src/orb_cpu.cpp:39-58) on packed half2 (2 pixels / instruction):
-//              second smallest / second largest of the four compass pixels against Ip +- thr, or saturated counts;
+// Kernel B: FAST-n + SAD score + 3x3 NMS + 5x5 box sums on one 128x64 tile of one level (tile + 4-pixel halo staged by one
+// TMA load, out-of-level pixels zero-filled).
+//   pretest  : the >=3-of-4 compass test (ref src/orb_cpu.cpp:39-58): a byte-SIMD necessary condition (VABSDIFF4, 4 pixels /
+//              instruction) drops ~2/3 of the 8-pixel row items; the survivors, compacted by ballot ranks, take the exact
+//              test on packed half2 (2 pixels / instruction): second smallest / second largest of the four compass pixels
+//              against Ip +- thr, or saturated counts;
 //   ring     : passers are compacted into a shared list and finished one pixel per thread (arc + SAD);
 //   NMS      : score == max of its 3x3 window, ties keep both (:126); survivors are appended to the level's
 //              candidate list (k_harris adds their response);
@@ -868,7 +875,8 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
 // Kernel C: Harris response of every NMS survivor (decision D5), one thread per candidate, grid-stride over the
 // candidates of a frame.  Replaces HarrisScore() (ref src/cuda/HarrisScore.cu:42-89, call site src/orb.cpp:65): the
 // reference blurs three full-frame product images to read them at <= 2N points; here the 9x9 neighbourhood of each
-// candidate is read from the level (L2-resident, just written) and the response goes into the high word of its key.
+// candidate is read from the level and the response goes into the high word of its key.  All Sobel arithmetic is exact
+// float arithmetic on small integers; only the 147 weighted accumulations round, in the reference order.
 #ifndef ORB_C_MINB
 #define ORB_C_MINB 8
 #endif
@@ -1568,6 +1576,49 @@ __global__ void k_nms_scores(const float* __restrict__ sc, int pitch, int w, int
       if (sc[(size_t)(y + dy) * pitch + x + dx] > v) return;
   const int slot = atomicAdd(count, 1);
   if (slot < cap) cand[slot] = (unsigned long long)(unsigned)((y << 16) | x);
+}
+
+// ---- the reference's stand-alone filter wrappers (stage entry points orb_conv2d_u8 / orb_gaussian_blur_1d) -----------
+// conv2d (ref src/cuda/Convolution.cu:20-103): K x K correlation of the u8 image promoted to float, accumulated row by row
+// with one FMA per tap (what `sum += tile * kernel` compiles to in the reference's default nvcc build), converted like
+// cv::Mat::convertTo(CV_8U) (round half to even, saturate).  reflect: the image is first extended by K/2 with
+// BORDER_REFLECT_101 (GaussianBlurCUDA, SobelCUDA, GaussianBlur), so the output has the input's size; otherwise valid mode.
+__device__ __forceinline__ uint8_t float_to_u8(float v) { return (uint8_t)min(max(__float2int_rn(v), 0), 255); }
+
+__global__ void k_conv2d_u8(const uint8_t* __restrict__ img, int pitch, int w, int h, const float* __restrict__ kernel, int K, int reflect,
+                            float divisor, uint8_t* __restrict__ out, int opitch, int ow, int oh) {
+  extern __shared__ float s_k[];
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x) s_k[i] = kernel[i];
+  __syncthreads();
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= ow || y >= oh) return;
+  const int r = K / 2;
+  float sum = 0.0f;
+  for (int i = 0; i < K; i++) {
+    const uint8_t* row = img + (size_t)(reflect ? reflect101(y + i - r, h) : y + i) * pitch;
+    for (int j = 0; j < K; j++) sum = __fmaf_rn((float)row[reflect ? reflect101(x + j - r, w) : x + j], s_k[i * K + j], sum);
+  }
+  if (divisor != 0.0f) sum = __fdiv_rn(sum, divisor);
+  out[(size_t)y * opitch + x] = float_to_u8(sum);
+}
+
+// GaussianBlur1D (ref src/cuda/GaussianBlur1D.cu): [1 4 6 4 1] / 16 along x then along y in float.  Every intermediate is a
+// small dyadic rational, so the float result equals v / 256 exactly with v the integer 5 x 5 sum; convertTo(CV_8U) rounds
+// half to even.
+__global__ void k_gauss1d_u8(const uint8_t* __restrict__ img, int pitch, int w, int h, uint8_t* __restrict__ out, int opitch) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  const int kw[5] = {1, 4, 6, 4, 1};
+  int v = 0;
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    const uint8_t* row = img + (size_t)reflect101(y + i - 2, h) * pitch;
+    int hs = 0;
+#pragma unroll
+    for (int j = 0; j < 5; j++) hs += kw[j] * row[reflect101(x + j - 2, w)];
+    v += kw[i] * hs;
+  }
+  out[(size_t)y * opitch + x] = float_to_u8(__fdiv_rn((float)v, 256.0f));
 }
 
 // trips one check on purpose (tests/test_gpu_bounds.py: the counters of a bounds-check build do count)

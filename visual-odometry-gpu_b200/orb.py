@@ -48,7 +48,7 @@ class ImageInfo(C.Structure):
 EXPORTS = [
     "orb_abi_version", "orb_default_params", "orb_create", "orb_destroy", "orb_last_error", "orb_set_stream", "orb_use_own_stream",
     "orb_synchronize", "orb_detect_and_compute", "orb_detect_and_compute_batch", "orb_get_level", "orb_level_size",
-    "orb_level_quota", "orb_fast_detect", "orb_nms_scores", "orb_harris", "orb_orientations", "orb_brief", "orb_get_side_arrays",
+    "orb_level_quota", "orb_fast_detect", "orb_nms_scores", "orb_conv2d_u8", "orb_gaussian_blur_1d", "orb_harris", "orb_orientations", "orb_brief", "orb_get_side_arrays",
     "orb_get_candidates", "orb_get_harris_weights", "orb_last_launch_count", "orb_set_profiling", "orb_get_stage_ms", "orb_match_knn2", "orb_match_knn2_batch", "orb_ratio_test", "orb_debug_eval_math", "orb_debug_bounds_check", "orb_debug_bounds_selftest", "bit_pattern_31_",
     "orb_png_info", "orb_png_decode_gray8", "orb_imread_gray8", "orb_detect_and_compute_files", "orb_get_ingested_frame", "orb_debug_inflate", "orb_lk_track", "orb_lk_levels", "orb_lk_get_level",
 ]
@@ -358,6 +358,25 @@ class Context:
         self._ck(self.lib.orb_nms_scores(self.h, _p(sc), sc.shape[1], sc.shape[0], C.c_size_t(sc.strides[0]), int(nms_window), int(nfeatures),
                                          C.c_float(threshold), _p(kps), C.byref(n)))
         return kps[:n.value]
+
+    def conv2d_u8(self, image, kernel, reflect=False, divisor=0.0):
+        """conv2d() of the reference (include/Convolution.cuh:5) -> uint8 image; reflect: BORDER_REFLECT_101 first (same size out)."""
+        img = _img(image)
+        k = np.ascontiguousarray(kernel, np.float32).ravel()
+        K = int(round(len(k) ** 0.5))
+        h, w = img.shape
+        oh, ow = (h, w) if reflect else (h - K + 1, w - K + 1)
+        out = np.zeros((max(oh, 1), max(ow, 1)), np.uint8)
+        self._ck(self.lib.orb_conv2d_u8(self.h, _p(img), w, h, C.c_size_t(img.strides[0]), _p(k), K, int(bool(reflect)), C.c_float(divisor),
+                                        _p(out), C.c_size_t(out.strides[0])))
+        return out
+
+    def gaussian_blur_1d(self, image):
+        img = _img(image)
+        out = np.zeros(img.shape, np.uint8)
+        self._ck(self.lib.orb_gaussian_blur_1d(self.h, _p(img), img.shape[1], img.shape[0], C.c_size_t(img.strides[0]), _p(out),
+                                               C.c_size_t(out.strides[0])))
+        return out
 
     def harris(self, image, kps):
         img = _img(image)
