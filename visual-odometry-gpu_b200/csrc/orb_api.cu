@@ -288,7 +288,8 @@ int launch_select(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, int nframes) {
   dim3 grid(P.nlevels, nframes);
   {
     StageTimer t(ctx, 3);
-    orbk::k_select<<<grid, orbk::K2_THREADS, (size_t)(npow2 + orbk::K2_SMEM_KEYS) * 8, ctx->stream>>>(P, B, npow2);
+    const size_t rows = (size_t)std::min(P.H, orbk::K2_MAX_ROWS) + 1;        // counting sort over rows: [npow2] row groups + row counters
+    orbk::k_select<<<grid, orbk::K2_THREADS, (size_t)(2 * npow2 + orbk::K2_SMEM_KEYS) * 8 + rows * 4, ctx->stream>>>(P, B, npow2);
   }
   CK(cudaGetLastError());
   ctx->launches += 1;
@@ -537,7 +538,8 @@ int orb_create(const orb_params* p, orb_ctx** out) {
     CK(cudaMemset(ctx->d_flags, 0, sizeof(int)));
     CK(cudaFuncSetAttribute(orbk::k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, orbk::B_SMEM));
     CK(cudaFuncSetAttribute(orbk::k_match_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, orbk::MT_SMEM));
-    CK(cudaFuncSetAttribute(orbk::k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (ORB_SORT_CAP + orbk::K2_SMEM_KEYS) * 8));
+    CK(cudaFuncSetAttribute(orbk::k_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (2 * ORB_SORT_CAP + orbk::K2_SMEM_KEYS) * 8 + (orbk::K2_MAX_ROWS + 1) * 4));
     return ORB_OK;
   };
   rc = body();

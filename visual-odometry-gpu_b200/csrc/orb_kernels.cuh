@@ -940,9 +940,10 @@ __global__ void __launch_bounds__(C_THREADS, ORB_C_MINB) k_harris(const OrbPlan 
 // Selection: CTA per (frame, level).
 constexpr int K2_THREADS = 512;
 constexpr int K2_SMEM_KEYS = 6144;   // candidate keys of a level are staged in shared memory when they fit
+constexpr int K2_MAX_ROWS = 4096;    // levels up to this height put their kept keys in raster order by a counting sort over rows
 
 __global__ void __launch_bounds__(K2_THREADS) k_select(const OrbPlan P, const Bufs B, int npow2_max) {
-  extern __shared__ __align__(16) unsigned long long s_dyn[];   // [npow2_max] sort buffer, then [K2_SMEM_KEYS] keys
+  extern __shared__ __align__(16) unsigned long long s_dyn[];   // [npow2_max] sort buffer, [K2_SMEM_KEYS] keys, [npow2_max] row groups, [h + 1] row counters
   unsigned long long* s_sort = s_dyn;
   unsigned long long* s_keys = s_dyn + npow2_max;
   __shared__ int s_hist[256];
@@ -1015,11 +1016,15 @@ __global__ void __launch_bounds__(K2_THREADS) k_select(const OrbPlan P, const Bu
     }
     T = s_prefix;
   }
-  // gather the kept keys as (raster << 32 | response order) and sort by raster
+  // gather the kept keys as (raster << 32 | response order) and put them in raster order
   if (tid == 0) s_n = 0;
   int npow2 = 1;
   while (npow2 < m) npow2 <<= 1;
-  for (int i = tid; i < npow2; i += K2_THREADS) s_sort[i] = ~0ull;
+  const bool by_rows = G.h <= K2_MAX_ROWS;       // counting sort over rows (below); bitonic sort for taller levels
+  int* s_row = (int*)(s_dyn + npow2_max + K2_SMEM_KEYS + (by_rows ? npow2_max : 0));   // [h + 1]
+  unsigned long long* s_out = s_dyn + npow2_max + K2_SMEM_KEYS;                        // [m] keys grouped by row
+  if (by_rows) for (int i = tid; i <= G.h; i += K2_THREADS) s_row[i] = 0;
+  else for (int i = tid; i < npow2; i += K2_THREADS) s_sort[i] = ~0ull;
   __syncthreads();
   if (m > 0)
     for (int i = tid; i < n; i += K2_THREADS) {
@@ -1028,27 +1033,68 @@ __global__ void __launch_bounds__(K2_THREADS) k_select(const OrbPlan P, const Bu
         int pos = atomicAdd(&s_n, 1);
         ORB_CHECK(pos < m && npow2 <= npow2_max);
         if (pos < npow2) s_sort[pos] = (k << 32) | (k >> 32);
+        if (by_rows) atomicAdd(&s_row[(int)((k >> 16) & 0xffff)], 1);
       }
     }
   __syncthreads();
-  for (int size = 2; size <= npow2; size <<= 1)
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = tid; i < (npow2 >> 1); i += K2_THREADS) {
-        int lo = 2 * i - (i & (stride - 1));
-        int hi = lo + stride;
-        bool up = (lo & size) == 0;
-        unsigned long long a = s_sort[lo], b = s_sort[hi];
-        if ((a > b) == up) { s_sort[lo] = b; s_sort[hi] = a; }
-      }
-      __syncthreads();
-    }
   uint32_t* kxy = B.kept_xy + (size_t)f * P.kept_per_frame + G.kept_ofs;
   float* kr = B.kept_r + (size_t)f * P.kept_per_frame + G.kept_ofs;
   ORB_CHECK(G.kept_ofs + m <= P.kept_per_frame && n <= G.cand_cap && (n <= K2_SMEM_KEYS || keys == gkeys));
-  for (int i = tid; i < m; i += K2_THREADS) {
-    unsigned long long v = s_sort[i];
-    kxy[i] = (uint32_t)(v >> 32);
-    kr[i] = P.select_policy == ORB_SELECT_HARRIS_TOP_N ? ord2f(~(uint32_t)v) : 0.0f;
+  const bool harris = P.select_policy == ORB_SELECT_HARRIS_TOP_N;
+  if (by_rows) {
+    // rows are few (<= K2_MAX_ROWS) and hold a handful of kept keys each: exclusive prefix over the row counts, scatter
+    // into row groups, then every key finds its place inside its row by counting the smaller ones -- five barriers
+    // instead of the ~45 of a bitonic sort of 512 keys
+    constexpr int RPT = (K2_MAX_ROWS + K2_THREADS - 1) / K2_THREADS;     // rows per thread
+    int loc[RPT], sum = 0;
+#pragma unroll
+    for (int j = 0; j < RPT; j++) { const int r = tid * RPT + j; loc[j] = r < G.h ? s_row[r] : 0; sum += loc[j]; }
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_hist[tid >> 5] = incl;                             // (s_hist is free after the radix passes)
+    __syncthreads();
+    int wbase = 0;
+    for (int wi = 0; wi < (tid >> 5); wi++) wbase += s_hist[wi];
+    int run = wbase + incl - sum;
+    __syncthreads();                                                     // every count has been read
+#pragma unroll
+    for (int j = 0; j < RPT; j++) { const int r = tid * RPT + j; if (r < G.h) s_row[r] = run; run += loc[j]; }   // cursor = first slot of the row
+    __syncthreads();
+    for (int i = tid; i < m; i += K2_THREADS) {
+      const unsigned long long v = s_sort[i];
+      s_out[atomicAdd(&s_row[(int)(v >> 48)], 1)] = v;                   // afterwards s_row[y] = end of row y = start of row y + 1
+    }
+    __syncthreads();
+    for (int i = tid; i < m; i += K2_THREADS) {
+      const unsigned long long v = s_out[i];
+      const int y = (int)(v >> 48), b0 = y ? s_row[y - 1] : 0, e0 = s_row[y];
+      int pos = b0;
+      for (int j = b0; j < e0; j++) pos += s_out[j] < v;
+      ORB_CHECK(pos < m && b0 <= i && i < e0);
+      kxy[pos] = (uint32_t)(v >> 32);
+      kr[pos] = harris ? ord2f(~(uint32_t)v) : 0.0f;
+    }
+  } else {
+    for (int size = 2; size <= npow2; size <<= 1)
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = tid; i < (npow2 >> 1); i += K2_THREADS) {
+          int lo = 2 * i - (i & (stride - 1));
+          int hi = lo + stride;
+          bool up = (lo & size) == 0;
+          unsigned long long a = s_sort[lo], b = s_sort[hi];
+          if ((a > b) == up) { s_sort[lo] = b; s_sort[hi] = a; }
+        }
+        __syncthreads();
+      }
+    for (int i = tid; i < m; i += K2_THREADS) {
+      unsigned long long v = s_sort[i];
+      kxy[i] = (uint32_t)(v >> 32);
+      kr[i] = harris ? ord2f(~(uint32_t)v) : 0.0f;
+    }
   }
   if (tid == 0) B.kept_count[f * ORB_MAX_LEVELS + l] = m;
 }
