@@ -421,6 +421,9 @@ constexpr int B_SH = B_TH + 2;         // rows y0-1 .. y0+B_TH
 #ifndef ORB_B_PREFILTER
 #define ORB_B_PREFILTER 1
 #endif
+#ifndef ORB_B_DIRECT_EMIT
+#define ORB_B_DIRECT_EMIT 1
+#endif
 constexpr int B_LIST = ORB_B_LIST;     // pretest passers kept in the list; denser tiles take the dense fallback
 constexpr int B_SURV = 1024;
 constexpr int B_PIX_BYTES = B_PH * B_SP, B_SCORE_BYTES = B_SH * B_SCP * 2;
@@ -465,6 +468,27 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
 #endif
   // passer bit b of a thread's mask word: row item b >> 3 (rows 14 apart), pixel 0,2,4,6,1,3,5,7 for b & 7 = 0..7
   if (tid < 32) s_tab[tid] = (uint16_t)((tid >> 3) * (14 * B_SP) + ((tid & 3) << 1) + ((tid >> 2) & 1));
+#if ORB_B_PREFILTER
+  {
+    constexpr int NG = 18;
+    if (tid < NG) {   // per column group: which of its 8 pixels are valid centres
+      const int xs = x0 - 8 + 8 * tid;
+      // valid centres: 3 <= x < w-3 (ref src/orb_cpu.cpp:35), inside tile + 1 halo column on each side
+      const int lo = max(max(0, 3 - xs), x0 - 1 - xs), hi = min(min(8, w - 3 - xs), x0 + B_TW + 1 - xs);
+      uint32_t vmask = 0, vb0 = 0, vb1 = 0;
+      if (lo < hi) {
+        const uint32_t v8m = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+  #pragma unroll
+        for (int q = 0; q < 4; q++) {                        // pixel 2q -> bit 10+q, pixel 2q+1 -> bit 26+q (see below)
+          vmask |= (((v8m >> (2 * q)) & 1u) << (10 + q)) | (((v8m >> (2 * q + 1)) & 1u) << (26 + q));
+          vb0 |= ((v8m >> q) & 1u) << (8 * q + 7);
+          vb1 |= ((v8m >> (4 + q)) & 1u) << (8 * q + 7);
+        }
+      }
+      s_vm[3 * tid] = vmask; s_vm[3 * tid + 1] = vb0; s_vm[3 * tid + 2] = vb1;
+    }
+  }
+#endif
   __syncthreads();          // the mbarrier is initialised for everybody
   mbar_wait(s_bar, 0);
 
@@ -479,23 +503,6 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
   //     that every lane of a warp has an item.
   const int thr = P.fast_threshold, fn = P.fast_n;
   constexpr int NG = 18, NRT = 14, NK = (B_SH + NRT - 1) / NRT;
-  if (tid < NG) {   // per column group: which of its 8 pixels are valid centres
-    const int xs = x0 - 8 + 8 * tid;
-    // valid centres: 3 <= x < w-3 (ref src/orb_cpu.cpp:35), inside tile + 1 halo column on each side
-    const int lo = max(max(0, 3 - xs), x0 - 1 - xs), hi = min(min(8, w - 3 - xs), x0 + B_TW + 1 - xs);
-    uint32_t vmask = 0, vb0 = 0, vb1 = 0;
-    if (lo < hi) {
-      const uint32_t v8m = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-#pragma unroll
-      for (int q = 0; q < 4; q++) {                        // pixel 2q -> bit 10+q, pixel 2q+1 -> bit 26+q (see below)
-        vmask |= (((v8m >> (2 * q)) & 1u) << (10 + q)) | (((v8m >> (2 * q + 1)) & 1u) << (26 + q));
-        vb0 |= ((v8m >> q) & 1u) << (8 * q + 7);
-        vb1 |= ((v8m >> (4 + q)) & 1u) << (8 * q + 7);
-      }
-    }
-    s_vm[3 * tid] = vmask; s_vm[3 * tid + 1] = vb0; s_vm[3 * tid + 2] = vb1;
-  }
-  __syncthreads();
   {
     const int g = tid % NG, rt = tid / NG;
     const int pc = 8 + 8 * g;
@@ -764,15 +771,21 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
                    max(max(s[1], s[B_SCP - 1]), max(s[B_SCP], s[B_SCP + 1])));
       if (v < mx) return;
     }
+#if ORB_B_DIRECT_EMIT
+    emit(idx, atomicAdd(gcount, 1));         // one global atomic per survivor (the compiler aggregates a warp's): no survivor
+                                             // list, no barriers between NMS, emission and the box sums
+#else
     const int slot = atomicAdd(&s_ctr[1], 1);
     if (slot < B_SURV) s_surv[slot] = (uint16_t)idx;
     else emit(idx, atomicAdd(gcount, 1));   // survivor list full: finish this one inline
+#endif
   };
   if (!dense) {
     for (int j = tid; j < n1; j += B_THREADS) nms_one(s_list[j]);
   } else {
     for (int i = tid; i < B_TH * B_TW; i += B_THREADS) nms_one((1 + i / B_TW) * B_SP + 16 + (i % B_TW));
   }
+#if !ORB_B_DIRECT_EMIT
   __syncthreads();
   const int nsurv = min(s_ctr[1], B_SURV);
   if (nsurv > 0) {
@@ -781,6 +794,7 @@ __global__ void __launch_bounds__(B_THREADS, ORB_B_MINB) k_fast(const OrbPlan P,
     const int base = s_ctr[2];
     for (int j = tid; j < nsurv; j += B_THREADS) emit(s_surv[j], base + j);
   }
+#endif
 
   // ---- phase 5/6: 5x5 box sums (replace the int32 integral image of ref src/orb_cpu.cpp:207-208) and the strip
   // sums for BRIEF boxes that leave the image on the right / bottom (decision D7):
