@@ -55,4 +55,5 @@ def build(force=False, verbose=False, extra=(), out=None):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv,
+                out=sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None))

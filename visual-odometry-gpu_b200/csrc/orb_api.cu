@@ -538,6 +538,7 @@ int orb_create(const orb_params* p, orb_ctx** out) {
     CK(cudaMemset(ctx->d_flags, 0, sizeof(int)));
     CK(cudaFuncSetAttribute(orbk::k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, orbk::B_SMEM));
     CK(cudaFuncSetAttribute(orbk::k_match_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, orbk::MT_SMEM));
+    { int dev = 0; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, dev)); }
     CK(cudaFuncSetAttribute(orbk::k_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (2 * ORB_SORT_CAP + orbk::K2_SMEM_KEYS) * 8 + (orbk::K2_MAX_ROWS + 1) * 4));
     return ORB_OK;
@@ -1021,7 +1022,7 @@ static int scratch(orb_ctx* ctx, int slot, size_t bytes, void** out) {
 
 // ---- descriptor matching -------------------------------------------------------------------------
 // Tensor-core path (orb_match_tc.cuh): descriptors are expanded to +-1 int8 rows in a grow-only device buffer, two tensor
-// maps (query rows, train rows; 128-byte swizzle) are encoded for the call, one CTA per 128 queries of a pair.
+// maps (query rows, train rows; 128-byte swizzle) are encoded for the call; persistent CTAs walk over (pair, 256 queries) items.
 static int match_tc(orb_ctx* ctx, const orb_descriptor* dq, int rows_q, long long stride_q, const orb_descriptor* dt, int rows_t,
                     long long stride_t, bool same_buffer, const int* dn, int nq, int nt, int npairs, long long out_stride, orb_match* dout) {
   if (npairs <= 0 || nq <= 0) return ORB_OK;
@@ -1051,8 +1052,11 @@ static int match_tc(orb_ctx* ctx, const orb_descriptor* dq, int rows_q, long lon
                        (size_t)std::max(same_buffer ? rows_q : rows_t, 1) * orbk::MT_KB, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B)))
     return rc;
   CK(cudaMemcpyAsync(ctx->d_match_maps, maps, sizeof(maps), cudaMemcpyHostToDevice, ctx->stream));
-  dim3 grid((nq + orbk::MT_M - 1) / orbk::MT_M, npairs);
-  orbk::k_match_tc<<<grid, orbk::MT_THREADS, orbk::MT_SMEM, ctx->stream>>>(ctx->d_match_maps, dn, nq, nt, out_stride, dout);
+  const int qblocks = (nq + orbk::MT_MB * orbk::MT_M - 1) / (orbk::MT_MB * orbk::MT_M);
+  const long long n_items = (long long)qblocks * npairs;
+  if (n_items > INT32_MAX) return fail(ctx, ORB_E_CAPACITY, "matcher: too many query blocks");
+  const int grid = (int)std::min<long long>(n_items, ctx->sm_count);
+  orbk::k_match_tc<<<grid, orbk::MT_THREADS, orbk::MT_SMEM, ctx->stream>>>(ctx->d_match_maps, dn, nq, nt, qblocks, (int)n_items, out_stride, dout);
   CK(cudaGetLastError());
   ctx->launches += same_buffer ? 2 : 3;
   return ORB_OK;

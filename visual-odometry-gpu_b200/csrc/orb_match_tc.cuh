@@ -3,14 +3,18 @@
 // Replaces flann->knnMatch(des1, des2, matches, 2) of the reference's VO loops (src/feature_matching.cpp:168,174-182;
 // src/feature_tracking.cpp:205-219) by an exact brute-force search, written as a contraction: with descriptor bits mapped to +-1,
 //     <a, b> = 256 - 2 * hamming(a, b),   i.e.   hamming = (256 - <a, b>) / 2,
-// and an INT8 x INT8 -> INT32 product of +-1 vectors of length 256 is exact (|sum| <= 256).  One CTA owns 128 query
-// descriptors of a frame pair and walks over the train descriptors in tiles of 256:
-//   k_match_expand : 256-bit descriptors -> 256 int8 (+1 / -1) per descriptor, rows beyond a frame's count zeroed;
-//   k_match_tc     : warp 0 (one lane) streams the int8 tiles with TMA (128-byte swizzle) into a two-stage ring,
-//                    warp 1 (one lane) issues tcgen05.mma.kind::i8 (M 128 x N 256 x K 32, eight per tile) into one of two
-//                    TMEM accumulators (2 x 256 columns), warps 2-5 read the finished accumulator with tcgen05.ld and keep
-//                    the two smallest (distance, index) keys per query row while the next tile is being multiplied.
-// Ties go to the lower train index (key = distance * 2^14 + index), exactly as the CPU oracle (orc_match_knn2).
+// and an INT8 x INT8 -> INT32 product of such vectors of length 256 is exact.
+//   k_match_expand : 256-bit descriptors -> 256 int8 (+8 / -8) per descriptor, rows beyond a frame's count zeroed;
+//   k_match_tc     : persistent, one CTA per SM walking over work items (frame pair, block of 256 query descriptors).
+//                    The item's two 128-row query blocks stay in shared memory while the train descriptors stream past in
+//                    tiles of 128 through a TMA ring (128-byte swizzle), so each train tile read from L2 serves 256 queries.
+//                    warp 0 (one lane) is the TMA producer, warp 1 (one lane) issues tcgen05.mma.kind::i8 (M 128 x N 128 x
+//                    K 32; eight per tile and query block, plus a ninth that adds the column index, see the kernel) into four
+//                    TMEM accumulators (2 query blocks x 2 buffers x 128 columns), warps 2-9 (one per TMEM lane quarter and
+//                    query block) read finished accumulators with tcgen05.ld and keep the two best per query row while the
+//                    next tile is being multiplied.  Pipeline state (barrier phases) carries over from item to item, so the
+//                    prologue of an item (query block load) overlaps the tail of the previous one.
+// Ties go to the lower train index, exactly as the CPU oracle (orc_match_knn2).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -21,12 +25,13 @@
 
 namespace orbk {
 
-constexpr int MT_M = 128, MT_N = 256, MT_KB = 256;          // queries per CTA, train descriptors per tile, bytes per descriptor
-constexpr int MT_STAGES = 2;
+constexpr int MT_M = 128, MT_N = 128, MT_KB = 256;          // rows of a query block, train descriptors per tile, bytes per descriptor
+constexpr int MT_MB = 2;                                    // query blocks per work item
+constexpr int MT_STAGES = 4;
 constexpr int MT_SLAB_A = MT_M * 128, MT_SLAB_B = MT_N * 128;   // one 128-byte K slab of a tile (SWIZZLE_128B atom rows)
 constexpr int MT_A_BYTES = 2 * MT_SLAB_A, MT_B_BYTES = 2 * MT_SLAB_B;
-constexpr int MT_SMEM = MT_A_BYTES + MT_STAGES * MT_B_BYTES + 128 + 1024 + 1024;   // + barriers + merge area + slack for the 1024-byte alignment
-constexpr int MT_EPI_WARPS = 8;                              // two warps per TMEM lane quarter, 128 columns of a tile each
+constexpr int MT_SMEM = MT_MB * MT_A_BYTES + MT_SLAB_A + MT_SLAB_B + MT_STAGES * MT_B_BYTES + 256 + 1024;   // + index slabs + barriers + alignment slack
+constexpr int MT_EPI_WARPS = 4 * MT_MB;                      // one warp per TMEM lane quarter and query block
 constexpr int MT_THREADS = 64 + 32 * MT_EPI_WARPS;            // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-9: epilogue
 constexpr int MT_MAX_INDEX = 1 << 14;                        // train indices must fit the key's low 14 bits
 
@@ -45,7 +50,7 @@ __global__ void k_match_expand(const orb_descriptor* __restrict__ desc, const in
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const uint32_t s = (((bits >> (4 * q)) & 0xfu) * 0x00204081u) & 0x01010101u;   // bit b of the nibble -> byte b (0 / 1)
-      w[q] = 0xffffffffu ^ (s * 0xfeu);                                               // 1 -> 0x01 (+1), 0 -> 0xff (-1)
+      w[q] = 0xf8f8f8f8u ^ (s * 0xf0u);                                               // 1 -> 0x08 (+8), 0 -> 0xf8 (-8)
     }
     v = make_uint4(w[0], w[1], w[2], w[3]);
   }
@@ -99,131 +104,230 @@ __device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, int (&v)[64]) {
                : "r"(taddr)
                : "memory");
 }
+// 32 lanes x 128 consecutive columns, low 16 bits of each, two columns per register -> 64 registers per thread
+__device__ __forceinline__ void tmem_ld_32x128_pack16(uint32_t taddr, int (&v)[64]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the loaded registers are valid only after tcgen05.wait::ld: pin every use behind the wait (no instructions emitted)
+__device__ __forceinline__ void tmem_ld_wait(int (&v)[64]) {
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 64; i++) asm volatile("" : "+r"(v[i]));
+}
 
-// grid (ceil(max queries / 128), pairs).  maps[0]: query rows, maps[1]: train rows (3-D: 256 bytes, rows, pairs; box 128 x 128).
+// grid: persistent (<= SM count).  maps[0]: query rows, maps[1]: train rows (3-D: 256 bytes, rows, pairs; box 128 x 128).
 // n_arr != nullptr: pair p matches the n_arr[p] descriptors of frame p against the n_arr[p + 1] of frame p + 1.
+// Work item i = (pair i / qblocks, query rows 256 * (i % qblocks) ..).
+//
+// The accumulator already IS the comparison key: the expanded rows hold +-8, so the eight data MMAs leave 64 * <a, b> (a
+// multiple of 128), and a ninth MMA over a constant K slab (query side: -1 in its first byte, train side: column - 64) adds
+// 64 - column:   acc = 64 * dot + 64 - column,   larger = nearer, ties to the lower column,
+// which the epilogue folds with three integer min / max per distance; tiles are merged in order into global keys
+// distance * 2^14 + index (smaller = nearer), so an equal distance in a later tile never displaces an earlier one.
 __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* __restrict__ maps, const int* __restrict__ n_arr, int nq_fixed,
-                                                            int nt_fixed, long long out_stride, orb_match* __restrict__ out) {
+                                                            int nt_fixed, int qblocks, int n_items, long long out_stride,
+                                                            orb_match* __restrict__ out) {
   extern __shared__ uint8_t mt_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)mt_smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B tiles: 1024-byte aligned
-  uint8_t* s_a = smem;
-  uint8_t* s_b = smem + MT_A_BYTES;
-  uint64_t* bars = (uint64_t*)(smem + MT_A_BYTES + MT_STAGES * MT_B_BYTES);
-  uint64_t *full = bars, *empty = bars + 2, *tfull = bars + 4, *tempty = bars + 6, *afull = bars + 8;
-  uint32_t* s_tmem = (uint32_t*)(bars + 10);
+  uint8_t* s_a = smem;                                    // [MT_MB] query blocks
+  uint8_t* s_ax = s_a + MT_MB * MT_A_BYTES;               // constant K slabs of the index term
+  uint8_t* s_bx = s_ax + MT_SLAB_A;
+  uint8_t* s_b = s_bx + MT_SLAB_B;                        // [MT_STAGES] train tiles
+  uint64_t* bars = (uint64_t*)(s_b + MT_STAGES * MT_B_BYTES);
+  uint64_t *bfull = bars, *bempty = bars + MT_STAGES, *afull = bars + 2 * MT_STAGES, *aempty = afull + MT_MB;
+  uint64_t *tfull = aempty + MT_MB, *tempty = tfull + 2 * MT_MB;   // [query block][buffer]
+  uint32_t* s_tmem = (uint32_t*)(tempty + 2 * MT_MB);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p = blockIdx.y, m0 = blockIdx.x * MT_M;
-  const int nq = n_arr ? n_arr[p] : nq_fixed, nt = n_arr ? n_arr[p + 1] : nt_fixed;
-  if (m0 >= nq) return;                                   // whole CTA: nothing allocated yet
-  const int ntiles = (nt + MT_N - 1) / MT_N;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(tfull + i, 1); mbar_init(tempty + i, MT_EPI_WARPS); }
-    mbar_init(afull, 1);
+    for (int i = 0; i < MT_STAGES; i++) { mbar_init(bfull + i, 1); mbar_init(bempty + i, 1); }
+    for (int i = 0; i < MT_MB; i++) { mbar_init(afull + i, 1); mbar_init(aempty + i, 1); }
+    for (int i = 0; i < 2 * MT_MB; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
     mbar_fence_init();
   }
-  if (warp == 1) {                                        // TMEM: 512 columns = two 128 x 256 int32 accumulators
+  if (warp == 1) {                                        // TMEM: 512 columns = four 128 x 128 int32 accumulators
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // index slabs, in the layout TMA's 128-byte swizzle gives the data slabs: 16-byte chunk c of row r sits at chunk c ^ (r & 7);
+  // only the first K step (32 bytes = chunks 0, 1) of a row is ever multiplied
+  for (int i = threadIdx.x; i < (MT_M + MT_N) * 8; i += MT_THREADS) {
+    const int r = i >> 3, c = i & 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (c == 0) v.x = r < MT_M ? 0xffu : (uint32_t)((r - MT_M - 64) & 0xff);   // queries: -1, train column j: j - 64
+    const int rr = r < MT_M ? r : r - MT_M;
+    *(uint4*)((r < MT_M ? s_ax : s_bx) + rr * 128 + ((c ^ (rr & 7)) << 4)) = v;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's reads
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
+  // every role walks the same item list and derives the same (nq, nt, blocks, tiles) for an item
+  auto item_shape = [&](int item, int& p, int& m0, int& nq, int& nt, int& mbs, int& ntiles) {
+    p = item / qblocks;
+    m0 = (item - p * qblocks) * (MT_MB * MT_M);
+    nq = n_arr ? n_arr[p] : nq_fixed;
+    nt = n_arr ? n_arr[p + 1] : nt_fixed;
+    ntiles = (nt + MT_N - 1) / MT_N;
+    mbs = nq <= m0 ? 0 : min(MT_MB, (nq - m0 + MT_M - 1) / MT_M);
+    if (ntiles == 0) mbs = -mbs;                          // nothing to multiply: the epilogue still writes "no neighbour"
+  };
+
   if (warp == 0) {
     if (lane == 0) {                                      // ===== TMA producer =====
-      mbar_expect_tx(afull, MT_A_BYTES);
-      tma_load_rows(s_a, maps + 0, afull, 0, m0, p);
-      tma_load_rows(s_a + MT_SLAB_A, maps + 0, afull, 128, m0, p);
-      for (int t = 0; t < ntiles; t++) {
-        const int st = t & 1;
-        mbar_wait(empty + st, ((t >> 1) & 1) ^ 1);        // the MMAs that read this stage have finished
+      uint32_t b_it = 0, a_it = 0;                        // tiles / items loaded so far (ring position and phase)
+      auto load_b = [&](int p, int t) {
+        const int st = b_it % MT_STAGES;
+        mbar_wait(bempty + st, ((b_it / MT_STAGES) & 1) ^ 1);   // the MMAs that read this stage have finished
         uint8_t* b = s_b + st * MT_B_BYTES;
-        mbar_expect_tx(full + st, MT_B_BYTES);
-        tma_load_rows(b, maps + 1, full + st, 0, t * MT_N, p);
-        tma_load_rows(b + MT_SLAB_A, maps + 1, full + st, 0, t * MT_N + 128, p);
-        tma_load_rows(b + MT_SLAB_B, maps + 1, full + st, 128, t * MT_N, p);
-        tma_load_rows(b + MT_SLAB_B + MT_SLAB_A, maps + 1, full + st, 128, t * MT_N + 128, p);
+        mbar_expect_tx(bfull + st, MT_B_BYTES);
+        tma_load_rows(b, maps + 1, bfull + st, 0, t * MT_N, p);
+        tma_load_rows(b + MT_SLAB_B, maps + 1, bfull + st, 128, t * MT_N, p);
+        b_it++;
+      };
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int p, m0, nq, nt, mbs, ntiles;
+        item_shape(item, p, m0, nq, nt, mbs, ntiles);
+        if (mbs <= 0) continue;
+        const int pre = min(ntiles, MT_STAGES - 1);       // train tiles requested before the query blocks: their stages free up first
+        for (int t = 0; t < pre; t++) load_b(p, t);
+        for (int mb = 0; mb < mbs; mb++) {
+          mbar_wait(aempty + mb, (a_it & 1) ^ 1);         // the previous item's MMAs on this block have finished
+          uint8_t* a = s_a + mb * MT_A_BYTES;
+          mbar_expect_tx(afull + mb, MT_A_BYTES);
+          tma_load_rows(a, maps + 0, afull + mb, 0, m0 + mb * MT_M, p);
+          tma_load_rows(a + MT_SLAB_A, maps + 0, afull + mb, 128, m0 + mb * MT_M, p);
+        }
+        for (int mb = mbs; mb < MT_MB; mb++) {            // unused block: keep its barriers in step
+          mbar_wait(aempty + mb, (a_it & 1) ^ 1);
+          mbar_arrive(afull + mb);
+        }
+        a_it++;
+        for (int t = pre; t < ntiles; t++) load_b(p, t);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {                                      // ===== MMA issuer =====
-      mbar_wait(afull, 0);
-      for (int t = 0; t < ntiles; t++) {
-        const int st = t & 1;
-        mbar_wait(tempty + st, ((t >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator
-        mbar_wait(full + st, (t >> 1) & 1);               // the tile has landed
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(s_a), b0 = smem_u32(s_b + st * MT_B_BYTES);
+      const uint64_t ax = umma_desc_k_sw128(smem_u32(s_ax)), bx = umma_desc_k_sw128(smem_u32(s_bx));
+      uint32_t b_it = 0, a_it = 0, acc_cnt[MT_MB] = {};   // tiles landed / items started / tiles multiplied per query block
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int p, m0, nq, nt, mbs, ntiles;
+        item_shape(item, p, m0, nq, nt, mbs, ntiles);
+        if (mbs <= 0) continue;
+        for (int t = 0; t < ntiles; t++, b_it++) {
+          const int st = b_it % MT_STAGES;
+          mbar_wait(bfull + st, (b_it / MT_STAGES) & 1);  // the tile has landed
+          const uint32_t b0 = smem_u32(s_b + st * MT_B_BYTES);
+          for (int mb = 0; mb < MT_MB; mb++) {
+            if (t == 0) mbar_wait(afull + mb, a_it & 1);
+            if (mb < mbs) {
+              const int buf = acc_cnt[mb] & 1;
+              mbar_wait(tempty + 2 * mb + buf, ((acc_cnt[mb] >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+              tc_fence_after();
+              const uint32_t a0 = smem_u32(s_a + mb * MT_A_BYTES), d = tmem + (2 * mb + buf) * MT_N;
 #pragma unroll
-        for (int ks = 0; ks < 8; ks++) {                  // K = 256 bytes = 8 x 32; 4 steps per 128-byte slab
-          const uint32_t ao = a0 + (ks >> 2) * MT_SLAB_A + (ks & 3) * 32, bo = b0 + (ks >> 2) * MT_SLAB_B + (ks & 3) * 32;
-          umma_i8(tmem + st * MT_N, umma_desc_k_sw128(ao), umma_desc_k_sw128(bo), ks > 0);
+              for (int ks = 0; ks < 8; ks++) {            // K = 256 bytes = 8 x 32; 4 steps per 128-byte slab
+                const uint32_t ao = a0 + (ks >> 2) * MT_SLAB_A + (ks & 3) * 32, bo = b0 + (ks >> 2) * MT_SLAB_B + (ks & 3) * 32;
+                umma_i8(d, umma_desc_k_sw128(ao), umma_desc_k_sw128(bo), ks > 0);
+              }
+              umma_i8(d, ax, bx, 1);                      // + 64 - column
+              umma_commit(tfull + 2 * mb + buf);          // accumulator ready
+              acc_cnt[mb]++;
+            }
+            if (t == ntiles - 1) umma_commit(aempty + mb);   // the query block may be replaced once everything issued so far is done
+          }
+          umma_commit(bempty + st);                       // smem stage free once these MMAs are done
         }
-        umma_commit(empty + st);                          // smem stage free once these MMAs are done
-        umma_commit(tfull + st);                          // accumulator ready
+        a_it++;
       }
     }
   } else {
-    // ===== epilogue: warp w owns TMEM lanes 32 * (w % 4) .. + 31 (its query rows) and columns 128 * half .. + 127 of every
-    // tile; chunks of 32 columns, the next chunk's tcgen05.ld in flight while the current one is folded into the keys =====
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
-    int k1 = 0x7fffffff, k2 = 0x7fffffff;                 // two smallest keys: distance << 14 | train index
-    auto fold = [&](const int (&v)[64], int kb, int nvalid) {   // key = (256 - dot) / 2 * 2^14 + j = (256 - dot) * 2^13 + j
-      if (nvalid >= 64) {
+    // ===== epilogue: warp w owns TMEM lanes 32 * (w % 4) .. + 31 = query rows of block mb = (w - 2) / 4, all 128 columns of
+    // every tile, read as two tcgen05.ld of 64 columns; one load is always in flight while the previous one is folded =====
+    const int quarter = warp & 3, mb = (warp - 2) >> 2;
+    const int NONE = (int)0x80000000;
+    uint32_t acc_it = 0;                                  // tiles of this warp's query block folded so far
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int p, m0, nq, nt, mbs, ntiles;
+      item_shape(item, p, m0, nq, nt, mbs, ntiles);
+      if (mbs == 0) continue;
+      const int row = m0 + mb * MT_M + quarter * 32 + lane;
+      if (mbs < 0) {                                      // no train descriptors
+        if (row < nq) out[(size_t)p * out_stride + row] = orb_match{-1, 0x7fffffff, -1, 0x7fffffff};
+        continue;
+      }
+      int g1 = 0x7fffffff, g2 = 0x7fffffff;               // two smallest global keys: distance << 14 | train index
+      int a1 = NONE, a2 = NONE, b1 = NONE, b2 = NONE;     // two largest accumulators of the tile, even / odd columns
+      auto fold = [&](const int (&v)[64], int nvalid) {
+        if (nvalid >= 64) {
 #pragma unroll
-        for (int i = 0; i < 64; i++) {
-          const int key = kb + i - v[i] * 8192;
-          k2 = min(k2, max(k1, key));
-          k1 = min(k1, key);
+          for (int i = 0; i < 64; i += 2) {
+            a2 = max(a2, min(a1, v[i]));
+            a1 = max(a1, v[i]);
+            b2 = max(b2, min(b1, v[i + 1]));
+            b1 = max(b1, v[i + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            const int x = i < nvalid ? v[i] : NONE, y = i + 1 < nvalid ? v[i + 1] : NONE;
+            a2 = max(a2, min(a1, x));
+            a1 = max(a1, x);
+            b2 = max(b2, min(b1, y));
+            b1 = max(b1, y);
+          }
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 64; i++) {
-          const int key = i < nvalid ? kb + i - v[i] * 8192 : 0x7fffffff;
-          k2 = min(k2, max(k1, key));
-          k1 = min(k1, key);
+      };
+      // acc = 64 * dot + 64 - j  ->  key = (256 - dot) / 2 * 2^14 + base + j = 2^21 + (w - j) * 128 + base + j,  w = 64 - acc
+      auto to_key = [&](int acc, int base) {
+        const int w = 64 - acc, j = w & 127;
+        return acc == NONE ? 0x7fffffff : w * 128 + ((1 << 21) + base) - j * 127;
+      };
+      auto merge_tile = [&](int base) {
+        const int t1 = max(a1, b1), t2 = max(min(a1, b1), max(a2, b2));
+        const int f1 = to_key(t1, base), f2 = to_key(t2, base);
+        g2 = min(max(g1, f1), min(g2, f2));
+        g1 = min(g1, f1);
+        a1 = a2 = b1 = b2 = NONE;
+      };
+      if (mb < mbs) {
+        const uint32_t ta0 = tmem + ((uint32_t)(quarter * 32) << 16) + 2 * mb * MT_N;
+        int va[64], vb[64];
+        mbar_wait(tfull + 2 * mb + (acc_it & 1), (acc_it >> 1) & 1);
+        tc_fence_after();
+        tmem_ld_32x64(ta0 + (acc_it & 1) * MT_N, va);
+        for (int t = 0; t < ntiles; t++, acc_it++) {
+          const int buf = acc_it & 1;
+          const int jn = min(MT_N, nt - t * MT_N);        // valid train columns of this tile
+          tmem_ld_wait(va);
+          tmem_ld_32x64(ta0 + buf * MT_N + 64, vb);
+          fold(va, jn);
+          tmem_ld_wait(vb);                               // the whole tile is in registers: the accumulator may be overwritten
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty + 2 * mb + buf);
+          if (t + 1 < ntiles) {
+            mbar_wait(tfull + 2 * mb + (buf ^ 1), ((acc_it + 1) >> 1) & 1);
+            tc_fence_after();
+            tmem_ld_32x64(ta0 + (buf ^ 1) * MT_N, va);
+          }
+          fold(vb, jn - 64);
+          merge_tile(t * MT_N);
+        }
+        if (row < nq) {
+          orb_match m;
+          m.idx1 = g1 == 0x7fffffff ? -1 : (g1 & (MT_MAX_INDEX - 1)); m.dist1 = g1 == 0x7fffffff ? 0x7fffffff : (g1 >> 14);
+          m.idx2 = g2 == 0x7fffffff ? -1 : (g2 & (MT_MAX_INDEX - 1)); m.dist2 = g2 == 0x7fffffff ? 0x7fffffff : (g2 >> 14);
+          out[(size_t)p * out_stride + row] = m;
         }
       }
-    };
-    for (int t = 0; t < ntiles; t++) {
-      const int st = t & 1;
-      mbar_wait(tfull + st, (t >> 1) & 1);
-      tc_fence_after();
-      const int c0 = half * 128;                          // first column of this warp inside the tile
-      const int jn = min(MT_N, nt - t * MT_N) - c0;       // valid train columns from c0 on (<= 0: nothing for this warp)
-      const uint32_t ta = tmem + ((uint32_t)(quarter * 32) << 16) + st * MT_N + c0;
-      const int kb = (256 << 13) + t * MT_N + c0;
-      int va[64], vb[64];
-      if (jn > 0) {
-        tmem_ld_32x64(ta, va);
-        tmem_ld_wait();
-        if (jn > 64) tmem_ld_32x64(ta + 64, vb);          // in flight while the first 64 columns are folded
-        fold(va, kb, jn);
-        if (jn > 64) {
-          tmem_ld_wait();
-          fold(vb, kb + 64, jn - 64);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty + st);
-    }
-    // the two column halves of a row meet in shared memory
-    int* s_merge = (int*)(bars + 16);
-    const int r = quarter * 32 + lane;
-    if (half == 1) { s_merge[2 * r] = k1; s_merge[2 * r + 1] = k2; }
-    asm volatile("bar.sync 1, %0;" ::"r"(32 * MT_EPI_WARPS) : "memory");
-    if (half == 0 && m0 + r < nq) {
-      const int b1 = s_merge[2 * r], b2 = s_merge[2 * r + 1];
-      const int m1 = min(k1, b1), m2 = min(max(k1, b1), min(k2, b2));
-      orb_match m;
-      m.idx1 = m1 == 0x7fffffff ? -1 : (m1 & (MT_MAX_INDEX - 1)); m.dist1 = m1 == 0x7fffffff ? 0x7fffffff : (m1 >> 14);
-      m.idx2 = m2 == 0x7fffffff ? -1 : (m2 & (MT_MAX_INDEX - 1)); m.dist2 = m2 == 0x7fffffff ? 0x7fffffff : (m2 >> 14);
-      out[(size_t)p * out_stride + m0 + r] = m;
     }
   }
   tc_fence_before();
