@@ -23,6 +23,14 @@
 #include "../../include/orb_b200.h"
 #include "orb_kernels.cuh"
 
+#ifndef ORB_MT_FP8
+#define ORB_MT_FP8 1   // 1: operands as FP8 (E4M3) into FP32 accumulators, 0: INT8 into INT32 (half the tensor-core rate on B200)
+#endif
+
+#ifndef ORB_MT_PROBE
+#define ORB_MT_PROBE 0   // timing probes (results wrong): 1 no accumulator reads, 2 one MMA per tile, 4 train tiles loaded once, 8 issuer does not wait for the epilogue
+#endif
+
 namespace orbk {
 
 constexpr int MT_M = 128, MT_N = 128, MT_KB = 256;          // rows of a query block, train descriptors per tile, bytes per descriptor
@@ -50,7 +58,11 @@ __global__ void k_match_expand(const orb_descriptor* __restrict__ desc, const in
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const uint32_t s = (((bits >> (4 * q)) & 0xfu) * 0x00204081u) & 0x01010101u;   // bit b of the nibble -> byte b (0 / 1)
+#if ORB_MT_FP8
+      w[q] = 0xd0d0d0d0u ^ (s * 0x80u);                                               // 1 -> 0x50 (+8.0 in E4M3), 0 -> 0xd0 (-8.0)
+#else
       w[q] = 0xf8f8f8f8u ^ (s * 0xf0u);                                               // 1 -> 0x08 (+8), 0 -> 0xf8 (-8)
+#endif
     }
     v = make_uint4(w[0], w[1], w[2], w[3]);
   }
@@ -63,27 +75,61 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
-// 2-D box (128 bytes x rows) of a 3-D tensor map -> shared memory (128-byte swizzle)
+// 2-D box (128 bytes x rows) of a 3-D tensor map -> shared memory (128-byte swizzle), issued by one elected lane
 __device__ __forceinline__ void tma_load_rows(void* dst, const CUtensorMap* map, uint64_t* bar, int k_byte, int row, int set) {
-  tma_load_3d(dst, map, bar, k_byte, row, set);
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+               "@e cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}\n" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(k_byte), "r"(row), "r"(set)
+               : "memory");
 }
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3fff) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
 }
-// instruction descriptor, kind::i8: D = S32, A = B = signed int8, both K-major, N at [17,23) (>> 3), M at [24,29) (>> 4)
+// instruction descriptor (cute::UMMA::InstrDescriptor): D format at [4,6), A at [7,10), B at [10,13), both K-major, N >> 3 at
+// [17,23), M >> 4 at [24,29).  kind::f8f6f4: D = F32 (1), A = B = E4M3 (0);  kind::i8: D = S32 (2), A = B = signed int8 (1)
+#if ORB_MT_FP8
+constexpr uint32_t MT_IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(MT_N >> 3) << 17) | ((uint32_t)(MT_M >> 4) << 24);
+#define ORB_MT_KIND "kind::f8f6f4"
+#else
 constexpr uint32_t MT_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MT_N >> 3) << 17) | ((uint32_t)(MT_M >> 4) << 24);
+#define ORB_MT_KIND "kind::i8"
+#endif
+// a small integer (|n| <= 15, or a power of two up to 256) as E4M3: 1 sign, 4 exponent (bias 7), 3 mantissa bits
+__device__ __forceinline__ uint32_t e4m3_of_int(int n) {
+  if (n == 0) return 0;
+  const uint32_t sgn = n < 0 ? 0x80u : 0u, a = (uint32_t)abs(n);
+  const int e = 31 - __clz(a);
+  return sgn | ((uint32_t)(e + 7) << 3) | (((a << 3) >> e) & 7u);
+}
 
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+// The producer and issuer warps run their loops CONVERGED and one elected lane executes the asynchronous instruction inside
+// the asm: addresses, descriptors and coordinates are then warp-uniform for the compiler and stay in uniform registers (issued
+// from inside `if (lane == 0)` every UTCxMMA / UTMALDG is wrapped in a R2UR.BROADCAST loop of ~18 instructions, and that
+// single-thread instruction stream, not the tensor pipe, set the pace: ~72 clk per MMA).
+__device__ __forceinline__ void umma_8bit(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
+      "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1." ORB_MT_KIND " [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
       "l"(a_desc), "l"(b_desc), "r"(MT_IDESC), "r"(accumulate), "r"(0u)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+               "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_elect(uint64_t* b, uint32_t bytes) {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n" ::"r"(
+                   smem_u32(b)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_elect(uint64_t* b) {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}\n" ::"r"(smem_u32(b))
+               : "memory");
 }
 // 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread i of the warp = TMEM lane base + i)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, int (&v)[32]) {
@@ -159,7 +205,17 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* _
   for (int i = threadIdx.x; i < (MT_M + MT_N) * 8; i += MT_THREADS) {
     const int r = i >> 3, c = i & 7;
     uint4 v = make_uint4(0, 0, 0, 0);
+#if ORB_MT_FP8
+    // 64 - j + 32768 as three E4M3 products: 1 * -(j & 15) + 16 * (4 - (j >> 4)) + 128 * 256; the offset keeps every
+    // accumulator a positive float, whose bit pattern orders like the value
+    if (c == 0) {
+      const int j = r - MT_M;
+      v.x = r < MT_M ? (e4m3_of_int(1) | e4m3_of_int(16) << 8 | e4m3_of_int(128) << 16)
+                     : (e4m3_of_int(-(j & 15)) | e4m3_of_int(4 - (j >> 4)) << 8 | e4m3_of_int(256) << 16);
+    }
+#else
     if (c == 0) v.x = r < MT_M ? 0xffu : (uint32_t)((r - MT_M - 64) & 0xff);   // queries: -1, train column j: j - 64
+#endif
     const int rr = r < MT_M ? r : r - MT_M;
     *(uint4*)((r < MT_M ? s_ax : s_bx) + rr * 128 + ((c ^ (rr & 7)) << 4)) = v;
   }
@@ -181,13 +237,16 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* _
   };
 
   if (warp == 0) {
-    if (lane == 0) {                                      // ===== TMA producer =====
+    {                                                     // ===== TMA producer (whole warp, converged) =====
       uint32_t b_it = 0, a_it = 0;                        // tiles / items loaded so far (ring position and phase)
       auto load_b = [&](int p, int t) {
         const int st = b_it % MT_STAGES;
         mbar_wait(bempty + st, ((b_it / MT_STAGES) & 1) ^ 1);   // the MMAs that read this stage have finished
         uint8_t* b = s_b + st * MT_B_BYTES;
-        mbar_expect_tx(bfull + st, MT_B_BYTES);
+#if ORB_MT_PROBE & 4
+        if (b_it >= MT_STAGES) { mbar_arrive_elect(bfull + st); b_it++; return; }
+#endif
+        mbar_expect_tx_elect(bfull + st, MT_B_BYTES);
         tma_load_rows(b, maps + 1, bfull + st, 0, t * MT_N, p);
         tma_load_rows(b + MT_SLAB_B, maps + 1, bfull + st, 128, t * MT_N, p);
         b_it++;
@@ -201,21 +260,22 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* _
         for (int mb = 0; mb < mbs; mb++) {
           mbar_wait(aempty + mb, (a_it & 1) ^ 1);         // the previous item's MMAs on this block have finished
           uint8_t* a = s_a + mb * MT_A_BYTES;
-          mbar_expect_tx(afull + mb, MT_A_BYTES);
+          mbar_expect_tx_elect(afull + mb, MT_A_BYTES);
           tma_load_rows(a, maps + 0, afull + mb, 0, m0 + mb * MT_M, p);
           tma_load_rows(a + MT_SLAB_A, maps + 0, afull + mb, 128, m0 + mb * MT_M, p);
         }
         for (int mb = mbs; mb < MT_MB; mb++) {            // unused block: keep its barriers in step
           mbar_wait(aempty + mb, (a_it & 1) ^ 1);
-          mbar_arrive(afull + mb);
+          mbar_arrive_elect(afull + mb);
         }
         a_it++;
         for (int t = pre; t < ntiles; t++) load_b(p, t);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {                                      // ===== MMA issuer =====
+    {                                                     // ===== MMA issuer (whole warp, converged) =====
       const uint64_t ax = umma_desc_k_sw128(smem_u32(s_ax)), bx = umma_desc_k_sw128(smem_u32(s_bx));
+      const uint64_t a_desc0 = umma_desc_k_sw128(smem_u32(s_a)), b_desc0 = umma_desc_k_sw128(smem_u32(s_b));
       uint32_t b_it = 0, a_it = 0, acc_cnt[MT_MB] = {};   // tiles landed / items started / tiles multiplied per query block
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         int p, m0, nq, nt, mbs, ntiles;
@@ -224,21 +284,30 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* _
         for (int t = 0; t < ntiles; t++, b_it++) {
           const int st = b_it % MT_STAGES;
           mbar_wait(bfull + st, (b_it / MT_STAGES) & 1);  // the tile has landed
-          const uint32_t b0 = smem_u32(s_b + st * MT_B_BYTES);
+          const uint64_t b_desc = b_desc0 + (uint64_t)((st * MT_B_BYTES) >> 4);   // the address field counts 16-byte units
           for (int mb = 0; mb < MT_MB; mb++) {
             if (t == 0) mbar_wait(afull + mb, a_it & 1);
             if (mb < mbs) {
               const int buf = acc_cnt[mb] & 1;
+#if !(ORB_MT_PROBE & 8)
               mbar_wait(tempty + 2 * mb + buf, ((acc_cnt[mb] >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+#endif
+#if !(ORB_MT_PROBE & 16)
               tc_fence_after();
-              const uint32_t a0 = smem_u32(s_a + mb * MT_A_BYTES), d = tmem + (2 * mb + buf) * MT_N;
+#endif
+              const uint64_t a_desc = a_desc0 + (uint64_t)((mb * MT_A_BYTES) >> 4);
+              const uint32_t d = (ORB_MT_PROBE & 64) ? tmem : tmem + (2 * mb + buf) * MT_N;
 #pragma unroll
-              for (int ks = 0; ks < 8; ks++) {            // K = 256 bytes = 8 x 32; 4 steps per 128-byte slab
-                const uint32_t ao = a0 + (ks >> 2) * MT_SLAB_A + (ks & 3) * 32, bo = b0 + (ks >> 2) * MT_SLAB_B + (ks & 3) * 32;
-                umma_i8(d, umma_desc_k_sw128(ao), umma_desc_k_sw128(bo), ks > 0);
+              for (int ks = 0; ks < ((ORB_MT_PROBE & 2) ? 1 : 8); ks++) {   // K = 256 bytes = 8 x 32; 4 steps per 128-byte slab
+                umma_8bit(d, a_desc + (uint64_t)(((ks >> 2) * MT_SLAB_A + (ks & 3) * 32) >> 4),
+                          b_desc + (uint64_t)(((ks >> 2) * MT_SLAB_B + (ks & 3) * 32) >> 4), ks > 0);
               }
-              umma_i8(d, ax, bx, 1);                      // + 64 - column
+              umma_8bit(d, ax, bx, 1);                      // + 64 - column
+#if !(ORB_MT_PROBE & 32)
               umma_commit(tfull + 2 * mb + buf);          // accumulator ready
+#else
+              if (t == ntiles - 1) umma_commit(tfull + 2 * mb + buf);
+#endif
               acc_cnt[mb]++;
             }
             if (t == ntiles - 1) umma_commit(aempty + mb);   // the query block may be replaced once everything issued so far is done
@@ -252,9 +321,13 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* _
     // ===== epilogue: warp w owns TMEM lanes 32 * (w % 4) .. + 31 = query rows of block mb = (w - 2) / 4, all 128 columns of
     // every tile, read as two tcgen05.ld of 64 columns; one load is always in flight while the previous one is folded =====
     const int quarter = warp & 3, mb = (warp - 2) >> 2;
+#if ORB_MT_FP8
+    const int NONE = 0;                                   // below the bits of any accumulator (all are positive floats)
+#else
     const int NONE = (int)0x80000000;
+#endif
     uint32_t acc_it = 0;                                  // tiles of this warp's query block folded so far
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = (ORB_MT_PROBE & 32) ? n_items : blockIdx.x; item < n_items; item += gridDim.x) {
       int p, m0, nq, nt, mbs, ntiles;
       item_shape(item, p, m0, nq, nt, mbs, ntiles);
       if (mbs == 0) continue;
@@ -287,7 +360,11 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* _
       };
       // acc = 64 * dot + 64 - j  ->  key = (256 - dot) / 2 * 2^14 + base + j = 2^21 + (w - j) * 128 + base + j,  w = 64 - acc
       auto to_key = [&](int acc, int base) {
+#if ORB_MT_FP8
+        const int w = (64 + 32768) - __float2int_rn(__int_as_float(acc)), j = w & 127;
+#else
         const int w = 64 - acc, j = w & 127;
+#endif
         return acc == NONE ? 0x7fffffff : w * 128 + ((1 << 21) + base) - j * 127;
       };
       auto merge_tile = [&](int base) {
@@ -302,10 +379,18 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* _
         int va[64], vb[64];
         mbar_wait(tfull + 2 * mb + (acc_it & 1), (acc_it >> 1) & 1);
         tc_fence_after();
+#if !(ORB_MT_PROBE & 1)
         tmem_ld_32x64(ta0 + (acc_it & 1) * MT_N, va);
+#endif
         for (int t = 0; t < ntiles; t++, acc_it++) {
           const int buf = acc_it & 1;
           const int jn = min(MT_N, nt - t * MT_N);        // valid train columns of this tile
+#if ORB_MT_PROBE & 1
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty + 2 * mb + buf);
+          if (t + 1 < ntiles) mbar_wait(tfull + 2 * mb + (buf ^ 1), ((acc_it + 1) >> 1) & 1);
+          continue;
+#endif
           tmem_ld_wait(va);
           tmem_ld_32x64(ta0 + buf * MT_N + 64, vb);
           fold(va, jn);
