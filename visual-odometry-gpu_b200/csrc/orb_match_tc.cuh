@@ -23,10 +23,6 @@
 #include "../../include/orb_b200.h"
 #include "orb_kernels.cuh"
 
-#ifndef ORB_MT_FP8
-#define ORB_MT_FP8 1   // 1: operands as FP8 (E4M3) into FP32 accumulators, 0: INT8 into INT32 (half the tensor-core rate on B200)
-#endif
-
 #ifndef ORB_MT_PROBE
 #define ORB_MT_PROBE 0   // timing probes (results wrong): 1 no accumulator reads, 2 one MMA per tile, 4 train tiles loaded once, 8 issuer does not wait for the epilogue
 #endif
@@ -58,11 +54,7 @@ __global__ void k_match_expand(const orb_descriptor* __restrict__ desc, const in
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const uint32_t s = (((bits >> (4 * q)) & 0xfu) * 0x00204081u) & 0x01010101u;   // bit b of the nibble -> byte b (0 / 1)
-#if ORB_MT_FP8
-      w[q] = 0xd0d0d0d0u ^ (s * 0x80u);                                               // 1 -> 0x50 (+8.0 in E4M3), 0 -> 0xd0 (-8.0)
-#else
       w[q] = 0xf8f8f8f8u ^ (s * 0xf0u);                                               // 1 -> 0x08 (+8), 0 -> 0xf8 (-8)
-#endif
     }
     v = make_uint4(w[0], w[1], w[2], w[3]);
   }
@@ -88,23 +80,11 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3fff) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): D format at [4,6), A at [7,10), B at [10,13), both K-major, N >> 3 at
-// [17,23), M >> 4 at [24,29).  kind::f8f6f4: D = F32 (1), A = B = E4M3 (0);  kind::i8: D = S32 (2), A = B = signed int8 (1)
-#if ORB_MT_FP8
-constexpr uint32_t MT_IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(MT_N >> 3) << 17) | ((uint32_t)(MT_M >> 4) << 24);
-#define ORB_MT_KIND "kind::f8f6f4"
-#else
+// instruction descriptor (cute::UMMA::InstrDescriptor), kind::i8: D = S32 (2) at [4,6), A = B = signed int8 (1) at [7,10) and
+// [10,13), both K-major, N >> 3 at [17,23), M >> 4 at [24,29).  (kind::f8f6f4 with E4M3 operands and FP32 accumulators is
+// exact here too and was measured: no faster, and its accumulators do not fit the 16-bit packed read of the epilogue.)
 constexpr uint32_t MT_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MT_N >> 3) << 17) | ((uint32_t)(MT_M >> 4) << 24);
 #define ORB_MT_KIND "kind::i8"
-#endif
-// a small integer (|n| <= 15, or a power of two up to 256) as E4M3: 1 sign, 4 exponent (bias 7), 3 mantissa bits
-__device__ __forceinline__ uint32_t e4m3_of_int(int n) {
-  if (n == 0) return 0;
-  const uint32_t sgn = n < 0 ? 0x80u : 0u, a = (uint32_t)abs(n);
-  const int e = 31 - __clz(a);
-  return sgn | ((uint32_t)(e + 7) << 3) | (((a << 3) >> e) & 7u);
-}
-
 // The producer and issuer warps run their loops CONVERGED and one elected lane executes the asynchronous instruction inside
 // the asm: addresses, descriptors and coordinates are then warp-uniform for the compiler and stay in uniform registers (issued
 // from inside `if (lane == 0)` every UTCxMMA / UTMALDG is wrapped in a R2UR.BROADCAST loop of ~18 instructions, and that
@@ -205,17 +185,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* _
   for (int i = threadIdx.x; i < (MT_M + MT_N) * 8; i += MT_THREADS) {
     const int r = i >> 3, c = i & 7;
     uint4 v = make_uint4(0, 0, 0, 0);
-#if ORB_MT_FP8
-    // 64 - j + 32768 as three E4M3 products: 1 * -(j & 15) + 16 * (4 - (j >> 4)) + 128 * 256; the offset keeps every
-    // accumulator a positive float, whose bit pattern orders like the value
-    if (c == 0) {
-      const int j = r - MT_M;
-      v.x = r < MT_M ? (e4m3_of_int(1) | e4m3_of_int(16) << 8 | e4m3_of_int(128) << 16)
-                     : (e4m3_of_int(-(j & 15)) | e4m3_of_int(4 - (j >> 4)) << 8 | e4m3_of_int(256) << 16);
-    }
-#else
     if (c == 0) v.x = r < MT_M ? 0xffu : (uint32_t)((r - MT_M - 64) & 0xff);   // queries: -1, train column j: j - 64
-#endif
     const int rr = r < MT_M ? r : r - MT_M;
     *(uint4*)((r < MT_M ? s_ax : s_bx) + rr * 128 + ((c ^ (rr & 7)) << 4)) = v;
   }
@@ -318,14 +288,13 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* _
       }
     }
   } else {
-    // ===== epilogue: warp w owns TMEM lanes 32 * (w % 4) .. + 31 = query rows of block mb = (w - 2) / 4, all 128 columns of
-    // every tile, read as two tcgen05.ld of 64 columns; one load is always in flight while the previous one is folded =====
+    // ===== epilogue: warp w owns TMEM lanes 32 * (w % 4) .. + 31 = query rows of block mb = (w - 2) / 4 and all 128 columns
+    // of every tile.  An accumulator fits 16 bits (|64 * dot + 64 - j| <= 16448), so ONE tcgen05.ld.pack::16b brings a whole
+    // tile row as 64 registers of two columns each, and the two best are kept per 16-bit half with packed min / max (1.5
+    // instructions per distance); as every value carries its own column, the halves are simply compared at the end of the
+    // tile.  The next tile's load is in flight while the current one is folded. =====
     const int quarter = warp & 3, mb = (warp - 2) >> 2;
-#if ORB_MT_FP8
-    const int NONE = 0;                                   // below the bits of any accumulator (all are positive floats)
-#else
-    const int NONE = (int)0x80000000;
-#endif
+    const uint32_t NONE2 = 0x80008000u;                   // -32768 | -32768: below any accumulator
     uint32_t acc_it = 0;                                  // tiles of this warp's query block folded so far
     for (int item = (ORB_MT_PROBE & 32) ? n_items : blockIdx.x; item < n_items; item += gridDim.x) {
       int p, m0, nq, nt, mbs, ntiles;
@@ -336,82 +305,73 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* _
         if (row < nq) out[(size_t)p * out_stride + row] = orb_match{-1, 0x7fffffff, -1, 0x7fffffff};
         continue;
       }
+      if (mb >= mbs) continue;
       int g1 = 0x7fffffff, g2 = 0x7fffffff;               // two smallest global keys: distance << 14 | train index
-      int a1 = NONE, a2 = NONE, b1 = NONE, b2 = NONE;     // two largest accumulators of the tile, even / odd columns
-      auto fold = [&](const int (&v)[64], int nvalid) {
-        if (nvalid >= 64) {
-#pragma unroll
-          for (int i = 0; i < 64; i += 2) {
-            a2 = max(a2, min(a1, v[i]));
-            a1 = max(a1, v[i]);
-            b2 = max(b2, min(b1, v[i + 1]));
-            b1 = max(b1, v[i + 1]);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 64; i += 2) {
-            const int x = i < nvalid ? v[i] : NONE, y = i + 1 < nvalid ? v[i + 1] : NONE;
-            a2 = max(a2, min(a1, x));
-            a1 = max(a1, x);
-            b2 = max(b2, min(b1, y));
-            b1 = max(b1, y);
-          }
-        }
-      };
       // acc = 64 * dot + 64 - j  ->  key = (256 - dot) / 2 * 2^14 + base + j = 2^21 + (w - j) * 128 + base + j,  w = 64 - acc
       auto to_key = [&](int acc, int base) {
-#if ORB_MT_FP8
-        const int w = (64 + 32768) - __float2int_rn(__int_as_float(acc)), j = w & 127;
-#else
         const int w = 64 - acc, j = w & 127;
-#endif
-        return acc == NONE ? 0x7fffffff : w * 128 + ((1 << 21) + base) - j * 127;
+        return acc == -32768 ? 0x7fffffff : w * 128 + ((1 << 21) + base) - j * 127;
       };
-      auto merge_tile = [&](int base) {
-        const int t1 = max(a1, b1), t2 = max(min(a1, b1), max(a2, b2));
-        const int f1 = to_key(t1, base), f2 = to_key(t2, base);
+      auto fold_tile = [&](const int (&v)[64], int nvalid, int base) {
+        uint32_t a1 = NONE2, a2 = NONE2, b1 = NONE2, b2 = NONE2;   // two largest per 16-bit half, even / odd registers
+        if (nvalid >= MT_N) {
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            a2 = __vmaxs2(a2, __vmins2(a1, (uint32_t)v[i]));
+            a1 = __vmaxs2(a1, (uint32_t)v[i]);
+            b2 = __vmaxs2(b2, __vmins2(b1, (uint32_t)v[i + 1]));
+            b1 = __vmaxs2(b1, (uint32_t)v[i + 1]);
+          }
+        } else {                                          // last tile of the pair: register i = columns 2 i (low half), 2 i + 1
+#pragma unroll
+          for (int i = 0; i < 64; i++) {
+            const uint32_t x = 2 * i + 1 < nvalid ? (uint32_t)v[i] : 2 * i < nvalid ? (((uint32_t)v[i] & 0xffffu) | 0x80000000u) : NONE2;
+            a2 = __vmaxs2(a2, __vmins2(a1, x));
+            a1 = __vmaxs2(a1, x);
+          }
+        }
+        const uint32_t t1 = __vmaxs2(a1, b1), t2 = __vmaxs2(__vmins2(a1, b1), __vmaxs2(a2, b2));
+        const int lo1 = (int)(short)(t1 & 0xffffu), hi1 = (int)t1 >> 16, lo2 = (int)(short)(t2 & 0xffffu), hi2 = (int)t2 >> 16;
+        const int f1 = to_key(max(lo1, hi1), base), f2 = to_key(max(min(lo1, hi1), max(lo2, hi2)), base);
         g2 = min(max(g1, f1), min(g2, f2));
         g1 = min(g1, f1);
-        a1 = a2 = b1 = b2 = NONE;
       };
-      if (mb < mbs) {
-        const uint32_t ta0 = tmem + ((uint32_t)(quarter * 32) << 16) + 2 * mb * MT_N;
-        int va[64], vb[64];
-        mbar_wait(tfull + 2 * mb + (acc_it & 1), (acc_it >> 1) & 1);
-        tc_fence_after();
+      const uint32_t ta0 = tmem + ((uint32_t)(quarter * 32) << 16) + 2 * mb * MT_N;
+      int va[64], vb[64];
+      // one step: the current tile's registers land, its accumulator is handed back, the next tile's load is started, and
+      // only then the current registers are folded
+      auto step = [&](int t, int (&cur)[64], int (&nxt)[64]) {
+        const int buf = acc_it & 1;
+        tmem_ld_wait(cur);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty + 2 * mb + buf);
+        if (t + 1 < ntiles) {
+          mbar_wait(tfull + 2 * mb + (buf ^ 1), ((acc_it + 1) >> 1) & 1);
+          tc_fence_after();
 #if !(ORB_MT_PROBE & 1)
-        tmem_ld_32x64(ta0 + (acc_it & 1) * MT_N, va);
+          tmem_ld_32x128_pack16(ta0 + (buf ^ 1) * MT_N, nxt);
 #endif
-        for (int t = 0; t < ntiles; t++, acc_it++) {
-          const int buf = acc_it & 1;
-          const int jn = min(MT_N, nt - t * MT_N);        // valid train columns of this tile
-#if ORB_MT_PROBE & 1
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty + 2 * mb + buf);
-          if (t + 1 < ntiles) mbar_wait(tfull + 2 * mb + (buf ^ 1), ((acc_it + 1) >> 1) & 1);
-          continue;
+        }
+#if !(ORB_MT_PROBE & 1)
+        fold_tile(cur, min(MT_N, nt - t * MT_N), t * MT_N);
 #endif
-          tmem_ld_wait(va);
-          tmem_ld_32x64(ta0 + buf * MT_N + 64, vb);
-          fold(va, jn);
-          tmem_ld_wait(vb);                               // the whole tile is in registers: the accumulator may be overwritten
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty + 2 * mb + buf);
-          if (t + 1 < ntiles) {
-            mbar_wait(tfull + 2 * mb + (buf ^ 1), ((acc_it + 1) >> 1) & 1);
-            tc_fence_after();
-            tmem_ld_32x64(ta0 + (buf ^ 1) * MT_N, va);
-          }
-          fold(vb, jn - 64);
-          merge_tile(t * MT_N);
-        }
-        if (row < nq) {
-          orb_match m;
-          m.idx1 = g1 == 0x7fffffff ? -1 : (g1 & (MT_MAX_INDEX - 1)); m.dist1 = g1 == 0x7fffffff ? 0x7fffffff : (g1 >> 14);
-          m.idx2 = g2 == 0x7fffffff ? -1 : (g2 & (MT_MAX_INDEX - 1)); m.dist2 = g2 == 0x7fffffff ? 0x7fffffff : (g2 >> 14);
-          out[(size_t)p * out_stride + row] = m;
-        }
+        acc_it++;
+      };
+      mbar_wait(tfull + 2 * mb + (acc_it & 1), (acc_it >> 1) & 1);
+      tc_fence_after();
+#if !(ORB_MT_PROBE & 1)
+      tmem_ld_32x128_pack16(ta0 + (acc_it & 1) * MT_N, va);
+#endif
+      for (int t = 0; t < ntiles; t += 2) {
+        step(t, va, vb);
+        if (t + 1 < ntiles) step(t + 1, vb, va);
+      }
+      if (row < nq) {
+        orb_match m;
+        m.idx1 = g1 == 0x7fffffff ? -1 : (g1 & (MT_MAX_INDEX - 1)); m.dist1 = g1 == 0x7fffffff ? 0x7fffffff : (g1 >> 14);
+        m.idx2 = g2 == 0x7fffffff ? -1 : (g2 & (MT_MAX_INDEX - 1)); m.dist2 = g2 == 0x7fffffff ? 0x7fffffff : (g2 >> 14);
+        out[(size_t)p * out_stride + row] = m;
       }
     }
   }
