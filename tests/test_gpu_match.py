@@ -30,7 +30,9 @@ def test_knn2_random_with_ties(V, O, ctx):
     assert np.array_equal(ctx.ratio_test(got), keep)
 
 
-@pytest.mark.parametrize("nq,nt", [(1, 0), (5, 1), (3, 2), (130, 64), (129, 65), (0, 10)])
+@pytest.mark.parametrize("nq,nt", [(1, 0), (5, 1), (3, 2), (130, 64), (129, 65), (0, 10),
+                                   # the kernel's shapes: 256 queries per work item (two blocks of 128), train tiles of 128
+                                   (128, 128), (127, 129), (256, 127), (257, 256), (255, 257), (513, 383), (700, 1)])
 def test_knn2_edge_sizes(V, O, ctx, nq, nt):
     rng = np.random.default_rng(nq * 100 + nt)
     q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
@@ -82,3 +84,31 @@ def test_match_device_resident(V, O, ctx):
         ref, _ = O.match_knn2(d[p, :n[p]], d[p + 1, :n[p + 1]])
         assert np.array_equal(m[p, :n[p]], ref)
         assert (m[p, n[p]:] == -7).all()
+
+
+def test_ragged_batch_with_empty_and_tiny_frames(V, O, ctx):
+    """Pairs of a batch whose frames hold 0, 1, 2 or a full set of descriptors: every work item of the persistent kernel sees its
+    own (query count, train count); an absent neighbour is (-1, INT32_MAX)."""
+    rng = np.random.default_rng(5)
+    cap = 300
+    n = np.array([300, 0, 129, 1, 2, 257, 300, 128], dtype=np.int32)
+    d = rng.integers(0, 256, (len(n), cap, 32), dtype=np.uint8)
+    d[6, :40] = d[5, 100:140]                       # exact matches across a pair
+    d[6, 200] = d[6, 7]                             # and a tie inside a train set
+    m = ctx.match_knn2_batch(d, n)
+    assert m.shape == (len(n) - 1, cap)
+    for p in range(len(n) - 1):
+        ref, _ = O.match_knn2(d[p, :n[p]], d[p + 1, :n[p + 1]])
+        assert np.array_equal(_as4(m[p, :n[p]]), ref.reshape(-1, 4)), p
+
+
+def test_many_pairs_walk_the_persistent_grid(V, O, ctx):
+    """More work items than SMs: each CTA walks over several items and its pipeline state carries over from one to the next."""
+    rng = np.random.default_rng(6)
+    F, cap = 80, 520                                 # 79 pairs x 3 query blocks = 237 items
+    n = rng.integers(cap - 140, cap + 1, F).astype(np.int32)
+    d = rng.integers(0, 256, (F, cap, 32), dtype=np.uint8)
+    m = ctx.match_knn2_batch(d, n)
+    for p in (0, 1, 37, 78):
+        ref, _ = O.match_knn2(d[p, :n[p]], d[p + 1, :n[p + 1]])
+        assert np.array_equal(_as4(m[p, :n[p]]), ref.reshape(-1, 4)), p

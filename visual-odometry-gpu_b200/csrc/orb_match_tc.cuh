@@ -8,12 +8,13 @@
 //   k_match_tc     : persistent, one CTA per SM walking over work items (frame pair, block of 256 query descriptors).
 //                    The item's two 128-row query blocks stay in shared memory while the train descriptors stream past in
 //                    tiles of 128 through a TMA ring (128-byte swizzle), so each train tile read from L2 serves 256 queries.
-//                    warp 0 (one lane) is the TMA producer, warp 1 (one lane) issues tcgen05.mma.kind::i8 (M 128 x N 128 x
-//                    K 32; eight per tile and query block, plus a ninth that adds the column index, see the kernel) into four
-//                    TMEM accumulators (2 query blocks x 2 buffers x 128 columns), warps 2-9 (one per TMEM lane quarter and
-//                    query block) read finished accumulators with tcgen05.ld and keep the two best per query row while the
-//                    next tile is being multiplied.  Pipeline state (barrier phases) carries over from item to item, so the
-//                    prologue of an item (query block load) overlaps the tail of the previous one.
+//                    warp 0 is the TMA producer, warp 1 issues tcgen05.mma.kind::i8 (M 128 x N 128 x K 32; eight per tile
+//                    and query block, plus a ninth that adds the column index, see the kernel) into four TMEM accumulators
+//                    (2 query blocks x 2 buffers x 128 columns) -- both warps run converged, one elected lane executes the
+//                    asynchronous instruction; warps 2-9 (one per TMEM lane quarter and query block) read finished
+//                    accumulators with tcgen05.ld.pack::16b and keep the two best per query row with packed 16-bit min / max
+//                    while the next tile is being multiplied.  Pipeline state (barrier phases) carries over from item to
+//                    item, so the prologue of an item (query block load) overlaps the tail of the previous one.
 // Ties go to the lower train index, exactly as the CPU oracle (orc_match_knn2).
 #pragma once
 #include <cuda.h>
@@ -73,6 +74,12 @@ __device__ __forceinline__ void tma_load_rows(void* dst, const CUtensorMap* map,
                "@e cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}\n" ::"r"(
                    smem_u32(dst)),
                "l"(map), "r"(smem_u32(bar)), "r"(k_byte), "r"(row), "r"(set)
+               : "memory");
+}
+// the same box, only pulled into L2 (no destination): takes the HBM latency off the next item's query load
+__device__ __forceinline__ void tma_prefetch_rows(const CUtensorMap* map, int k_byte, int row, int set) {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+               "@e cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];\n\t}\n" ::"l"(map), "r"(k_byte), "r"(row), "r"(set)
                : "memory");
 }
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
@@ -239,6 +246,14 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* _
           mbar_arrive_elect(afull + mb);
         }
         a_it++;
+        if (item + (int)gridDim.x < n_items) {            // next item's query rows -> L2 while this item is being multiplied
+          int p2, m2, nq2, nt2, mbs2, ntiles2;
+          item_shape(item + gridDim.x, p2, m2, nq2, nt2, mbs2, ntiles2);
+          for (int mb = 0; mb < mbs2; mb++) {
+            tma_prefetch_rows(maps + 0, 0, m2 + mb * MT_M, p2);
+            tma_prefetch_rows(maps + 0, 128, m2 + mb * MT_M, p2);
+          }
+        }
         for (int t = pre; t < ntiles; t++) load_b(p, t);
       }
     }
@@ -262,22 +277,16 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* _
 #if !(ORB_MT_PROBE & 8)
               mbar_wait(tempty + 2 * mb + buf, ((acc_cnt[mb] >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
 #endif
-#if !(ORB_MT_PROBE & 16)
               tc_fence_after();
-#endif
               const uint64_t a_desc = a_desc0 + (uint64_t)((mb * MT_A_BYTES) >> 4);
-              const uint32_t d = (ORB_MT_PROBE & 64) ? tmem : tmem + (2 * mb + buf) * MT_N;
+              const uint32_t d = tmem + (2 * mb + buf) * MT_N;
 #pragma unroll
               for (int ks = 0; ks < ((ORB_MT_PROBE & 2) ? 1 : 8); ks++) {   // K = 256 bytes = 8 x 32; 4 steps per 128-byte slab
                 umma_8bit(d, a_desc + (uint64_t)(((ks >> 2) * MT_SLAB_A + (ks & 3) * 32) >> 4),
                           b_desc + (uint64_t)(((ks >> 2) * MT_SLAB_B + (ks & 3) * 32) >> 4), ks > 0);
               }
               umma_8bit(d, ax, bx, 1);                      // + 64 - column
-#if !(ORB_MT_PROBE & 32)
               umma_commit(tfull + 2 * mb + buf);          // accumulator ready
-#else
-              if (t == ntiles - 1) umma_commit(tfull + 2 * mb + buf);
-#endif
               acc_cnt[mb]++;
             }
             if (t == ntiles - 1) umma_commit(aempty + mb);   // the query block may be replaced once everything issued so far is done
@@ -296,7 +305,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* _
     const int quarter = warp & 3, mb = (warp - 2) >> 2;
     const uint32_t NONE2 = 0x80008000u;                   // -32768 | -32768: below any accumulator
     uint32_t acc_it = 0;                                  // tiles of this warp's query block folded so far
-    for (int item = (ORB_MT_PROBE & 32) ? n_items : blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int p, m0, nq, nt, mbs, ntiles;
       item_shape(item, p, m0, nq, nt, mbs, ntiles);
       if (mbs == 0) continue;
