@@ -461,6 +461,20 @@ def main():
             ctx.match_knn2_batch_ptr(d_d.data_ptr(), d_n.data_ptr(), F, cap, d_m.data_ptr())
         ms_match = timed(step_match, 2, 1)[0] / 2
 
+    # tensor-core roofline of the matcher (expansion kernel included in the time): 2 * 256 operations per descriptor pair actually
+    # compared; peak = dense 8-bit rate = 2 x the measured bf16 cuBLAS rate of MEASURED_PEAKS.json (else the nominal 4500 TOP/s)
+    match_roofline = None
+    if ms_match:
+        n_host = d_n.cpu().numpy().astype(np.int64)
+        ops = 2.0 * 256.0 * float((n_host[:-1] * n_host[1:]).sum())
+        try:
+            tpeak, tsrc = 2.0 * float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]), "2 x MEASURED_PEAKS.json bf16_tflops"
+        except Exception:
+            tpeak, tsrc = 4500.0, "nominal dense INT8 / FP8"
+        tach = ops / (ms_match * 1e-3) / 1e12
+        match_roofline = {"bound": "tensor", "kernel": "k_match_expand + k_match_tc", "achieved": tach, "peak": tpeak, "unit": "TOP/s",
+                          "frac": tach / tpeak, "peak_source": tsrc}
+
     e2e_steps = max(1, args.steps // 2)
     ms_e2e, per_e2e = timed(step_e2e, e2e_steps, 2)
     assert int(h_n.sum().item()) == n_kp, "host and device paths disagree"
@@ -567,7 +581,7 @@ def main():
                    "cache_hygiene": "input batch %.0f MB > 126 MB L2; scratch arena reused per chunk" % (F * H * PITCH / 1e6),
                    "stage_names": names,
                    "stage_ms_per_step": [m / prof_steps for m in st_ms], "stage_share": stage_share,
-                   "match_knn2_ms_per_step": ms_match, "match_pairs_per_step": F - 1, "ingest_png": ingest, "lk_track": lk,
+                   "match_knn2_ms_per_step": ms_match, "match_pairs_per_step": F - 1, "match_roofline": match_roofline, "ingest_png": ingest, "lk_track": lk,
                    "pass_b_min_bytes_per_frame": b_min, "pass_hbm_gbs_per_gpu": pass_gbs, "pass_hbm_frac": pass_gbs / peak,
                    "peak_source": peak_src},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(F * H * PITCH) * world,
