@@ -474,7 +474,13 @@ int orb_create(const orb_params* p, orb_ctx** out) {
     // per wave when frames and results stay on the device, 128 when they are staged from / to the host so that the
     // copies of one wave hide behind the kernels of another (bounded by 3 GB of scratch)
     int chunk = p->chunk_frames > 0 ? p->chunk_frames : (int)std::max<size_t>(1, std::min<size_t>(512, ((size_t)3 << 30) / per_frame));
-    ctx->chunk_staged = p->chunk_frames > 0 ? p->chunk_frames : 128;
+    // host-staged waves: ~30 MB of frames each (64 KITTI frames, 14 at 1080p, 4 at 4K) -- small enough that the first wave's
+    // upload and the last wave's computation, the two parts the link cannot hide, stay short; measured on KITTI frames:
+    // 32-64 frames 107-108 k frames/s end to end, 96-128 frames 103 k, 24 frames 101 k (launch overhead)
+    ctx->chunk_staged = p->chunk_frames > 0 ? p->chunk_frames
+                                            : (int)std::max<size_t>(2, std::min<size_t>(128, (30000000 + (size_t)p->max_width * p->max_height / 2) /
+                                                                                                 ((size_t)p->max_width * p->max_height)));
+    if (const char* e = getenv("ORB_B200_STAGED_WAVE")) { const int v = atoi(e); if (v > 0) ctx->chunk_staged = v; }   // tuning knob
     ctx->chunk = std::max(1, std::min(chunk, p->max_batch));
     ctx->chunk_staged = std::max(1, std::min(ctx->chunk_staged, ctx->chunk));
     const int C = ctx->chunk, Bn = p->max_batch;
