@@ -387,7 +387,6 @@ void orb_destroy(orb_ctx* ctx) {
   if (ctx->d_scores) cudaFree(ctx->d_scores);
   for (void* q : ctx->d_scratch) if (q) cudaFree(q);
   if (ctx->d_match_exp) cudaFree(ctx->d_match_exp);
-  if (ctx->d_match_maps) cudaFree(ctx->d_match_maps);
   if (ctx->h_comp) cudaFreeHost(ctx->h_comp);
   if (ctx->h_descs) cudaFreeHost(ctx->h_descs);
   if (ctx->h_inf_status) cudaFreeHost(ctx->h_inf_status);
@@ -1042,7 +1041,6 @@ static int match_tc(orb_ctx* ctx, const orb_descriptor* dq, int rows_q, long lon
     CK(cudaMalloc(&ctx->d_match_exp, bytes_q + bytes_t + 1024));
     ctx->match_exp_bytes = bytes_q + bytes_t;
   }
-  if (!ctx->d_match_maps) CK(cudaMalloc(&ctx->d_match_maps, 2 * sizeof(CUtensorMap)));
   int8_t* eq = ctx->d_match_exp;
   int8_t* et = same_buffer ? eq + (size_t)rows_q * orbk::MT_KB : eq + bytes_q;
   orbk::k_match_expand<<<dim3((rows_q * 16 + 255) / 256, sets_q), 256, 0, ctx->stream>>>(dq, same_buffer ? dn : nullptr, rows_q, stride_q, rows_q, eq);
@@ -1057,12 +1055,11 @@ static int match_tc(orb_ctx* ctx, const orb_descriptor* dq, int rows_q, long lon
   if ((rc = encode_map(ctx, &maps[1], CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, et, orbk::MT_KB, std::max(rows_t, 1), npairs, orbk::MT_KB,
                        (size_t)std::max(same_buffer ? rows_q : rows_t, 1) * orbk::MT_KB, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B)))
     return rc;
-  CK(cudaMemcpyAsync(ctx->d_match_maps, maps, sizeof(maps), cudaMemcpyHostToDevice, ctx->stream));
   const int qblocks = (nq + orbk::MT_MB * orbk::MT_M - 1) / (orbk::MT_MB * orbk::MT_M);
   const long long n_items = (long long)qblocks * npairs;
   if (n_items > INT32_MAX) return fail(ctx, ORB_E_CAPACITY, "matcher: too many query blocks");
   const int grid = (int)std::min<long long>(n_items, ctx->sm_count);
-  orbk::k_match_tc<<<grid, orbk::MT_THREADS, orbk::MT_SMEM, ctx->stream>>>(ctx->d_match_maps, dn, nq, nt, qblocks, (int)n_items, out_stride, dout);
+  orbk::k_match_tc<<<grid, orbk::MT_THREADS, orbk::MT_SMEM, ctx->stream>>>(maps[0], maps[1], dn, nq, nt, qblocks, (int)n_items, out_stride, dout);
   CK(cudaGetLastError());
   ctx->launches += same_buffer ? 2 : 3;
   return ORB_OK;

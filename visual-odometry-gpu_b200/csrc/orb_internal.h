@@ -31,7 +31,7 @@ struct orb_ctx {
   uint8_t* d_pyr = nullptr; uint16_t* d_box = nullptr; unsigned long long* d_cand = nullptr;
   int* d_edge2 = nullptr;
   void* d_scratch[3] = {nullptr, nullptr, nullptr}; size_t scratch_bytes[3] = {0, 0, 0};   // host-buffer matcher / debug calls (grow-only)
-  int8_t* d_match_exp = nullptr; size_t match_exp_bytes = 0; CUtensorMap* d_match_maps = nullptr;   // tensor-core matcher: +-8 int8 rows, tensor maps
+  int8_t* d_match_exp = nullptr; size_t match_exp_bytes = 0;   // tensor-core matcher: +-8 int8 rows (the tensor maps travel as kernel parameters)
   int sm_count = 0;                                      // persistent kernels: one CTA per SM
   float* d_scores = nullptr; size_t d_scores_bytes = 0;   // orb_nms_scores: the caller's score map (grow-only)
   int* d_cand_count = nullptr; size_t zero_bytes_per_frame = 0; uint32_t* d_kept_xy = nullptr; float* d_kept_r = nullptr; int* d_kept_count = nullptr;

@@ -48,7 +48,7 @@ __global__ void k_match_expand(const orb_descriptor* __restrict__ desc, const in
   const int r = i >> 4, g = i & 15;
   if (r >= rows_out) return;
   uint4 v = make_uint4(0, 0, 0, 0);
-  const int nf = n ? min(n[f], rows_in) : rows_in;
+  const int nf = n ? max(0, min(n[f], rows_in)) : rows_in;
   if (r < nf) {
     const uint32_t bits = ((const uint16_t*)(desc + (size_t)f * in_stride + r))[g];
     uint32_t w[4];
@@ -152,7 +152,8 @@ __device__ __forceinline__ void tmem_ld_wait(int (&v)[64]) {
   for (int i = 0; i < 64; i++) asm volatile("" : "+r"(v[i]));
 }
 
-// grid: persistent (<= SM count).  maps[0]: query rows, maps[1]: train rows (3-D: 256 bytes, rows, pairs; box 128 x 128).
+// grid: persistent (<= SM count).  map_q: query rows, map_t: train rows (3-D: 256 bytes, rows, pairs; box 128 x 128), passed as
+// kernel parameters (no device copy of the descriptors, no copy to wait for).
 // n_arr != nullptr: pair p matches the n_arr[p] descriptors of frame p against the n_arr[p + 1] of frame p + 1.
 // Work item i = (pair i / qblocks, query rows 256 * (i % qblocks) ..).
 //
@@ -161,7 +162,8 @@ __device__ __forceinline__ void tmem_ld_wait(int (&v)[64]) {
 // 64 - column:   acc = 64 * dot + 64 - column,   larger = nearer, ties to the lower column,
 // which the epilogue folds with three integer min / max per distance; tiles are merged in order into global keys
 // distance * 2^14 + index (smaller = nearer), so an equal distance in a later tile never displaces an earlier one.
-__global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* __restrict__ maps, const int* __restrict__ n_arr, int nq_fixed,
+__global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
+                                                            const int* __restrict__ n_arr, int nq_fixed,
                                                             int nt_fixed, int qblocks, int n_items, long long out_stride,
                                                             orb_match* __restrict__ out) {
   extern __shared__ uint8_t mt_smem_raw[];
@@ -206,8 +208,8 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* _
   auto item_shape = [&](int item, int& p, int& m0, int& nq, int& nt, int& mbs, int& ntiles) {
     p = item / qblocks;
     m0 = (item - p * qblocks) * (MT_MB * MT_M);
-    nq = n_arr ? n_arr[p] : nq_fixed;
-    nt = n_arr ? n_arr[p + 1] : nt_fixed;
+    nq = n_arr ? max(0, min(n_arr[p], nq_fixed)) : nq_fixed;        // counts beyond the capacity of a set are clipped, as in k_match_expand
+    nt = n_arr ? max(0, min(n_arr[p + 1], nt_fixed)) : nt_fixed;
     ntiles = (nt + MT_N - 1) / MT_N;
     mbs = nq <= m0 ? 0 : min(MT_MB, (nq - m0 + MT_M - 1) / MT_M);
     if (ntiles == 0) mbs = -mbs;                          // nothing to multiply: the epilogue still writes "no neighbour"
@@ -224,8 +226,8 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* _
         if (b_it >= MT_STAGES) { mbar_arrive_elect(bfull + st); b_it++; return; }
 #endif
         mbar_expect_tx_elect(bfull + st, MT_B_BYTES);
-        tma_load_rows(b, maps + 1, bfull + st, 0, t * MT_N, p);
-        tma_load_rows(b + MT_SLAB_B, maps + 1, bfull + st, 128, t * MT_N, p);
+        tma_load_rows(b, &map_t, bfull + st, 0, t * MT_N, p);
+        tma_load_rows(b + MT_SLAB_B, &map_t, bfull + st, 128, t * MT_N, p);
         b_it++;
       };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -238,8 +240,8 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* _
           mbar_wait(aempty + mb, (a_it & 1) ^ 1);         // the previous item's MMAs on this block have finished
           uint8_t* a = s_a + mb * MT_A_BYTES;
           mbar_expect_tx_elect(afull + mb, MT_A_BYTES);
-          tma_load_rows(a, maps + 0, afull + mb, 0, m0 + mb * MT_M, p);
-          tma_load_rows(a + MT_SLAB_A, maps + 0, afull + mb, 128, m0 + mb * MT_M, p);
+          tma_load_rows(a, &map_q, afull + mb, 0, m0 + mb * MT_M, p);
+          tma_load_rows(a + MT_SLAB_A, &map_q, afull + mb, 128, m0 + mb * MT_M, p);
         }
         for (int mb = mbs; mb < MT_MB; mb++) {            // unused block: keep its barriers in step
           mbar_wait(aempty + mb, (a_it & 1) ^ 1);
@@ -250,8 +252,8 @@ __global__ void __launch_bounds__(MT_THREADS, 1) k_match_tc(const CUtensorMap* _
           int p2, m2, nq2, nt2, mbs2, ntiles2;
           item_shape(item + gridDim.x, p2, m2, nq2, nt2, mbs2, ntiles2);
           for (int mb = 0; mb < mbs2; mb++) {
-            tma_prefetch_rows(maps + 0, 0, m2 + mb * MT_M, p2);
-            tma_prefetch_rows(maps + 0, 128, m2 + mb * MT_M, p2);
+            tma_prefetch_rows(&map_q, 0, m2 + mb * MT_M, p2);
+            tma_prefetch_rows(&map_q, 128, m2 + mb * MT_M, p2);
           }
         }
         for (int t = pre; t < ntiles; t++) load_b(p, t);
