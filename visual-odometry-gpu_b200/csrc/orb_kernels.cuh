@@ -320,9 +320,13 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
       const uint32_t t0 = prmt(__ldg(q0), __ldg(q0 + 1), sel), t1 = prmt(__ldg(q1), __ldg(q1 + 1), sel);
       const int h0a = (int)__dp2a_lo(xa0, t0, 0u), h0b = (int)__dp2a_hi(xa1, t0, 0u);
       const int h1a = (int)__dp2a_lo(xa0, t1, 0u), h1b = (int)__dp2a_hi(xa1, t1, 0u);
-      const int va = ((((int)ty.z * (h0a >> 4)) >> 16) + (((int)ty.w * (h1a >> 4)) >> 16) + 2) >> 2;
-      const int vb = ((((int)ty.z * (h0b >> 4)) >> 16) + (((int)ty.w * (h1b >> 4)) >> 16) + 2) >> 2;
-      *(uint16_t*)(s_res + ry * A_RP + col) = (uint16_t)(va | (vb << 8));   // va, vb <= 255 (see resize_column)
+      // (b0 * (h0 >> 4) >> 16) + (b1 * (h1 >> 4) >> 16) + 2 >> 2 for both columns in 16-bit lanes: the products are < 2^27, so
+      // one byte permute takes ">> 16" of two of them at once, the lane sums stay < 2^13, and the two bits the final shift
+      // drags from the upper lane land above the result byte (va, vb <= 255, see resize_column)
+      const uint32_t pa0 = (uint32_t)((int)ty.z * (h0a >> 4)), pa1 = (uint32_t)((int)ty.w * (h1a >> 4));
+      const uint32_t pb0 = (uint32_t)((int)ty.z * (h0b >> 4)), pb1 = (uint32_t)((int)ty.w * (h1b >> 4));
+      const uint32_t v2 = (prmt(pa0, pb0, 0x7632) + prmt(pa1, pb1, 0x7632) + 0x00020002u) >> 2;
+      *(uint16_t*)(s_res + ry * A_RP + col) = (uint16_t)prmt(v2, 0u, 0x4420);
     }
   };
   if (P.W <= 3 * w) {
