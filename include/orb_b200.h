@@ -209,6 +209,14 @@ int  orb_get_ingested_frame(orb_ctx* ctx, int frame, uint8_t* dst, size_t dst_pi
 int  orb_lk_track(orb_ctx* ctx, const uint8_t* prev, const uint8_t* next, int w, int h, size_t pitch, const float* prev_pts,
                   int n, int win, int max_level, int max_iter, double eps, float min_eig, float* next_pts, uint8_t* status,
                   float* err);
+/* The same for a batch whose frames stay on the device (the VO loop of reference src/feature_tracking.cpp:160-225 run over a
+ * sequence): frame t is tracked into frame t + 1, t = 0 .. n_frames - 2, every pyramid built once, one launch for all points.
+ * prev_pts / next_pts [n_frames - 1][cap][2], status / err [n_frames - 1][cap]; n_pts [n_frames - 1] (NULL: cap points in every
+ * pair) -- all in device memory if pts_on_device, else in host memory (results are then complete on return; with device
+ * pointers the call is asynchronous on the context's stream).  Entries beyond a pair's count are left untouched. */
+int  orb_lk_track_batch(orb_ctx* ctx, const uint8_t* frames, int frames_on_device, int n_frames, int w, int h, size_t pitch,
+                        size_t frame_stride, const float* prev_pts, const int* n_pts, int cap, int pts_on_device, int win,
+                        int max_level, int max_iter, double eps, float min_eig, float* next_pts, uint8_t* status, float* err);
 /* highest pyramid level index the tracker uses for this frame size (OpenCV stops before a level <= the window) */
 int  orb_lk_levels(int w, int h, int win, int max_level);
 /* pyramid level of the last orb_lk_track call (which: 0 = prev, 1 = next), packed rows; size returned in w, h */

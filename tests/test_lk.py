@@ -170,3 +170,60 @@ def test_vo_front_end_chain_is_consistent():
         assert np.median(d) < 1.5 and (d < 4).mean() > 0.8, (np.median(d), (d < 4).mean())
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_batch_tracker_is_the_single_pair_tracker(O):
+    """orb_lk_track_batch: frame t into frame t + 1 over a sequence, every pyramid built once, one launch for all points.  Host
+    form against the checker pair by pair (ragged point counts, one empty pair), then the device-resident form (frames with a
+    row pitch, points and results in device memory) against the host form, bit for bit."""
+    import torch
+    a, b = kitti_pair()
+    rng = np.random.default_rng(11)
+    frames = np.stack([a, b, np.roll(b, (1, -2), (0, 1)), a, rng.integers(0, 256, a.shape, dtype=np.uint8)])
+    F, h, w = frames.shape
+    cap = 700
+    pts = np.zeros((F - 1, cap, 2), np.float32)
+    n = np.array([700, 650, 0, 11], np.int32)
+    for p in range(F - 1):
+        base = fast_points(frames[p], cap)
+        q = np.concatenate([border_points(w, h), base])[:cap]
+        pts[p, :len(q)] = q
+        n[p] = min(n[p], len(q))
+    ctx = orb.Context(orb.make_params(nfeatures=500, max_width=1241, max_height=376, max_batch=F))
+    try:
+        for cfg in (CRIT, dict(win=9, max_level=0, max_iter=30, eps=0.01, min_eig=0.001)):
+            n1, st1, er1 = ctx.lk_track_batch(frames, pts, n, **cfg)
+            for p in range(F - 1):
+                m = n[p]
+                n2, st2, er2 = O.lk_track(frames[p], frames[p + 1], pts[p, :m], **cfg)
+                assert np.array_equal(st1[p, :m], st2), p
+                assert np.array_equal(n1[p, :m].view(np.uint32), n2.view(np.uint32)), p
+                assert np.array_equal(er1[p, :m].view(np.uint32), er2.view(np.uint32)), p
+                assert not st1[p, m:].any()
+        # all pairs full (n_pts = None) == per-pair calls
+        n1, st1, er1 = ctx.lk_track_batch(frames[:3], pts[:2], None, **CRIT)
+        for p in range(2):
+            n2, st2, er2 = ctx.lk_track(frames[p], frames[p + 1], pts[p], **CRIT)
+            assert np.array_equal(st1[p], st2) and np.array_equal(n1[p].view(np.uint32), n2.view(np.uint32))
+        # device-resident: pitched frames, device points / counts / results
+        pitch = (w + 1 + 15) // 16 * 16
+        pf = np.zeros((F, h, pitch), np.uint8)
+        pf[:, :, :w] = frames
+        dev = torch.device("cuda", 0)
+        d_f = torch.from_numpy(pf).to(dev)
+        d_p, d_n = torch.from_numpy(pts).to(dev), torch.from_numpy(n).to(dev)
+        d_o = torch.zeros(F - 1, cap, 2, dtype=torch.float32, device=dev)
+        d_s = torch.zeros(F - 1, cap, dtype=torch.uint8, device=dev)
+        d_e = torch.zeros(F - 1, cap, dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()                         # the context works on its own stream
+        ctx.lk_track_batch_ptr(d_f.data_ptr(), F, w, h, pitch, h * pitch, d_p.data_ptr(), d_n.data_ptr(), cap, d_o.data_ptr(),
+                               d_s.data_ptr(), d_e.data_ptr(), **CRIT)
+        ctx.synchronize()
+        n1, st1, er1 = ctx.lk_track_batch(frames, pts, n, **CRIT)
+        assert np.array_equal(d_s.cpu().numpy(), st1)
+        assert np.array_equal(d_o.cpu().numpy().view(np.uint32), n1.view(np.uint32))
+        assert np.array_equal(d_e.cpu().numpy().view(np.uint32), er1.view(np.uint32))
+        assert ctx.lk_track_batch(frames[:1], np.zeros((0, cap, 2), np.float32))[0].shape == (0, cap, 2)
+    finally:
+        ctx.close()

@@ -22,8 +22,9 @@ constexpr int LK_MAX_WIN = 33;
 constexpr int LK_WARPS = 4;
 
 struct LkPyr {
-  const uint8_t* img[LK_MAX_LEVELS];   // packed levels (pitch = width)
+  const uint8_t* img[LK_MAX_LEVELS];   // levels >= 1 are packed (pitch = width); level 0 may be the caller's frame with its own pitch
   int w[LK_MAX_LEVELS], h[LK_MAX_LEVELS];
+  int pitch0;                          // row pitch of level 0
 };
 
 __device__ __forceinline__ int lk_reflect101(int p, int n) {
@@ -32,9 +33,13 @@ __device__ __forceinline__ int lk_reflect101(int p, int n) {
   return p;
 }
 
-__global__ void k_lk_pyrdown(const uint8_t* __restrict__ src, int sw, int sh, int spitch, uint8_t* __restrict__ dst, int dw, int dh) {
+// blockIdx.z = frame of a batch (src_stride / dst_stride bytes between the levels of consecutive frames; one frame: 0)
+__global__ void k_lk_pyrdown(const uint8_t* __restrict__ src, int sw, int sh, int spitch, uint8_t* __restrict__ dst, int dw, int dh,
+                             size_t src_stride, size_t dst_stride) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= dw || y >= dh) return;
+  src += (size_t)blockIdx.z * src_stride;
+  dst += (size_t)blockIdx.z * dst_stride;
   int s = 0;
 #pragma unroll
   for (int j = 0; j < 5; j++) {
@@ -67,29 +72,37 @@ __device__ __forceinline__ LkWeights lk_weights(float a, float b) {
 }
 
 // bilinear sample of the image (5 fractional bits) at integer corner (X, Y)
-__device__ __forceinline__ int lk_sample(const uint8_t* __restrict__ img, int w, int h, int X, int Y, const LkWeights& W, bool inside) {
+__device__ __forceinline__ int lk_sample(const uint8_t* __restrict__ img, int w, int h, int pitch, int X, int Y, const LkWeights& W, bool inside) {
   int p00, p01, p10, p11;
   if (inside) {
-    const uint8_t* r = img + (size_t)Y * w + X;
-    p00 = r[0]; p01 = r[1]; p10 = r[w]; p11 = r[w + 1];
+    const uint8_t* r = img + (size_t)Y * pitch + X;
+    p00 = r[0]; p01 = r[1]; p10 = r[pitch]; p11 = r[pitch + 1];
   } else {
     const int x0 = lk_reflect101(X, w), x1 = lk_reflect101(X + 1, w);
-    const uint8_t* r0 = img + (size_t)lk_reflect101(Y, h) * w;
-    const uint8_t* r1 = img + (size_t)lk_reflect101(Y + 1, h) * w;
+    const uint8_t* r0 = img + (size_t)lk_reflect101(Y, h) * pitch;
+    const uint8_t* r1 = img + (size_t)lk_reflect101(Y + 1, h) * pitch;
     p00 = r0[x0]; p01 = r0[x1]; p10 = r1[x0]; p11 = r1[x1];
   }
   return lk_descale(p00 * W.w00 + p01 * W.w01 + p10 * W.w10 + p11 * W.w11, 14 - 5);
 }
 
+// blockIdx.y = frame pair of a batch: its pyramids lie pair * pair_stride bytes (level 0: pair * pair_stride0) behind P / N, its points pair * pts_stride
+// entries behind prev_pts / next_pts / status / err, and it tracks n_arr[pair] (clipped to n) points; one pair: strides 0,
+// n_arr NULL.
 __global__ void __launch_bounds__(LK_WARPS * 32) k_lk_track(const LkPyr P, const LkPyr N, int top, const float* __restrict__ prev_pts, int n,
                                                             int win, int max_iter, double eps2, float min_eig,
                                                             float* __restrict__ next_pts, uint8_t* __restrict__ status,
-                                                            float* __restrict__ err) {
+                                                            float* __restrict__ err, size_t pair_stride0, size_t pair_stride, size_t pts_stride,
+                                                            const int* __restrict__ n_arr) {
   __shared__ short s_I[LK_WARPS][LK_MAX_WIN * LK_MAX_WIN];
   __shared__ short s_dI[LK_WARPS][2 * LK_MAX_WIN * LK_MAX_WIN];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int pt = blockIdx.x * LK_WARPS + wid;
+  if (n_arr) n = max(0, min(n, n_arr[blockIdx.y]));
   if (pt >= n) return;
+  prev_pts += 2 * (size_t)blockIdx.y * pts_stride; next_pts += 2 * (size_t)blockIdx.y * pts_stride;
+  status += (size_t)blockIdx.y * pts_stride;
+  if (err) err += (size_t)blockIdx.y * pts_stride;
   short* Iw = s_I[wid];
   short* dIw = s_dI[wid];
   const int area = win * win;
@@ -102,9 +115,10 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_lk_track(const LkPyr P, const
   const int ex0 = lane % win, ey0 = lane / win;
 
   for (int level = top; level >= 0; level--) {
-    const uint8_t* I = P.img[level];
-    const uint8_t* J = N.img[level];
-    const int w = P.w[level], h = P.h[level];
+    const size_t img_ofs = (size_t)blockIdx.y * (level == 0 ? pair_stride0 : pair_stride);
+    const uint8_t* I = P.img[level] + img_ofs;
+    const uint8_t* J = N.img[level] + img_ofs;
+    const int w = P.w[level], h = P.h[level], pitch = level == 0 ? P.pitch0 : w;
     const float sc = (float)(1. / (double)(1 << level));
     float px = __fmul_rn(p0x, sc), py = __fmul_rn(p0y, sc);
     float nx, ny;
@@ -128,7 +142,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_lk_track(const LkPyr P, const
         int p[4][4];
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-          const uint8_t* row = I + (size_t)(inside ? Y + r - 1 : lk_reflect101(Y + r - 1, h)) * w;
+          const uint8_t* row = I + (size_t)(inside ? Y + r - 1 : lk_reflect101(Y + r - 1, h)) * pitch;
 #pragma unroll
           for (int c = 0; c < 4; c++) p[r][c] = row[inside ? X + c - 1 : lk_reflect101(X + c - 1, w)];
         }
@@ -185,7 +199,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_lk_track(const LkPyr P, const
       float b1 = 0.f, b2 = 0.f;
       int x = ex0, y = ey0;
       for (int e = lane; e < area; e += 32) {
-        const int diff = lk_sample(J, w, h, inx + x, iny + y, W, inside) - Iw[e];
+        const int diff = lk_sample(J, w, h, pitch, inx + x, iny + y, W, inside) - Iw[e];
         b1 = __fadd_rn(b1, (float)(diff * dIw[2 * e]));
         b2 = __fadd_rn(b2, (float)(diff * dIw[2 * e + 1]));
         x += 32;
@@ -214,7 +228,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_lk_track(const LkPyr P, const
       float ev = 0.f;
       int x = ex0, y = ey0;
       for (int e = lane; e < area; e += 32) {
-        const int diff = lk_sample(J, w, h, inx + x, iny + y, W, inside) - Iw[e];
+        const int diff = lk_sample(J, w, h, pitch, inx + x, iny + y, W, inside) - Iw[e];
         ev = __fadd_rn(ev, fabsf((float)diff));
         x += 32;
         while (x >= win) { x -= win; y++; }

@@ -50,7 +50,7 @@ EXPORTS = [
     "orb_synchronize", "orb_detect_and_compute", "orb_detect_and_compute_batch", "orb_get_level", "orb_level_size",
     "orb_level_quota", "orb_fast_detect", "orb_nms_scores", "orb_conv2d_u8", "orb_gaussian_blur_1d", "orb_harris", "orb_orientations", "orb_brief", "orb_get_side_arrays",
     "orb_get_candidates", "orb_get_harris_weights", "orb_last_launch_count", "orb_set_profiling", "orb_get_stage_ms", "orb_match_knn2", "orb_match_knn2_batch", "orb_ratio_test", "orb_debug_eval_math", "orb_debug_bounds_check", "orb_debug_bounds_selftest", "bit_pattern_31_",
-    "orb_png_info", "orb_png_decode_gray8", "orb_imread_gray8", "orb_detect_and_compute_files", "orb_get_ingested_frame", "orb_debug_inflate", "orb_lk_track", "orb_lk_levels", "orb_lk_get_level",
+    "orb_png_info", "orb_png_decode_gray8", "orb_imread_gray8", "orb_detect_and_compute_files", "orb_get_ingested_frame", "orb_debug_inflate", "orb_lk_track", "orb_lk_track_batch", "orb_lk_levels", "orb_lk_get_level",
 ]
 
 _lib = None
@@ -109,6 +109,7 @@ def load_library():
     L.orb_get_ingested_frame.argtypes = [vp, i, vp, sz, C.POINTER(i), C.POINTER(i)]
     L.orb_debug_inflate.argtypes = [vp, vp, vp, i, vp, vp, vp]
     L.orb_lk_track.argtypes = [vp, vp, vp, i, i, sz, vp, i, i, i, i, C.c_double, C.c_float, vp, vp, vp]
+    L.orb_lk_track_batch.argtypes = [vp, vp, i, i, i, i, sz, sz, vp, vp, i, i, i, i, i, C.c_double, C.c_float, vp, vp, vp]
     L.orb_lk_levels.argtypes = [i, i, i, i]
     L.orb_lk_get_level.argtypes = [vp, i, i, vp, C.POINTER(i), C.POINTER(i)]
     _lib = L
@@ -275,6 +276,31 @@ class Context:
         self._ck(self.lib.orb_lk_track(self.h, _p(prev), _p(nxt), prev.shape[1], prev.shape[0], prev.strides[0], _p(pts),
                                        len(pts), win, max_level, max_iter, eps, min_eig, _p(out), _p(st), _p(er)))
         return out, st, er
+
+    def lk_track_batch(self, frames, pts, n_pts=None, win=21, max_level=3, max_iter=30, eps=0.01, min_eig=0.001):
+        """Frame t tracked into frame t + 1 for a whole sequence (host arrays): frames [F, h, w] uint8, pts [F-1, cap, 2] float32,
+        n_pts [F-1] (None: cap points everywhere).  Returns (next_pts [F-1, cap, 2], status [F-1, cap], err [F-1, cap])."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        F, h, w = frames.shape
+        pts = np.ascontiguousarray(pts, np.float32)
+        cap = pts.shape[1]
+        assert pts.shape == (F - 1, cap, 2)
+        n = None if n_pts is None else np.ascontiguousarray(n_pts, np.int32)
+        out = np.zeros_like(pts)
+        st = np.zeros((F - 1, cap), np.uint8)
+        er = np.zeros((F - 1, cap), np.float32)
+        self._ck(self.lib.orb_lk_track_batch(self.h, _p(frames), 0, F, w, h, frames.strides[1], frames.strides[0], _p(pts),
+                                             None if n is None else _p(n), cap, 0, win, max_level, max_iter, eps, min_eig,
+                                             _p(out), _p(st), _p(er)))
+        return out, st, er
+
+    def lk_track_batch_ptr(self, frames_ptr, n_frames, w, h, pitch, frame_stride, pts_ptr, n_ptr, cap, next_ptr, status_ptr, err_ptr,
+                           win=21, max_level=3, max_iter=30, eps=0.01, min_eig=0.001):
+        """device-resident form (asynchronous on the context's stream): frames as given to detect_and_compute_batch_ptr,
+        points / counts / results in device memory"""
+        self._ck(self.lib.orb_lk_track_batch(self.h, C.c_void_p(frames_ptr), 1, n_frames, w, h, pitch, frame_stride, C.c_void_p(pts_ptr),
+                                             C.c_void_p(n_ptr) if n_ptr else None, cap, 1, win, max_level, max_iter, eps, min_eig,
+                                             C.c_void_p(next_ptr), C.c_void_p(status_ptr), C.c_void_p(err_ptr) if err_ptr else None))
 
     def lk_get_level(self, which, level, w0, h0):
         """Pyramid level of the last lk_track call (which: 0 prev, 1 next); w0, h0 = frame size of that call."""
