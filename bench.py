@@ -510,6 +510,24 @@ def main():
             ctx_lk.close()
         except Exception as e:      # the fixture pair is optional for the headline number
             lk = {"error": str(e)}
+        # the same tracker over the whole device-resident batch: the ORB keypoints of frame t tracked into frame t + 1
+        # (frames, points and results stay on the device; every frame's pyramid is built once)
+        try:
+            if F > 1 and args.config == "kitti":
+                d_pts = d_k[:F - 1].to(torch.float32).contiguous()
+                d_nx = torch.zeros_like(d_pts)
+                d_st = torch.zeros(F - 1, cap, dtype=torch.uint8, device=dev)
+                d_er = torch.zeros(F - 1, cap, dtype=torch.float32, device=dev)
+
+                def step_lk():
+                    ctx.lk_track_batch_ptr(d_frames.data_ptr(), F, W, H, PITCH, H * PITCH, d_pts.data_ptr(), d_n.data_ptr(), cap,
+                                           d_nx.data_ptr(), d_st.data_ptr(), d_er.data_ptr())
+                ms_lk = timed(step_lk, 2, 1)[0] / 2
+                n_trk = int(d_n[:F - 1].sum().item())
+                lk = dict(lk or {}, batch={"ms_per_step": ms_lk, "pairs": F - 1, "points": n_trk, "tracked": int(d_st.sum().item()),
+                                            "pairs_per_s": (F - 1) / (ms_lk * 1e-3), "points_per_s": n_trk / (ms_lk * 1e-3)})
+        except Exception as e:
+            lk = dict(lk or {}, batch={"error": str(e)})
 
     ingest = None
     if rank == 0 and world == 1 and not args.no_ingest and args.config == "kitti":
