@@ -239,6 +239,7 @@ constexpr int A_UNROLL = ORB_A_UNROLL;             // rows of the column-pair re
 #define ORB_A_SEG 4
 #endif
 constexpr int A_SEG = ORB_A_SEG;                   // output rows per thread in the blur (4: all 256 threads, 8: 128)
+static_assert((A_TW / 8) * (A_TH / A_SEG) <= A_THREADS && A_TH % A_SEG == 0, "blur: one thread per (column group, row segment)");
 
 __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bufs B) {
   __shared__ uint32_t s_xs[A_RW];    // column taps: s0 | s1 << 16
