@@ -239,6 +239,11 @@ int  orb_synchronize(orb_ctx* ctx);
 /* libm twins used on the device, evaluated on host arrays (test hook): op 0 atan2f(a,b), 1 cosf(a),
  * 2 sinf(a), 3 lround(a) -- the glibc calls of reference src/orb_cpu.cpp:178,217-218,228-232 */
 int  orb_debug_eval_math(orb_ctx* ctx, int op, const float* a, const float* b, int n, float* out);
+/* host logic of the batch pipeline, callable without a GPU: wave boundaries for a batch of n_frames with waves of `wave`
+ * frames (ramp_up: frames staged from the host; ramp_down: results copied back to the host).  Writes up to cap begins
+ * (the last one is n_frames) and returns how many there are. */
+int  orb_debug_wave_schedule(int n_frames, int wave, int ramp_up, int ramp_down, int* begins, int cap);
+
 /* Bounds-check builds (-DORB_BOUNDS_CHECK: every shared / global index of the ORB kernels is checked before use; stands in
  * for compute-sanitizer, which is closed on the B200 pool): *enabled = 1 in such a build, *failures = failed checks since the
  * library was loaded, *first_line = source line (orb_kernels.cuh) of the first one, *kernels_checked = CTAs that ran checks. */

@@ -134,3 +134,28 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("kitti_synth_1241x376_L8_N2000")
+
+
+@pytest.mark.parametrize("n,wave", [(1000, 64), (1000, 128), (256, 14), (64, 4), (64, 2), (7, 64), (256, 64), (255, 64), (1, 1), (5, 1), (0, 8)])
+def test_wave_schedule_host_logic(V, n, wave):
+    """Batch pipeline, host side (csrc/orb_api.cu wave_schedule): every frame in exactly one wave, no wave above the wave
+    size; host-staged batches ramp up (so the kernels start early) and, when results go back to the host, ramp down (so
+    little is left to compute after the last frame has arrived)."""
+    for up in (False, True):
+        for down in (False, True):
+            b = V.orb.wave_schedule(n, wave, up, down)
+            assert b[0] == 0 or n == 0
+            assert b[-1] == n
+            sizes = np.diff(b)
+            assert (sizes > 0).all() and sizes.sum() == n and (sizes <= wave).all()
+            if not up and not down and n:
+                assert (sizes[:-1] == wave).all()
+            if up and n > wave:
+                assert sizes[0] == max(1, wave // 8)
+                k = 1
+                while k < len(sizes) and sizes[k - 1] < wave and sizes[k] <= wave and sizes[k] == 2 * sizes[k - 1]:
+                    k += 1
+                assert sizes[k - 1] >= min(wave, sizes[0] * 2 ** (k - 1))
+            if down and n >= 4 * wave and wave >= 2:
+                assert sizes[-1] <= max(1, wave // 2)
+                assert sizes[-1] <= sizes[-2] or sizes[-2] <= wave // 2

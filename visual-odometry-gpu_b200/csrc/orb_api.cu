@@ -311,6 +311,29 @@ int launch_describe(orb_ctx* ctx, const OrbPlan& P, const Bufs& B, const Describ
   return ORB_OK;
 }
 
+// Wave boundaries of a batch of n_frames: begins[i] .. begins[i + 1] is wave i (begins ends with n_frames).
+// ramp_up (frames staged from the host): the first waves are wave/8, wave/4, wave/2 frames, so that the kernels start while
+// most of the batch is still in flight over PCIe.  ramp_down (results go back to the host): the last waves shrink again
+// (wave/2, wave/4, the rest), so that what is left after the last frame has arrived is the computation and the result
+// copy of a short wave only; batches shorter than four waves keep full waves to the end.
+void wave_schedule(int n_frames, int wave, bool ramp_up, bool ramp_down, std::vector<int>& begins) {
+  begins.clear();
+  wave = std::max(1, wave);
+  int c0 = 0, ramp = (ramp_up && n_frames > wave) ? std::max(1, wave / 8) : wave;
+  int tail = 0;
+  if (ramp_down && n_frames >= 4 * wave) tail = wave / 2 + wave / 4 + wave / 8;
+  while (c0 < n_frames - tail) {
+    begins.push_back(c0);
+    c0 += std::min(std::min(ramp, wave), n_frames - tail - c0);
+    if (ramp < wave) ramp *= 2;
+  }
+  for (int d = wave / 2; tail > 0 && c0 < n_frames; d = std::max(1, d / 2)) {
+    begins.push_back(c0);
+    c0 += std::min(d <= wave / 8 ? n_frames - c0 : d, n_frames - c0);
+  }
+  begins.push_back(std::max(n_frames, 0));
+}
+
 int check_flags(orb_ctx* ctx) {
   CK(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -673,29 +696,12 @@ static int run_batch_body(orb_ctx* ctx, const uint8_t* frames, int frames_on_dev
   int total_quota = 0;
   for (int l = 0; l < P.nlevels; l++) total_quota += P.lv[l].quota;
   const int nwarps = std::min(total_quota, cap);
-  // wave boundaries: full waves of `chunk` frames; when frames are staged from the host the first waves are short
-  // (chunk/8, chunk/4, chunk/2) so that the kernels start while most of the batch is still in flight over PCIe
+  // wave boundaries (wave_schedule): full waves; host-staged batches start with short waves and end with short waves
   std::vector<int> wave_begin;
   {
     int wave = (direct && outputs_on_device) ? ctx->chunk : ctx->chunk_staged;
     if (source && source->preferred_wave(ctx) > 0) wave = std::min(ctx->chunk, source->preferred_wave(ctx));
-    int c0 = 0, ramp = (!direct && n_frames > wave) ? std::max(1, wave / 8) : wave;
-    // ... and (ORB_E2E_RAMP_DOWN) the last waves shrink again (wave/2, wave/4, wave/8): what is left after the last frame
-    // has arrived is the computation and the result copy of the last wave only
-    int tail = 0;
-#if ORB_E2E_RAMP_DOWN
-    if (!direct && !outputs_on_device && !source && n_frames >= 4 * wave) tail = wave / 2 + wave / 4 + wave / 8;
-#endif
-    while (c0 < n_frames - tail) {
-      wave_begin.push_back(c0);
-      c0 += std::min(std::min(ramp, wave), n_frames - tail - c0);
-      if (ramp < wave) ramp *= 2;
-    }
-    for (int d = wave / 2; tail > 0 && c0 < n_frames; d = std::max(1, d / 2)) {
-      wave_begin.push_back(c0);
-      c0 += std::min(d <= wave / 8 ? n_frames - c0 : d, n_frames - c0);
-    }
-    wave_begin.push_back(n_frames);
+    wave_schedule(n_frames, wave, !direct, ORB_E2E_RAMP_DOWN && !direct && !outputs_on_device && !source, wave_begin);
   }
   const int nchunks = (int)wave_begin.size() - 1;
   const bool piped = !direct || !outputs_on_device;
@@ -1063,6 +1069,13 @@ static int match_tc(orb_ctx* ctx, const orb_descriptor* dq, int rows_q, long lon
   CK(cudaGetLastError());
   ctx->launches += same_buffer ? 2 : 3;
   return ORB_OK;
+}
+
+int orb_debug_wave_schedule(int n_frames, int wave, int ramp_up, int ramp_down, int* begins, int cap) {
+  std::vector<int> b;
+  wave_schedule(n_frames, wave, ramp_up != 0, ramp_down != 0, b);
+  for (int i = 0; i < (int)b.size() && i < cap; i++) begins[i] = b[i];
+  return (int)b.size();
 }
 
 int orb_match_knn2(orb_ctx* ctx, const orb_descriptor* query, int nq, const orb_descriptor* train, int nt, int on_device,

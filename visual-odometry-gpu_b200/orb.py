@@ -50,7 +50,7 @@ EXPORTS = [
     "orb_synchronize", "orb_detect_and_compute", "orb_detect_and_compute_batch", "orb_get_level", "orb_level_size",
     "orb_level_quota", "orb_fast_detect", "orb_nms_scores", "orb_conv2d_u8", "orb_gaussian_blur_1d", "orb_harris", "orb_orientations", "orb_brief", "orb_get_side_arrays",
     "orb_get_candidates", "orb_get_harris_weights", "orb_last_launch_count", "orb_set_profiling", "orb_get_stage_ms", "orb_match_knn2", "orb_match_knn2_batch", "orb_ratio_test", "orb_debug_eval_math", "orb_debug_bounds_check", "orb_debug_bounds_selftest", "bit_pattern_31_",
-    "orb_png_info", "orb_png_decode_gray8", "orb_imread_gray8", "orb_detect_and_compute_files", "orb_get_ingested_frame", "orb_debug_inflate", "orb_lk_track", "orb_lk_track_batch", "orb_lk_levels", "orb_lk_get_level",
+    "orb_png_info", "orb_png_decode_gray8", "orb_imread_gray8", "orb_detect_and_compute_files", "orb_get_ingested_frame", "orb_debug_inflate", "orb_lk_track", "orb_lk_track_batch", "orb_lk_levels", "orb_lk_get_level", "orb_debug_wave_schedule",
 ]
 
 _lib = None
@@ -109,11 +109,20 @@ def load_library():
     L.orb_get_ingested_frame.argtypes = [vp, i, vp, sz, C.POINTER(i), C.POINTER(i)]
     L.orb_debug_inflate.argtypes = [vp, vp, vp, i, vp, vp, vp]
     L.orb_lk_track.argtypes = [vp, vp, vp, i, i, sz, vp, i, i, i, i, C.c_double, C.c_float, vp, vp, vp]
+    L.orb_debug_wave_schedule.argtypes = [i, i, i, i, vp, i]
     L.orb_lk_track_batch.argtypes = [vp, vp, i, i, i, i, sz, sz, vp, vp, i, i, i, i, i, C.c_double, C.c_float, vp, vp, vp]
     L.orb_lk_levels.argtypes = [i, i, i, i]
     L.orb_lk_get_level.argtypes = [vp, i, i, vp, C.POINTER(i), C.POINTER(i)]
     _lib = L
     return L
+
+
+def wave_schedule(n_frames, wave, ramp_up, ramp_down):
+    """Wave boundaries the batch pipeline uses (host logic, no GPU needed): list of begins ending with n_frames."""
+    lib = load_library()
+    buf = (C.c_int * (n_frames + 2))()
+    n = lib.orb_debug_wave_schedule(n_frames, wave, int(ramp_up), int(ramp_down), buf, n_frames + 2)
+    return list(buf[:n])
 
 
 def default_params():
