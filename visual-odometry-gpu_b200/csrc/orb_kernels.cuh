@@ -242,10 +242,15 @@ constexpr int A_SEG = ORB_A_SEG;                   // output rows per thread in 
 static_assert((A_TW / 8) * (A_TH / A_SEG) <= A_THREADS && A_TH % A_SEG == 0, "blur: one thread per (column group, row segment)");
 
 __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bufs B) {
-  __shared__ uint32_t s_xs[A_RW];    // column taps: s0 | s1 << 16
-  __shared__ uint32_t s_xa[A_RW];    //              a0 | a1 << 16
-  __shared__ __align__(16) uint4 s_yt[A_RH];   // row taps: byte offsets of the two source rows inside the frame, b0, b1
-  __shared__ __align__(16) uint8_t s_res[A_RH * A_RP];
+  // [horizontal blur sums, 16 bytes per (row, 8-pixel group) -- the tap tables live in their first 2 KB until the resize is
+  // over][resized rows]: 26.7 KB, still eight CTAs per SM
+  __shared__ __align__(16) uint8_t s_all[A_RH * (A_TW / 8) * 16 + A_RH * A_RP];
+  uint4* s_hs = (uint4*)s_all;
+  uint32_t* s_xs = (uint32_t*)s_all;             // column taps: s0 | s1 << 16
+  uint32_t* s_xa = s_xs + A_RW;                  //              a0 | a1 << 16
+  uint4* s_yt = (uint4*)(s_all + 2 * A_RW * 4);  // row taps: byte offsets of the two source rows inside the frame, b0, b1
+  uint8_t* s_res = s_all + A_RH * (A_TW / 8) * 16;
+  static_assert((2 * A_RW * 4) % 16 == 0 && 2 * A_RW * 4 + A_RH * 16 <= A_RH * (A_TW / 8) * 16, "tap tables inside the hs area");
   const int tid = threadIdx.x, f = blockIdx.y;
   const uint32_t tt = __ldg(B.tile_a + blockIdx.x);
   const int l = tt & 15;
@@ -355,34 +360,42 @@ __global__ void __launch_bounds__(A_THREADS) k_pyramid(const OrbPlan P, const Bu
     return;
   }
 
-  // [1 4 6 4 1] x [1 4 6 4 1] through registers: a thread owns an 8-pixel column group and A_SEG output rows.  The
-  // horizontal sums of its A_SEG + 4 resized rows are computed once each (16-bit lanes holding pixels two apart:
-  // (o0,o2) (o1,o3) (o4,o6) (o5,o7)) and kept in a five-row register window; the vertical pass reads only registers.
-  // One rounding: (sum + 128) >> 8  (cv::GaussianBlur 5x5 sigma 0 on u8).
+  // [1 4 6 4 1] x [1 4 6 4 1] in two steps.  (1) The horizontal sums of every resized row are computed once (a thread takes
+  // (row, 8-pixel group) items; 16-bit lanes holding pixels two apart: (o0,o2) (o1,o3) (o4,o6) (o5,o7)) and stored to shared
+  // memory.  (2) A thread owns a column group and A_SEG output rows and walks down the A_SEG + 4 rows of sums with a
+  // five-row register window.  One rounding: (sum + 128) >> 8  (cv::GaussianBlur 5x5 sigma 0 on u8).
+  {
+    const uint32_t M = 0x00ff00ffu;
+    for (int it = tid; it < A_RH * (A_TW / 8); it += A_THREADS) {
+      const int g = it & (A_TW / 8 - 1), row = it / (A_TW / 8);
+      const uint8_t* r = s_res + row * A_RP + 8 * g;
+      const uint2 w01 = *(const uint2*)r;
+      const uint32_t w2 = *(const uint32_t*)(r + 8);
+      const uint32_t v1 = prmt(w01.x, w01.y, 0x5432), v2 = prmt(w01.y, w2, 0x5432);
+      const uint32_t q0 = w01.x & M, q1 = odd_bytes(w01.x), q2 = v1 & M, q3 = odd_bytes(v1), q4 = w01.y & M,
+                     q5 = odd_bytes(w01.y), q6 = v2 & M, q7 = odd_bytes(v2), q8 = w2 & M, q9 = odd_bytes(w2);
+      uint4 o;
+      o.x = q0 + q4 + 4 * (q1 + q3) + 6 * q2;
+      o.y = q1 + q5 + 4 * (q2 + q4) + 6 * q3;
+      o.z = q4 + q8 + 4 * (q5 + q7) + 6 * q6;
+      o.w = q5 + q9 + 4 * (q6 + q8) + 6 * q7;
+      s_hs[it] = o;
+    }
+  }
+  __syncthreads();
   if (tid < (A_TW / 8) * (A_TH / A_SEG)) {
     const int g = tid & (A_TW / 8 - 1), oy0 = (tid / (A_TW / 8)) * A_SEG;
     if (y0 + oy0 < h && x0 + 8 * g < G.pitch) {
-      const uint32_t M = 0x00ff00ffu, R = 0x00800080u;
-      const uint8_t* r = s_res + oy0 * A_RP + 8 * g;
+      const uint32_t R = 0x00800080u;
       uint8_t* d = dst + (size_t)(y0 + oy0) * G.pitch + x0 + 8 * g;
-      ORB_CHECK(oy0 + A_SEG + 4 <= A_RH && 8 * g + 12 <= A_RP);
+      ORB_CHECK(oy0 + A_SEG + 4 <= A_RH);
       ORB_CHECK_RANGE(d, 8, dst, (size_t)G.h * G.pitch);                // (later rows of the segment are guarded by y < h)
       uint4 hs[5];
 #pragma unroll
       for (int k = 0; k < A_SEG + 4; k++) {
-        const uint2 w01 = *(const uint2*)r;
-        const uint32_t w2 = *(const uint32_t*)(r + 8);
-        r += A_RP;
-        const uint32_t v1 = prmt(w01.x, w01.y, 0x5432), v2 = prmt(w01.y, w2, 0x5432);
-        const uint32_t q0 = w01.x & M, q1 = odd_bytes(w01.x), q2 = v1 & M, q3 = odd_bytes(v1), q4 = w01.y & M,
-                       q5 = odd_bytes(w01.y), q6 = v2 & M, q7 = odd_bytes(v2), q8 = w2 & M, q9 = odd_bytes(w2);
-        uint4 o;
-        o.x = q0 + q4 + 4 * (q1 + q3) + 6 * q2;
-        o.y = q1 + q5 + 4 * (q2 + q4) + 6 * q3;
-        o.z = q4 + q8 + 4 * (q5 + q7) + 6 * q6;
-        o.w = q5 + q9 + 4 * (q6 + q8) + 6 * q7;
+        const uint4 o = s_hs[(oy0 + k) * (A_TW / 8) + g];
         hs[k % 5] = o;
-        if (k >= 4 && y0 + oy0 + k - 4 < h) {      // output row oy0 + k - 4 from resized rows k-4 .. k of this thread
+        if (k >= 4 && y0 + oy0 + k - 4 < h) {      // output row oy0 + k - 4 from resized rows k-4 .. k
           const uint4 &m2 = hs[(k + 1) % 5], &m1 = hs[(k + 2) % 5], &c0 = hs[(k + 3) % 5], &p1 = hs[(k + 4) % 5];
           const uint32_t a = m2.x + o.x + 4 * (m1.x + p1.x) + 6 * c0.x + R;
           const uint32_t b = m2.y + o.y + 4 * (m1.y + p1.y) + 6 * c0.y + R;
